@@ -1,0 +1,54 @@
+// C-ABI plumbing: error string, version, struct sizes, device properties.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void rs_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *rs_last_error(void) { return g_err; }
+extern "C" int rs_abi_version(void) { return RS_ABI_VERSION; }
+
+extern "C" uint64_t rs_sizeof_args(int which) {
+    switch (which) {
+    case 0:
+        return sizeof(rs_project_fwd_args);
+    case 1:
+        return sizeof(rs_project_bwd_args);
+    case 2:
+        return sizeof(rs_isect_args);
+    case 3:
+        return sizeof(rs_sort_args);
+    case 4:
+        return sizeof(rs_raster_fwd_args);
+    case 5:
+        return sizeof(rs_raster_bwd_args);
+    case 6:
+        return sizeof(rs_frame_args);
+    case 7:
+        return sizeof(rs_rigid_t);
+    default:
+        return 0;
+    }
+}
+
+int rs_num_sms() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64)
+        return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}

@@ -1,0 +1,111 @@
+// Shared device/host helpers for librigidsplat (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/rigidsplat.h"
+
+#define RS_ALPHA_THRESHOLD (1.f / 255.f) // gsplat/cuda/include/Common.h:54
+#define RS_TILE 16                       // the only tile size the reference exercises (rendering.py:184-185)
+
+// elements (image x gaussian pairs) covered by one CTA of the projection / tile-count / key-emission kernels;
+// also the granularity of `block_sums`.
+#define RS_ISECT_BLOCK 1024
+#define RS_ISECT_THREADS 256
+
+void rs_set_error(const char *fmt, ...);
+
+#define RS_CHECK(cond, ...)                                                                                            \
+    do {                                                                                                               \
+        if (!(cond)) {                                                                                                 \
+            rs_set_error(__VA_ARGS__);                                                                                 \
+            return 1;                                                                                                  \
+        }                                                                                                              \
+    } while (0)
+
+#define RS_CUDA(call)                                                                                                  \
+    do {                                                                                                               \
+        cudaError_t err__ = (call);                                                                                    \
+        if (err__ != cudaSuccess) {                                                                                    \
+            rs_set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(err__));             \
+            return 2;                                                                                                  \
+        }                                                                                                              \
+    } while (0)
+
+#define RS_LAUNCH_CHECK(name)                                                                                          \
+    do {                                                                                                               \
+        cudaError_t err__ = cudaGetLastError();                                                                        \
+        if (err__ != cudaSuccess) {                                                                                    \
+            rs_set_error("launch of %s failed: %s", name, cudaGetErrorString(err__));                                  \
+            return 3;                                                                                                  \
+        }                                                                                                              \
+    } while (0)
+
+static inline int rs_cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// bit width helpers matching `(uint32_t)floor(log2(x)) + 1` of csrc/Intersect.cpp:50-51
+static inline __host__ __device__ uint32_t rs_bit_width(uint32_t x) {
+    uint32_t n = 0;
+    while (x) {
+        ++n;
+        x >>= 1;
+    }
+    return n;
+}
+
+// number of SMs of the current device (cached)
+int rs_num_sms();
+
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned rs_lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// Tile rectangle of one projected Gaussian: csrc/IntersectTile.cu:55-84.
+// tile_min inclusive, tile_max exclusive; float->uint conversion saturates negatives to 0 exactly like the reference's
+// `(uint32_t)floor(...)`.
+struct RsTileRect {
+    uint32_t x0, y0, x1, y1;
+};
+__device__ __forceinline__ RsTileRect rs_tile_rect(float mx, float my, float rx, float ry, uint32_t tile_size,
+                                                   uint32_t tile_width, uint32_t tile_height) {
+    float ts = static_cast<float>(tile_size);
+    float tile_radius_x = rx / ts;
+    float tile_radius_y = ry / ts;
+    float tile_x = mx / ts;
+    float tile_y = my / ts;
+    RsTileRect r;
+    r.x0 = min((uint32_t)floorf(tile_x - tile_radius_x), tile_width);
+    r.y0 = min((uint32_t)floorf(tile_y - tile_radius_y), tile_height);
+    r.x1 = min((uint32_t)ceilf(tile_x + tile_radius_x), tile_width);
+    r.y1 = min((uint32_t)ceilf(tile_y + tile_radius_y), tile_height);
+    return r;
+}
+__device__ __forceinline__ int32_t rs_tile_count(int32_t radius_x, int32_t radius_y, float mx, float my,
+                                                 uint32_t tile_size, uint32_t tile_width, uint32_t tile_height) {
+    if (radius_x <= 0 || radius_y <= 0)
+        return 0;
+    RsTileRect r = rs_tile_rect(mx, my, (float)radius_x, (float)radius_y, tile_size, tile_width, tile_height);
+    return (int32_t)((r.y1 - r.y0) * (r.x1 - r.x0));
+}
+
+// block-wide sum of one int per thread (blockDim.x == RS_ISECT_THREADS), result valid in thread 0
+__device__ __forceinline__ int rs_block_sum_256(int v, int *smem8) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0)
+        smem8[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int s = 0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 0; w < RS_ISECT_THREADS / 32; ++w)
+            s += smem8[w];
+    }
+    return s;
+}
+#endif

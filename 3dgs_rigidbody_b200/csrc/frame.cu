@@ -1,0 +1,188 @@
+// rs_render_frame: animate -> project -> tile-sort -> composite for one frame, no host synchronisation.
+// This is what one iteration of the (commented-out) animation loop of main.py:357-409 does through
+// apply_transform() + rasterization() (rendering.py:33-770, packed=False, sh_degree=None), minus the per-body tensor
+// clones, the torch glue kernels and the `.item()` sync of csrc/Intersect.cpp:80.
+#include <string.h>
+
+#include "common.cuh"
+
+int rs_sort_pairs_u64_internal(int64_t n_bound, const int32_t *n_dev, int begin_bit, int end_bit, uint64_t *keys_a,
+                               uint64_t *keys_b, int32_t *vals_a, int32_t *vals_b, void *workspace,
+                               uint64_t workspace_bytes, int32_t *result_in_b, cudaStream_t s);
+
+namespace {
+struct FrameLayout {
+    size_t radii, means2d, depths, conics, tiles_per_gauss, block_sums, keys_a, keys_b, vals_a, vals_b, sort_ws,
+        sort_ws_bytes, tile_offsets, last_ids, total;
+};
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+FrameLayout make_layout(int32_t C, int32_t N, int32_t W, int32_t H, int32_t tile_size, int64_t max_isects) {
+    FrameLayout L;
+    const size_t E = (size_t)C * N;
+    const size_t tw = (W + tile_size - 1) / tile_size, th = (H + tile_size - 1) / tile_size;
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        size_t at = o;
+        o = align256(o + bytes);
+        return at;
+    };
+    L.radii = take(E * 2 * 4);
+    L.means2d = take(E * 2 * 4);
+    L.depths = take(E * 4);
+    L.conics = take(E * 3 * 4);
+    L.tiles_per_gauss = take(E * 4);
+    L.block_sums = take(((size_t)rs_isect_num_blocks((int64_t)E) + 1) * 4);
+    L.keys_a = take((size_t)max_isects * 8);
+    L.keys_b = take((size_t)max_isects * 8);
+    L.vals_a = take((size_t)max_isects * 4);
+    L.vals_b = take((size_t)max_isects * 4);
+    L.sort_ws_bytes = rs_radix_sort_workspace_bytes(max_isects);
+    L.sort_ws = take(L.sort_ws_bytes);
+    L.tile_offsets = take((size_t)C * tw * th * 4);
+    L.last_ids = take((size_t)C * W * H * 4);
+    L.total = o;
+    return L;
+}
+} // namespace
+
+extern "C" uint64_t rs_frame_workspace_bytes(int32_t C, int32_t N, int32_t image_width, int32_t image_height,
+                                             int32_t tile_size, int32_t channels, int64_t max_isects) {
+    (void)channels;
+    if (C <= 0 || N < 0 || image_width <= 0 || image_height <= 0 || tile_size <= 0 || max_isects < 0)
+        return 0;
+    return make_layout(C, N, image_width, image_height, tile_size, max_isects).total;
+}
+
+static int frame_end_bit(const rs_frame_args *a) {
+    const rs_project_fwd_args &p = a->proj;
+    const int tw = (p.image_width + p.tile_size - 1) / p.tile_size, th = (p.image_height + p.tile_size - 1) / p.tile_size;
+    return 32 + (int)rs_bit_width((uint32_t)(tw * th)) + (int)rs_bit_width((uint32_t)p.C);
+}
+
+extern "C" void *rs_frame_workspace_ptr(const rs_frame_args *a, int which) {
+    if (a == nullptr || a->workspace == nullptr)
+        return nullptr;
+    const rs_project_fwd_args &p = a->proj;
+    const FrameLayout L = make_layout(p.C, p.N, p.image_width, p.image_height, p.tile_size, a->max_isects);
+    char *w = reinterpret_cast<char *>(a->workspace);
+    const int passes = (frame_end_bit(a) + 7) / 8;
+    const bool in_b = passes & 1;
+    switch (which) {
+    case 0:
+        return w + (in_b ? L.keys_b : L.keys_a);
+    case 1:
+        return w + (in_b ? L.vals_b : L.vals_a);
+    case 2:
+        return w + L.tile_offsets;
+    case 3:
+        return w + L.last_ids;
+    case 4:
+        return w + L.tiles_per_gauss;
+    case 5:
+        return w + L.radii;
+    case 6:
+        return w + L.means2d;
+    case 7:
+        return w + L.depths;
+    case 8:
+        return w + L.conics;
+    default:
+        return nullptr;
+    }
+}
+
+extern "C" int rs_render_frame(const rs_frame_args *a, rs_stream_t stream) {
+    RS_CHECK(a != nullptr, "rs_render_frame: null args");
+    rs_project_fwd_args p = a->proj;
+    RS_CHECK(p.B == 1, "rs_render_frame: B must be 1");
+    RS_CHECK(p.C >= 1 && p.N >= 0, "rs_render_frame: bad sizes");
+    RS_CHECK(p.tile_size == RS_TILE, "rs_render_frame: tile_size must be 16");
+    RS_CHECK(a->channels >= 1 && a->channels <= RS_MAX_CHANNELS, "rs_render_frame: Unsupported number of color channels: %d",
+             a->channels);
+    RS_CHECK(a->colors && a->render_colors && a->render_alphas && a->status && a->workspace,
+             "rs_render_frame: null pointer");
+    RS_CHECK(p.opacities != nullptr, "rs_render_frame: opacities required");
+    RS_CHECK(p.compensations == nullptr, "rs_render_frame: antialiased mode is not available on the fused path");
+    RS_CHECK(a->max_isects > 0 && a->max_isects < ((int64_t)1 << 31), "rs_render_frame: bad max_isects");
+    p.tile_width = (p.image_width + p.tile_size - 1) / p.tile_size;
+    p.tile_height = (p.image_height + p.tile_size - 1) / p.tile_size;
+    const FrameLayout L = make_layout(p.C, p.N, p.image_width, p.image_height, p.tile_size, a->max_isects);
+    RS_CHECK(a->workspace_bytes >= L.total, "rs_render_frame: workspace too small (%llu < %llu)",
+             (unsigned long long)a->workspace_bytes, (unsigned long long)L.total);
+    char *w = reinterpret_cast<char *>(a->workspace);
+    cudaStream_t s = (cudaStream_t)stream;
+
+    p.radii = reinterpret_cast<int32_t *>(w + L.radii);
+    p.means2d = reinterpret_cast<float *>(w + L.means2d);
+    p.depths = reinterpret_cast<float *>(w + L.depths);
+    p.conics = reinterpret_cast<float *>(w + L.conics);
+    p.tiles_per_gauss = reinterpret_cast<int32_t *>(w + L.tiles_per_gauss);
+    p.block_sums = reinterpret_cast<int32_t *>(w + L.block_sums);
+    if (int e = rs_project_fwd(&p, stream))
+        return e;
+
+    rs_isect_args ia;
+    memset(&ia, 0, sizeof(ia));
+    ia.n_elems = p.C * p.N;
+    ia.N = p.N;
+    ia.I = p.C;
+    ia.tile_size = p.tile_size;
+    ia.tile_width = p.tile_width;
+    ia.tile_height = p.tile_height;
+    ia.means2d = p.means2d;
+    ia.radii = p.radii;
+    ia.depths = p.depths;
+    ia.tiles_per_gauss = p.tiles_per_gauss;
+    ia.block_sums = p.block_sums;
+    ia.n_isects = a->status;      // status[0]
+    ia.overflow = a->status + 1;  // status[1]
+    ia.isect_ids = reinterpret_cast<int64_t *>(w + L.keys_a);
+    ia.flatten_ids = reinterpret_cast<int32_t *>(w + L.vals_a);
+    ia.capacity = a->max_isects;
+    if (int e = rs_isect_scan(&ia, stream))
+        return e;
+    if (int e = rs_isect_emit(&ia, stream))
+        return e;
+
+    int32_t in_b = 0;
+    if (int e = rs_sort_pairs_u64_internal(a->max_isects, a->status, 0, frame_end_bit(a),
+                                           reinterpret_cast<uint64_t *>(w + L.keys_a),
+                                           reinterpret_cast<uint64_t *>(w + L.keys_b),
+                                           reinterpret_cast<int32_t *>(w + L.vals_a),
+                                           reinterpret_cast<int32_t *>(w + L.vals_b), w + L.sort_ws, L.sort_ws_bytes,
+                                           &in_b, s))
+        return e;
+    const int64_t *keys_sorted = reinterpret_cast<const int64_t *>(w + (in_b ? L.keys_b : L.keys_a));
+    const int32_t *vals_sorted = reinterpret_cast<const int32_t *>(w + (in_b ? L.vals_b : L.vals_a));
+    int32_t *offsets = a->out_tile_offsets != nullptr ? a->out_tile_offsets : reinterpret_cast<int32_t *>(w + L.tile_offsets);
+    if (int e = rs_isect_offsets(keys_sorted, a->max_isects, a->status, p.C, p.tile_width, p.tile_height, offsets, stream))
+        return e;
+
+    rs_raster_fwd_args r;
+    memset(&r, 0, sizeof(r));
+    r.I = p.C;
+    r.N = p.N;
+    r.channels = a->channels;
+    r.image_width = p.image_width;
+    r.image_height = p.image_height;
+    r.tile_size = p.tile_size;
+    r.tile_width = p.tile_width;
+    r.tile_height = p.tile_height;
+    r.n_isects = a->max_isects;
+    r.n_isects_dev = a->status;
+    r.means2d = p.means2d;
+    r.conics = p.conics;
+    r.colors = a->colors;
+    r.opacities = p.opacities;
+    r.attr_mod_colors = a->colors_per_camera ? 0 : p.N;
+    r.attr_mod_opacities = p.N;
+    r.backgrounds = a->backgrounds;
+    r.masks = nullptr;
+    r.tile_offsets = offsets;
+    r.flatten_ids = vals_sorted;
+    r.render_colors = a->render_colors;
+    r.render_alphas = a->render_alphas;
+    r.last_ids = reinterpret_cast<int32_t *>(w + L.last_ids);
+    return rs_raster_fwd(&r, stream);
+}

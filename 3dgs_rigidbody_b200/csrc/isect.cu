@@ -1,0 +1,298 @@
+// Tile intersection: count, scan, key emission, offsets.
+// Replaces csrc/Intersect.cpp:15-168 + csrc/IntersectTile.cu:23-292 (the cub sort is in sort.cu).
+//
+// The reference runs the per-Gaussian kernel twice around an `at::cumsum` + `.item()` host sync and lets ONE thread
+// write all tiles of a Gaussian (serial double loop, IntersectTile.cu:102-113).  Here:
+//   count  : 1 thread / element, writes tiles_per_gauss and one partial sum per 1024-element block
+//   scan   : one CTA turns the block sums into exclusive offsets and the device-side total (no host sync needed)
+//   emit   : a CTA re-scans its 1024 counts in shared memory and its 256 threads write the block's intersections
+//            cooperatively: output slot j finds its owner by binary search, so stores are fully coalesced and a
+//            Gaussian that covers thousands of tiles is spread over the whole CTA.
+// All of it is HBM-bound integer work: 20 B read per element + 12 B written per intersection.
+#include "common.cuh"
+
+extern "C" int32_t rs_isect_num_blocks(int64_t n_elems) { return (int32_t)((n_elems + RS_ISECT_BLOCK - 1) / RS_ISECT_BLOCK); }
+
+__global__ void __launch_bounds__(RS_ISECT_THREADS) rs_isect_count_kernel(const rs_isect_args a) {
+    __shared__ int sums[8];
+    const int64_t base = (int64_t)blockIdx.x * RS_ISECT_BLOCK;
+    int mine = 0;
+#pragma unroll
+    for (int it = 0; it < RS_ISECT_BLOCK / RS_ISECT_THREADS; ++it) {
+        const int64_t idx = base + it * RS_ISECT_THREADS + threadIdx.x;
+        if (idx < a.n_elems) {
+            const int2 r = reinterpret_cast<const int2 *>(a.radii)[idx];
+            int cnt = 0;
+            if (r.x > 0 && r.y > 0) {
+                const float2 m = reinterpret_cast<const float2 *>(a.means2d)[idx];
+                cnt = rs_tile_count(r.x, r.y, m.x, m.y, (uint32_t)a.tile_size, (uint32_t)a.tile_width,
+                                    (uint32_t)a.tile_height);
+            }
+            a.tiles_per_gauss[idx] = cnt;
+            mine += cnt;
+        }
+    }
+    int s = rs_block_sum_256(mine, sums);
+    if (threadIdx.x == 0)
+        a.block_sums[blockIdx.x] = s;
+}
+
+// Exclusive scan of `nb` block sums (in place) by a single CTA; block_sums[nb] and *n_isects receive the total.
+// nb is small (1M elements -> 977 blocks), so a serial-over-chunks CTA scan is launch-latency bound.
+#define RS_SCAN_THREADS 1024
+__global__ void __launch_bounds__(RS_SCAN_THREADS)
+rs_isect_scan_kernel(int32_t *block_sums, int nb, int32_t *n_isects, int64_t capacity, int32_t *overflow) {
+    __shared__ long long warp_tot[32];
+    __shared__ long long carry_s;
+    if (threadIdx.x == 0)
+        carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int start = 0; start < nb; start += RS_SCAN_THREADS) {
+        const int i = start + threadIdx.x;
+        long long v = (i < nb) ? block_sums[i] : 0;
+        long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            long long n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o)
+                incl += n;
+        }
+        if (lane == 31)
+            warp_tot[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            long long w = warp_tot[lane];
+            long long wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                long long n = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o)
+                    wi += n;
+            }
+            warp_tot[lane] = wi - w; // exclusive prefix of warp totals
+        }
+        __syncthreads();
+        const long long carry = carry_s;
+        const long long excl = carry + warp_tot[warp] + incl - v;
+        if (i < nb)
+            block_sums[i] = (int32_t)min(excl, (long long)INT32_MAX);
+        __syncthreads();
+        if (threadIdx.x == RS_SCAN_THREADS - 1)
+            carry_s = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const long long total = carry_s;
+        block_sums[nb] = (int32_t)min(total, (long long)INT32_MAX);
+        if (n_isects != nullptr)
+            *n_isects = (int32_t)min(total, (long long)INT32_MAX);
+        if (overflow != nullptr)
+            *overflow = (total > capacity || total > (long long)INT32_MAX) ? 1 : 0;
+    }
+}
+
+struct EmitSmem {
+    int32_t excl[RS_ISECT_BLOCK + 1]; // exclusive scan of this block's tile counts
+    uint32_t rect[RS_ISECT_BLOCK];    // x0 | y0 << 16
+    uint32_t width[RS_ISECT_BLOCK];   // x1 - x0
+    uint32_t depth[RS_ISECT_BLOCK];   // raw float bits
+    int32_t warp_tot[8];
+};
+
+__global__ void __launch_bounds__(RS_ISECT_THREADS) rs_isect_emit_kernel(const rs_isect_args a, uint32_t tile_n_bits) {
+    __shared__ EmitSmem sm;
+    const int64_t base = (int64_t)blockIdx.x * RS_ISECT_BLOCK;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // each thread owns 4 CONSECUTIVE elements (blocked arrangement) so the scan is a per-thread serial prefix
+    // followed by one CTA scan of 256 thread totals.
+    int cnt[4];
+    int tsum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int e = threadIdx.x * 4 + k;
+        const int64_t idx = base + e;
+        int c = 0;
+        if (idx < a.n_elems) {
+            c = a.tiles_per_gauss[idx];
+            if (c > 0) {
+                const int2 r = reinterpret_cast<const int2 *>(a.radii)[idx];
+                const float2 m = reinterpret_cast<const float2 *>(a.means2d)[idx];
+                const RsTileRect tr = rs_tile_rect(m.x, m.y, (float)r.x, (float)r.y, (uint32_t)a.tile_size,
+                                                   (uint32_t)a.tile_width, (uint32_t)a.tile_height);
+                sm.rect[e] = tr.x0 | (tr.y0 << 16);
+                sm.width[e] = tr.x1 - tr.x0;
+                sm.depth[e] = __float_as_uint(a.depths[idx]);
+            }
+        }
+        cnt[k] = c;
+        tsum += c;
+    }
+    int incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o)
+            incl += n;
+    }
+    if (lane == 31)
+        sm.warp_tot[warp] = incl;
+    __syncthreads();
+    int wbase = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w)
+        wbase += (w < warp) ? sm.warp_tot[w] : 0;
+    int run = wbase + incl - tsum;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        sm.excl[threadIdx.x * 4 + k] = run;
+        run += cnt[k];
+    }
+    if (threadIdx.x == RS_ISECT_THREADS - 1)
+        sm.excl[RS_ISECT_BLOCK] = run;
+    __syncthreads();
+
+    const int total = sm.excl[RS_ISECT_BLOCK];
+    const int64_t out_base = a.block_sums[blockIdx.x]; // exclusive offset of this block (after rs_isect_scan)
+    for (int j = threadIdx.x; j < total; j += RS_ISECT_THREADS) {
+        // largest e with excl[e] <= j   (counts of zero are skipped automatically)
+        int lo = 0, hi = RS_ISECT_BLOCK;
+#pragma unroll
+        for (int step = 0; step < 10; ++step) { // log2(1024)
+            const int mid = (lo + hi) >> 1;
+            if (sm.excl[mid] <= j)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const int e = lo;
+        const uint32_t r = (uint32_t)(j - sm.excl[e]);
+        const uint32_t w = sm.width[e];
+        const uint32_t ty = (sm.rect[e] >> 16) + r / w;
+        const uint32_t tx = (sm.rect[e] & 0xffffu) + r % w;
+        const int64_t idx = base + e;
+        const int64_t iid = (a.image_ids != nullptr) ? a.image_ids[idx] : (idx / a.N);
+        const int64_t tile_id = (int64_t)ty * a.tile_width + tx;
+        const int64_t key = (iid << (32 + tile_n_bits)) | (tile_id << 32) | (int64_t)sm.depth[e];
+        const int64_t o = out_base + j;
+        if (o < a.capacity) {
+            a.isect_ids[o] = key;
+            a.flatten_ids[o] = (int32_t)idx;
+        }
+    }
+}
+
+// csrc/IntersectTile.cu:209-257
+__global__ void __launch_bounds__(256)
+rs_isect_offsets_kernel(const int64_t *__restrict__ isect_ids, int64_t n_bound, const int32_t *__restrict__ n_dev,
+                        uint32_t I, uint32_t n_tiles, uint32_t tile_n_bits, int32_t *__restrict__ offsets) {
+    const int64_t n_isects = (n_dev != nullptr) ? min((int64_t)*n_dev, n_bound) : n_bound;
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (n_isects == 0) { // Intersect.cpp:273-276: offsets.fill_(0)
+        for (int64_t i = idx; i < (int64_t)I * n_tiles; i += (int64_t)gridDim.x * blockDim.x)
+            offsets[i] = 0;
+        return;
+    }
+    if (idx >= n_isects)
+        return;
+    const int64_t cur = isect_ids[idx] >> 32;
+    const int64_t id_curr = (cur >> tile_n_bits) * n_tiles + (cur & ((1ll << tile_n_bits) - 1));
+    if (idx == 0) {
+        for (int64_t i = 0; i < id_curr + 1; ++i)
+            offsets[i] = 0;
+    }
+    if (idx == n_isects - 1) {
+        for (int64_t i = id_curr + 1; i < (int64_t)I * n_tiles; ++i)
+            offsets[i] = (int32_t)n_isects;
+    }
+    if (idx > 0) {
+        const int64_t prev = isect_ids[idx - 1] >> 32;
+        if (prev == cur)
+            return;
+        const int64_t id_prev = (prev >> tile_n_bits) * n_tiles + (prev & ((1ll << tile_n_bits) - 1));
+        for (int64_t i = id_prev + 1; i < id_curr + 1; ++i)
+            offsets[i] = (int32_t)idx;
+    }
+}
+
+static int check_isect_args(const rs_isect_args *a, const char *who) {
+    RS_CHECK(a != nullptr, "%s: null args", who);
+    RS_CHECK(a->n_elems >= 0 && a->I >= 0, "%s: negative sizes", who);
+    RS_CHECK(a->tile_size > 0 && a->tile_width > 0 && a->tile_height > 0, "%s: bad tile geometry", who);
+    RS_CHECK(a->tile_width < 65536 && a->tile_height < 65536, "%s: tile grid too large", who);
+    // Intersect.cpp:50-54: image and tile ids share the upper 32 key bits
+    RS_CHECK(rs_bit_width((uint32_t)a->I) + rs_bit_width((uint32_t)(a->tile_width * a->tile_height)) <= 32,
+             "%s: image_n_bits + tile_n_bits > 32", who);
+    return 0;
+}
+
+extern "C" int rs_isect_count(const rs_isect_args *a, rs_stream_t stream) {
+    if (int e = check_isect_args(a, "rs_isect_count"))
+        return e;
+    if (a->n_elems == 0)
+        return 0;
+    RS_CHECK(a->means2d && a->radii && a->tiles_per_gauss && a->block_sums, "rs_isect_count: null pointer");
+    rs_isect_count_kernel<<<rs_isect_num_blocks(a->n_elems), RS_ISECT_THREADS, 0, (cudaStream_t)stream>>>(*a);
+    RS_LAUNCH_CHECK("rs_isect_count_kernel");
+    return 0;
+}
+
+extern "C" int rs_isect_scan(const rs_isect_args *a, rs_stream_t stream) {
+    if (int e = check_isect_args(a, "rs_isect_scan"))
+        return e;
+    RS_CHECK(a->block_sums && a->n_isects, "rs_isect_scan: null pointer");
+    rs_isect_scan_kernel<<<1, RS_SCAN_THREADS, 0, (cudaStream_t)stream>>>(
+        a->block_sums, rs_isect_num_blocks(a->n_elems), a->n_isects, a->capacity > 0 ? a->capacity : INT64_MAX,
+        a->overflow);
+    RS_LAUNCH_CHECK("rs_isect_scan_kernel");
+    return 0;
+}
+
+extern "C" int rs_isect_count_total(const rs_isect_args *a, rs_stream_t stream, int64_t *n_isects_host) {
+    RS_CHECK(a && a->n_isects && n_isects_host, "rs_isect_count_total: null pointer");
+    int32_t h = 0;
+    RS_CUDA(cudaMemcpyAsync(&h, a->n_isects, sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    RS_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    RS_CHECK(h != INT32_MAX, "rs_isect_count_total: more than 2^31-1 tile intersections");
+    *n_isects_host = h;
+    return 0;
+}
+
+extern "C" int rs_isect_emit(const rs_isect_args *a, rs_stream_t stream) {
+    if (int e = check_isect_args(a, "rs_isect_emit"))
+        return e;
+    if (a->n_elems == 0)
+        return 0;
+    RS_CHECK(a->means2d && a->radii && a->depths && a->tiles_per_gauss && a->block_sums && a->isect_ids &&
+                 a->flatten_ids,
+             "rs_isect_emit: null pointer");
+    RS_CHECK(a->image_ids != nullptr || a->N > 0, "rs_isect_emit: N required when not packed");
+    const uint32_t tile_n_bits = rs_bit_width((uint32_t)(a->tile_width * a->tile_height));
+    rs_isect_emit_kernel<<<rs_isect_num_blocks(a->n_elems), RS_ISECT_THREADS, 0, (cudaStream_t)stream>>>(*a,
+                                                                                                          tile_n_bits);
+    RS_LAUNCH_CHECK("rs_isect_emit_kernel");
+    return 0;
+}
+
+extern "C" int rs_isect_offsets(const int64_t *isect_ids_sorted, int64_t n_isects, const int32_t *n_isects_dev,
+                                int32_t I, int32_t tile_width, int32_t tile_height, int32_t *offsets,
+                                rs_stream_t stream) {
+    RS_CHECK(offsets != nullptr, "rs_isect_offsets: null offsets");
+    RS_CHECK(I >= 0 && tile_width > 0 && tile_height > 0, "rs_isect_offsets: bad geometry");
+    if ((int64_t)I * tile_width * tile_height == 0)
+        return 0;
+    RS_CHECK(n_isects == 0 || isect_ids_sorted != nullptr, "rs_isect_offsets: null isect_ids");
+    const uint32_t n_tiles = (uint32_t)(tile_width * tile_height);
+    const uint32_t tile_n_bits = rs_bit_width(n_tiles);
+    int64_t grid = (n_isects + 255) / 256;
+    if (grid < 1)
+        grid = 1;
+    // a device-side count of zero needs enough threads to clear the table
+    if (n_isects_dev != nullptr)
+        grid = max(grid, (int64_t)rs_num_sms());
+    rs_isect_offsets_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(isect_ids_sorted, n_isects, n_isects_dev,
+                                                                             (uint32_t)I, n_tiles, tile_n_bits, offsets);
+    RS_LAUNCH_CHECK("rs_isect_offsets_kernel");
+    return 0;
+}

@@ -1,0 +1,457 @@
+// rs_project_bwd: VJP of (rigid transform + fused EWA projection).
+// Replaces csrc/ProjectionEWA3DGSFused.cu:293-531 (host side csrc/Projection.cpp:191-281); VJP pieces follow
+// gsplat/cuda/include/Utils.cuh: inverse_vjp 373-378, add_blur_vjp 390-423, persp_proj_vjp 539-616, ortho 454-489,
+// fisheye 657-747, posW2C_VJP 30-48, covarW2C_VJP 59-80, quat_scale_to_covar_vjp 224-261, quat_to_rotmat_vjp 166-189.
+// The rigid transform is chained in: v_mean = R_k^T v_mean', v_quat = conj(q_k) (x) v_quat', v_Sigma = R_k^T v_Sigma' R_k.
+//
+// Same CTA shape as the forward kernel (1024 elements per CTA, pose table in shared memory).  Gradients are
+// accumulated with red.global: one per component per visible (camera, gaussian) pair; with a single camera every
+// address is touched once, so these are uncontended.
+#include "project_math.cuh"
+
+__device__ __forceinline__ void mm2(const float A[4], const float B[4], float C[4]) {
+    C[0] = A[0] * B[0] + A[1] * B[2];
+    C[1] = A[0] * B[1] + A[1] * B[3];
+    C[2] = A[2] * B[0] + A[3] * B[2];
+    C[3] = A[2] * B[1] + A[3] * B[3];
+}
+
+// v_cov3d += J^T v_cov2d J ; v_J = v_cov2d J cov3d^T + v_cov2d^T J cov3d   (J is 2x3, row-major [6])
+__device__ __forceinline__ void proj_cov_vjp(const float J[6], const float cov3d[9], const float vc[4],
+                                             float v_cov3d[9], float v_J[6]) {
+    // G = v_cov2d * J (2x3)
+    float G[6], Gt[6];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        G[j] = vc[0] * J[j] + vc[1] * J[3 + j];
+        G[3 + j] = vc[2] * J[j] + vc[3] * J[3 + j];
+        Gt[j] = vc[0] * J[j] + vc[2] * J[3 + j];
+        Gt[3 + j] = vc[1] * J[j] + vc[3] * J[3 + j];
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            v_cov3d[3 * i + j] += J[i] * G[j] + J[3 + i] * G[3 + j];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            // (G * cov3d^T)_ij = sum_k G_ik cov3d_jk ; (Gt * cov3d)_ij = sum_k Gt_ik cov3d_kj
+            v_J[3 * i + j] = (G[3 * i + 0] * cov3d[3 * j + 0] + G[3 * i + 1] * cov3d[3 * j + 1] +
+                              G[3 * i + 2] * cov3d[3 * j + 2]) +
+                             (Gt[3 * i + 0] * cov3d[0 + j] + Gt[3 * i + 1] * cov3d[3 + j] + Gt[3 * i + 2] * cov3d[6 + j]);
+        }
+}
+
+// Utils.cuh:539-616
+__device__ __forceinline__ void persp_vjp(const float p[3], const float cov3d[9], const RsCam &c, uint32_t width,
+                                          uint32_t height, const float vc[4], const float vm[2], float v_mean3d[3],
+                                          float v_cov3d[9]) {
+    float x = p[0], y = p[1], z = p[2];
+    float tan_fovx = 0.5f * width / c.fx;
+    float tan_fovy = 0.5f * height / c.fy;
+    float lim_x_pos = (width - c.cx) / c.fx + 0.3f * tan_fovx;
+    float lim_x_neg = c.cx / c.fx + 0.3f * tan_fovx;
+    float lim_y_pos = (height - c.cy) / c.fy + 0.3f * tan_fovy;
+    float lim_y_neg = c.cy / c.fy + 0.3f * tan_fovy;
+    float rz = 1.f / z;
+    float rz2 = rz * rz;
+    float tx = z * min(lim_x_pos, max(-lim_x_neg, x * rz));
+    float ty = z * min(lim_y_pos, max(-lim_y_neg, y * rz));
+    float J[6] = {c.fx * rz, 0.f, -c.fx * tx * rz2, 0.f, c.fy * rz, -c.fy * ty * rz2};
+    float v_J[6];
+    proj_cov_vjp(J, cov3d, vc, v_cov3d, v_J);
+    v_mean3d[0] += c.fx * rz * vm[0];
+    v_mean3d[1] += c.fy * rz * vm[1];
+    v_mean3d[2] += -(c.fx * x * vm[0] + c.fy * y * vm[1]) * rz2;
+    float rz3 = rz2 * rz;
+    if (x * rz <= lim_x_pos && x * rz >= -lim_x_neg)
+        v_mean3d[0] += -c.fx * rz2 * v_J[2];
+    else
+        v_mean3d[2] += -c.fx * rz3 * v_J[2] * tx;
+    if (y * rz <= lim_y_pos && y * rz >= -lim_y_neg)
+        v_mean3d[1] += -c.fy * rz2 * v_J[5];
+    else
+        v_mean3d[2] += -c.fy * rz3 * v_J[5] * ty;
+    v_mean3d[2] += -c.fx * rz2 * v_J[0] - c.fy * rz2 * v_J[4] + 2.f * c.fx * tx * rz3 * v_J[2] +
+                   2.f * c.fy * ty * rz3 * v_J[5];
+}
+
+// Utils.cuh:454-489
+__device__ __forceinline__ void ortho_vjp(const float cov3d[9], const RsCam &c, const float vc[4], const float vm[2],
+                                          float v_mean3d[3], float v_cov3d[9]) {
+    float J[6] = {c.fx, 0.f, 0.f, 0.f, c.fy, 0.f};
+    float v_J[6];
+    proj_cov_vjp(J, cov3d, vc, v_cov3d, v_J);
+    v_mean3d[0] += c.fx * vm[0];
+    v_mean3d[1] += c.fy * vm[1];
+}
+
+// Utils.cuh:657-747
+__device__ __forceinline__ void fisheye_vjp(const float p[3], const float cov3d[9], const RsCam &c, const float vc[4],
+                                            const float vm[2], float v_mean3d[3], float v_cov3d[9]) {
+    float x = p[0], y = p[1], z = p[2];
+    const float fx = c.fx, fy = c.fy;
+    const float eps = 0.0000001f;
+    float x2 = x * x + eps;
+    float y2 = y * y;
+    float xy = x * y;
+    float x2y2 = x2 + y2;
+    float len_xy = sqrtf(x * x + y * y) + eps;
+    const float x2y2z2 = x2y2 + z * z;
+    float x2y2z2_inv = 1.f / x2y2z2;
+    float b = atan2f(len_xy, z) / len_xy / x2y2;
+    float a = z * x2y2z2_inv / (x2y2);
+    v_mean3d[0] += fx * (x2 * a + y2 * b) * vm[0] + fy * xy * (a - b) * vm[1];
+    v_mean3d[1] += fx * xy * (a - b) * vm[0] + fy * (y2 * a + x2 * b) * vm[1];
+    v_mean3d[2] += -fx * x * x2y2z2_inv * vm[0] - fy * y * x2y2z2_inv * vm[1];
+
+    const float theta = atan2f(len_xy, z);
+    const float J_b = theta / len_xy / x2y2;
+    const float J_a = z * x2y2z2_inv / (x2y2);
+    float J[6] = {fx * (x2 * J_a + y2 * J_b), fx * xy * (J_a - J_b), -fx * x * x2y2z2_inv,
+                  fy * xy * (J_a - J_b),      fy * (y2 * J_a + x2 * J_b), -fy * y * x2y2z2_inv};
+    float v_J[6];
+    proj_cov_vjp(J, cov3d, vc, v_cov3d, v_J);
+    float l4 = x2y2z2 * x2y2z2;
+    float E = -l4 * x2y2 * theta + x2y2z2 * x2y2 * len_xy * z;
+    float F = 3 * l4 * theta - 3 * x2y2z2 * len_xy * z - 2 * x2y2 * len_xy * z;
+    float A = x * (3 * E + x2 * F);
+    float B = y * (E + x2 * F);
+    float C = x * (E + y2 * F);
+    float D = y * (3 * E + y2 * F);
+    float S1 = x2 - y2 - z * z;
+    float S2 = y2 - x2 - z * z;
+    float inv1 = x2y2z2_inv * x2y2z2_inv;
+    float inv2 = inv1 / (x2y2 * x2y2 * len_xy);
+    float dJ_dx00 = fx * A * inv2;
+    float dJ_dx01 = fx * B * inv2;
+    float dJ_dx02 = fx * S1 * inv1;
+    float dJ_dx10 = fy * B * inv2;
+    float dJ_dx11 = fy * C * inv2;
+    float dJ_dx12 = 2.f * fy * xy * inv1;
+    float dJ_dy00 = dJ_dx01;
+    float dJ_dy01 = fx * C * inv2;
+    float dJ_dy02 = 2.f * fx * xy * inv1;
+    float dJ_dy10 = dJ_dx11;
+    float dJ_dy11 = fy * D * inv2;
+    float dJ_dy12 = fy * S2 * inv1;
+    float dJ_dz00 = dJ_dx02;
+    float dJ_dz01 = dJ_dy02;
+    float dJ_dz02 = 2.f * fx * x * z * inv1;
+    float dJ_dz10 = dJ_dx12;
+    float dJ_dz11 = dJ_dy12;
+    float dJ_dz12 = 2.f * fy * y * z * inv1;
+    v_mean3d[0] += dJ_dx00 * v_J[0] + dJ_dx01 * v_J[1] + dJ_dx02 * v_J[2] + dJ_dx10 * v_J[3] + dJ_dx11 * v_J[4] +
+                   dJ_dx12 * v_J[5];
+    v_mean3d[1] += dJ_dy00 * v_J[0] + dJ_dy01 * v_J[1] + dJ_dy02 * v_J[2] + dJ_dy10 * v_J[3] + dJ_dy11 * v_J[4] +
+                   dJ_dy12 * v_J[5];
+    v_mean3d[2] += dJ_dz00 * v_J[0] + dJ_dz01 * v_J[1] + dJ_dz02 * v_J[2] + dJ_dz10 * v_J[3] + dJ_dz11 * v_J[4] +
+                   dJ_dz12 * v_J[5];
+}
+
+template <bool HAS_RIGID>
+__global__ void __launch_bounds__(RS_ISECT_THREADS)
+rs_project_bwd_kernel(const rs_project_bwd_args a) {
+    extern __shared__ __align__(16) float smem_dyn[];
+    const uint32_t N = a.N, C = a.C;
+    const uint64_t total = (uint64_t)a.B * C * N;
+    const uint64_t block_base = (uint64_t)blockIdx.x * RS_ISECT_BLOCK;
+    if (HAS_RIGID) {
+        rs_load_pose_table(a.rigid, smem_dyn);
+        __syncthreads();
+    }
+#pragma unroll 1
+    for (int it = 0; it < RS_ISECT_BLOCK / RS_ISECT_THREADS; ++it) {
+        const uint64_t idx = block_base + (uint64_t)it * RS_ISECT_THREADS + threadIdx.x;
+        bool active = idx < total;
+        uint32_t img = 0, gid = 0, bid = 0;
+        if (active) {
+            const int2 r = reinterpret_cast<const int2 *>(a.radii)[idx];
+            active = r.x > 0 && r.y > 0;
+            img = (uint32_t)(idx / N);
+            gid = (uint32_t)(idx - (uint64_t)img * N);
+            bid = img / C;
+        }
+        float v_R[9], v_t[3];
+#pragma unroll
+        for (int q = 0; q < 9; ++q)
+            v_R[q] = 0.f;
+        v_t[0] = v_t[1] = v_t[2] = 0.f;
+
+        if (active) {
+            const size_t gsrc = (size_t)bid * N + gid;
+            RsCam cam;
+            rs_load_cam(a.viewmats + (size_t)img * 16, a.Ks + (size_t)img * 9, cam);
+
+            // inverse_vjp: v_cov2d = -Cinv * Vinv * Cinv
+            const float ca = a.conics[idx * 3 + 0], cb = a.conics[idx * 3 + 1], cc = a.conics[idx * 3 + 2];
+            const float va = a.v_conics[idx * 3 + 0], vb = a.v_conics[idx * 3 + 1], vcc = a.v_conics[idx * 3 + 2];
+            const float Cinv[4] = {ca, cb, cb, cc};
+            const float Vinv[4] = {va, vb * .5f, vb * .5f, vcc};
+            float tmp[4], vc2[4];
+            mm2(Cinv, Vinv, tmp);
+            mm2(tmp, Cinv, vc2);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                vc2[q] = -vc2[q];
+            if (a.v_compensations != nullptr) { // add_blur_vjp
+                const float comp = a.compensations[idx];
+                const float v_comp = a.v_compensations[idx];
+                const float det_conic = ca * cc - cb * cb;
+                const float v_sqr_comp = v_comp * 0.5f / (comp + 1e-6f);
+                const float om = 1.f - comp * comp;
+                vc2[0] += v_sqr_comp * (om * ca - a.eps2d * det_conic);
+                vc2[1] += v_sqr_comp * (om * cb);
+                vc2[2] += v_sqr_comp * (om * cb);
+                vc2[3] += v_sqr_comp * (om * cc - a.eps2d * det_conic);
+            }
+
+            float mean0[3] = {a.means[gsrc * 3 + 0], a.means[gsrc * 3 + 1], a.means[gsrc * 3 + 2]};
+            float mean[3] = {mean0[0], mean0[1], mean0[2]};
+            const bool has_quat = a.covars == nullptr;
+            float quat0[4] = {1.f, 0.f, 0.f, 0.f}, quat[4];
+            float scale[3] = {0.f, 0.f, 0.f};
+            if (has_quat) {
+                const float4 q4 = *reinterpret_cast<const float4 *>(a.quats + gsrc * 4);
+                quat0[0] = q4.x;
+                quat0[1] = q4.y;
+                quat0[2] = q4.z;
+                quat0[3] = q4.w;
+                scale[0] = a.scales[gsrc * 3 + 0];
+                scale[1] = a.scales[gsrc * 3 + 1];
+                scale[2] = a.scales[gsrc * 3 + 2];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                quat[q] = quat0[q];
+            float body[RS_BODY_FLOATS];
+            int k = -1;
+            if (HAS_RIGID)
+                k = rs_rigid_transform(a.rigid, smem_dyn, gid, mean, quat, has_quat, body);
+            float covar[9], Rq[9];
+            if (has_quat) {
+                rs_quat_scale_to_covar(quat, scale, covar, Rq);
+            } else {
+                const float *cv = a.covars + gsrc * 6;
+                covar[0] = cv[0];
+                covar[1] = cv[1];
+                covar[2] = cv[2];
+                covar[3] = cv[1];
+                covar[4] = cv[3];
+                covar[5] = cv[4];
+                covar[6] = cv[2];
+                covar[7] = cv[4];
+                covar[8] = cv[5];
+                if (HAS_RIGID && k >= 0) {
+                    float t9[9];
+                    rs_mm3(body, covar, t9);
+                    rs_mm3_nt(t9, body, covar);
+                }
+            }
+            float p[3];
+            p[0] = cam.R[0] * mean[0] + cam.R[1] * mean[1] + cam.R[2] * mean[2] + cam.t[0];
+            p[1] = cam.R[3] * mean[0] + cam.R[4] * mean[1] + cam.R[5] * mean[2] + cam.t[1];
+            p[2] = cam.R[6] * mean[0] + cam.R[7] * mean[1] + cam.R[8] * mean[2] + cam.t[2];
+            float A9[9], covar_c[9];
+            rs_mm3(cam.R, covar, A9);
+            rs_mm3_nt(A9, cam.R, covar_c);
+
+            float v_covar_c[9], v_mean_c[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int q = 0; q < 9; ++q)
+                v_covar_c[q] = 0.f;
+            const float vm[2] = {a.v_means2d[idx * 2 + 0], a.v_means2d[idx * 2 + 1]};
+            if (a.camera_model == RS_PINHOLE)
+                persp_vjp(p, covar_c, cam, (uint32_t)a.image_width, (uint32_t)a.image_height, vc2, vm, v_mean_c,
+                          v_covar_c);
+            else if (a.camera_model == RS_ORTHO)
+                ortho_vjp(covar_c, cam, vc2, vm, v_mean_c, v_covar_c);
+            else
+                fisheye_vjp(p, covar_c, cam, vc2, vm, v_mean_c, v_covar_c);
+            v_mean_c[2] += a.v_depths[idx];
+
+            // posW2C_VJP
+            float v_mean[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    v_R[3 * i + j] = v_mean_c[i] * mean[j];
+                v_t[i] = v_mean_c[i];
+                v_mean[i] = cam.R[0 + i] * v_mean_c[0] + cam.R[3 + i] * v_mean_c[1] + cam.R[6 + i] * v_mean_c[2];
+            }
+            // covarW2C_VJP: v_R += v_covar_c R covar^T + v_covar_c^T R covar ; v_covar = R^T v_covar_c R
+            float v_covar[9];
+            {
+                float t1[9], t2[9];
+                rs_mm3(v_covar_c, cam.R, t1);
+                rs_mm3_nt(t1, covar, t2);
+#pragma unroll
+                for (int q = 0; q < 9; ++q)
+                    v_R[q] += t2[q];
+                rs_mm3_tn(v_covar_c, cam.R, t1);
+                rs_mm3(t1, covar, t2);
+#pragma unroll
+                for (int q = 0; q < 9; ++q)
+                    v_R[q] += t2[q];
+                rs_mm3_tn(cam.R, v_covar_c, t1);
+                rs_mm3(t1, cam.R, v_covar);
+            }
+
+            // chain through the rigid transform and write out
+            if (HAS_RIGID && k >= 0) {
+                float vm3[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) // R_k^T v_mean'
+                    vm3[i] = body[0 + i] * v_mean[0] + body[3 + i] * v_mean[1] + body[6 + i] * v_mean[2];
+                v_mean[0] = vm3[0];
+                v_mean[1] = vm3[1];
+                v_mean[2] = vm3[2];
+            }
+            if (a.v_means != nullptr) {
+                atomicAdd(a.v_means + gsrc * 3 + 0, v_mean[0]);
+                atomicAdd(a.v_means + gsrc * 3 + 1, v_mean[1]);
+                atomicAdd(a.v_means + gsrc * 3 + 2, v_mean[2]);
+            }
+            if (!has_quat) {
+                if (a.v_covars != nullptr) {
+                    if (HAS_RIGID && k >= 0) { // v_Sigma = R_k^T v_Sigma' R_k
+                        float t1[9];
+                        rs_mm3_tn(body, v_covar, t1);
+                        rs_mm3(t1, body, v_covar);
+                    }
+                    float *o = a.v_covars + gsrc * 6;
+                    atomicAdd(o + 0, v_covar[0]);
+                    atomicAdd(o + 1, v_covar[1] + v_covar[3]);
+                    atomicAdd(o + 2, v_covar[2] + v_covar[6]);
+                    atomicAdd(o + 3, v_covar[4]);
+                    atomicAdd(o + 4, v_covar[5] + v_covar[7]);
+                    atomicAdd(o + 5, v_covar[8]);
+                }
+            } else if (a.v_quats != nullptr || a.v_scales != nullptr) {
+                // quat_scale_to_covar_vjp (Utils.cuh:224-261) on the TRANSFORMED quaternion
+                float M[9], v_M[9], sym[9];
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        M[3 * i + j] = Rq[3 * i + j] * scale[j];
+                        sym[3 * i + j] = v_covar[3 * i + j] + v_covar[3 * j + i];
+                    }
+                rs_mm3(sym, M, v_M);
+                float v_scale[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    v_scale[j] = Rq[0 + j] * v_M[0 + j] + Rq[3 + j] * v_M[3 + j] + Rq[6 + j] * v_M[6 + j];
+                float m[9]; // v_R of the Gaussian's own rotation, math (row, col)
+#pragma unroll
+                for (int i = 0; i < 3; ++i)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j)
+                        m[3 * i + j] = v_M[3 * i + j] * scale[j];
+                // quat_to_rotmat_vjp (Utils.cuh:166-189)
+                float w = quat[0], x = quat[1], y = quat[2], z = quat[3];
+                const float inv_norm = rsqrtf(x * x + y * y + z * z + w * w);
+                x *= inv_norm;
+                y *= inv_norm;
+                z *= inv_norm;
+                w *= inv_norm;
+                float vq[4];
+                vq[0] = 2.f * (x * (m[7] - m[5]) + y * (m[2] - m[6]) + z * (m[3] - m[1]));
+                vq[1] = 2.f * (-2.f * x * (m[4] + m[8]) + y * (m[3] + m[1]) + z * (m[6] + m[2]) + w * (m[7] - m[5]));
+                vq[2] = 2.f * (x * (m[3] + m[1]) - 2.f * y * (m[0] + m[8]) + z * (m[7] + m[5]) + w * (m[2] - m[6]));
+                vq[3] = 2.f * (x * (m[6] + m[2]) + y * (m[7] + m[5]) - 2.f * z * (m[0] + m[4]) + w * (m[3] - m[1]));
+                const float dot = vq[0] * w + vq[1] * x + vq[2] * y + vq[3] * z;
+                float v_quat[4];
+                v_quat[0] = (vq[0] - dot * w) * inv_norm;
+                v_quat[1] = (vq[1] - dot * x) * inv_norm;
+                v_quat[2] = (vq[2] - dot * y) * inv_norm;
+                v_quat[3] = (vq[3] - dot * z) * inv_norm;
+                if (HAS_RIGID && k >= 0) {
+                    // q' = q_k (x) q  =>  v_q = conj(q_k) (x) v_q'
+                    const float w1 = body[15], x1 = -body[16], y1 = -body[17], z1 = -body[18];
+                    const float w2 = v_quat[0], x2 = v_quat[1], y2 = v_quat[2], z2 = v_quat[3];
+                    v_quat[0] = w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2;
+                    v_quat[1] = w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2;
+                    v_quat[2] = w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2;
+                    v_quat[3] = w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2;
+                }
+                if (a.v_quats != nullptr) {
+                    float *o = a.v_quats + gsrc * 4;
+                    atomicAdd(o + 0, v_quat[0]);
+                    atomicAdd(o + 1, v_quat[1]);
+                    atomicAdd(o + 2, v_quat[2]);
+                    atomicAdd(o + 3, v_quat[3]);
+                }
+                if (a.v_scales != nullptr) {
+                    float *o = a.v_scales + gsrc * 3;
+                    atomicAdd(o + 0, v_scale[0]);
+                    atomicAdd(o + 1, v_scale[1]);
+                    atomicAdd(o + 2, v_scale[2]);
+                }
+            }
+        }
+
+        if (a.v_viewmats != nullptr) {
+            // reduce over the Gaussians of one camera: warp shuffle when the warp is on a single image
+            const unsigned any_active = __ballot_sync(0xffffffffu, active);
+            if (any_active) {
+                const uint32_t img_lane0 = __shfl_sync(0xffffffffu, img, __ffs(any_active) - 1);
+                const bool uniform = __all_sync(0xffffffffu, !active || img == img_lane0);
+                if (uniform) {
+#pragma unroll
+                    for (int q = 0; q < 9; ++q)
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1)
+                            v_R[q] += __shfl_xor_sync(0xffffffffu, v_R[q], o);
+#pragma unroll
+                    for (int q = 0; q < 3; ++q)
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1)
+                            v_t[q] += __shfl_xor_sync(0xffffffffu, v_t[q], o);
+                }
+                if (active && (!uniform || (threadIdx.x & 31) == (unsigned)(__ffs(any_active) - 1))) {
+                    float *o = a.v_viewmats + (size_t)img * 16;
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+                        for (int j = 0; j < 3; ++j)
+                            atomicAdd(o + i * 4 + j, v_R[3 * i + j]);
+                        atomicAdd(o + i * 4 + 3, v_t[i]);
+                    }
+                }
+            }
+        }
+    }
+}
+
+extern "C" int rs_project_bwd(const rs_project_bwd_args *a, rs_stream_t stream) {
+    RS_CHECK(a != nullptr, "rs_project_bwd: null args");
+    RS_CHECK(a->camera_model == RS_PINHOLE || a->camera_model == RS_ORTHO || a->camera_model == RS_FISHEYE,
+             "rs_project_bwd: unsupported camera model %d", a->camera_model);
+    RS_CHECK((a->covars != nullptr) != (a->quats != nullptr && a->scales != nullptr),
+             "rs_project_bwd: exactly one of covars or (quats, scales) must be given");
+    const int64_t total = (int64_t)a->B * a->C * a->N;
+    if (total == 0)
+        return 0;
+    RS_CHECK(total < (int64_t)1 << 31, "rs_project_bwd: B*C*N exceeds int32 indexing");
+    RS_CHECK(a->means && a->viewmats && a->Ks && a->radii && a->conics && a->v_means2d && a->v_depths && a->v_conics,
+             "rs_project_bwd: null required pointer");
+    RS_CHECK((a->v_compensations == nullptr) || (a->compensations != nullptr),
+             "rs_project_bwd: v_compensations given without compensations");
+    const bool rigid = a->rigid.cluster_ids != nullptr;
+    if (rigid)
+        RS_CHECK(a->rigid.body_quats && a->rigid.body_trans && a->rigid.K > 0, "rs_project_bwd: rigid table incomplete");
+    const int grid = rs_isect_num_blocks(total);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (rigid) {
+        size_t smem = a->rigid.K <= RS_MAX_SMEM_BODIES ? (size_t)a->rigid.K * RS_BODY_FLOATS * sizeof(float) : 0;
+        rs_project_bwd_kernel<true><<<grid, RS_ISECT_THREADS, smem, s>>>(*a);
+    } else {
+        rs_project_bwd_kernel<false><<<grid, RS_ISECT_THREADS, 0, s>>>(*a);
+    }
+    RS_LAUNCH_CHECK("rs_project_bwd_kernel");
+    return 0;
+}

@@ -1,0 +1,249 @@
+/*
+ * rigidsplat.h -- C ABI of librigidsplat.so: the B200-native (sm_100a) animate -> project -> tile-sort ->
+ * composite hot path of JTStephens18/3DGS_rigidbody (a gsplat 1.5.3 fork).
+ *
+ * This header is the drop-in boundary.  Every entry point replaces one operator that the reference binds
+ * through its pybind module `_C` (gsplat/cuda/ext.cpp:6-104, C++ signatures in gsplat/cuda/include/Ops.h);
+ * the file:line each one stands in for is cited on the declaration.  Conventions:
+ *   - plain C: POD structs, raw DEVICE pointers (float32 / int32 / int64), sizes, an explicit CUDA stream
+ *     (`void*` = cudaStream_t; NULL = legacy default stream).  No torch / ATen types.
+ *   - inputs are borrowed, must be contiguous and live on the current device; outputs are caller-allocated
+ *     (the reference allocates them in its host launchers, e.g. csrc/Projection.cpp:144-162; our Python shim
+ *     `3dgs_rigidbody_b200/_C.py` does that with torch and passes the pointers here).
+ *   - every function returns 0 on success, non-zero on failure; `rs_last_error()` then holds a message
+ *     (thread-local).  Launch errors are checked (the reference does not check them at all).
+ *   - nothing here synchronises the stream or the device, except rs_isect_count_total().
+ *   - optional pointers may be NULL where marked "optional".
+ */
+#ifndef RIGIDSPLAT_H_
+#define RIGIDSPLAT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RS_ABI_VERSION 3
+
+/* gsplat/cuda/include/Common.h:46-51 (CameraModelType) */
+enum { RS_PINHOLE = 0, RS_ORTHO = 1, RS_FISHEYE = 2, RS_FTHETA = 3 };
+
+typedef void *rs_stream_t; /* cudaStream_t */
+
+int rs_abi_version(void);
+const char *rs_last_error(void);
+/* sizeof() of every args struct, for binding self-checks: which = 0 project_fwd, 1 project_bwd, 2 isect,
+ * 3 sort, 4 raster_fwd, 5 raster_bwd, 6 frame.  Returns 0 for an unknown id. */
+uint64_t rs_sizeof_args(int which);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Rigid pose table.  Replaces main.py:183-228 (apply_transform) + main.py:173-181 (quat_multiply) +
+ * gsplat/utils.py:109-134 (normalized_quat_to_rotmat): instead of cloning every splat tensor per body and
+ * running ~15 torch ops, the per-body pose is consumed inside the projection kernels.
+ *   mean'  = R_k (mean - center_k) + center_k + trans_k      (main.py:210-213, 222)
+ *   quat'  = (q_k / |q_k|) (x) quat        wxyz Hamilton     (main.py:207, 219)
+ * cluster_ids[g] = k in [0,K) selects the body; k < 0 ("background") leaves the Gaussian untouched.
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+    const int32_t *cluster_ids; /* [N] optional (NULL = no rigid transform) */
+    const float *body_quats;    /* [K,4] wxyz, need not be unit */
+    const float *body_trans;    /* [K,3] */
+    const float *body_centers;  /* [K,3] optional (NULL = rotate about the origin) */
+    int32_t K;
+    int32_t _pad;
+} rs_rigid_t;
+
+/* ------------------------------------------------------------------------------------------------------------
+ * rs_project_fwd: replaces `projection_ewa_3dgs_fused_fwd` (Ops.h:42-64, csrc/Projection.cpp:104-189, kernel
+ * csrc/ProjectionEWA3DGSFused.cu:15-212) with the rigid transform fused in front, and (optionally) the first pass
+ * of `intersect_tile` (csrc/IntersectTile.cu:55-84) fused behind it.
+ * Culled entries get radii = 0 and ZEROS in means2d/depths/conics (the reference leaves them uninitialised).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t B, C, N;            /* batches, cameras per batch, Gaussians per batch */
+    int32_t image_width, image_height;
+    int32_t camera_model;       /* RS_PINHOLE | RS_ORTHO | RS_FISHEYE */
+    float eps2d, near_plane, far_plane, radius_clip;
+    const float *means;         /* [B,N,3] */
+    const float *covars;        /* [B,N,6] optional, exclusive with quats+scales */
+    const float *quats;         /* [B,N,4] optional */
+    const float *scales;        /* [B,N,3] optional */
+    const float *opacities;     /* [B,N] optional */
+    const float *viewmats;      /* [B,C,4,4] row-major world->camera */
+    const float *Ks;            /* [B,C,3,3] */
+    rs_rigid_t rigid;           /* applied when rigid.cluster_ids != NULL (ids shared by all batches) */
+    int32_t *radii;             /* [B,C,N,2] out */
+    float *means2d;             /* [B,C,N,2] out */
+    float *depths;              /* [B,C,N]   out */
+    float *conics;              /* [B,C,N,3] out */
+    float *compensations;       /* [B,C,N]   out, optional (non-NULL <=> calc_compensations) */
+    /* optional fused tile counting (all three or none): */
+    int32_t *tiles_per_gauss;   /* [B*C*N] out, optional */
+    int32_t *block_sums;        /* [rs_isect_num_blocks(B*C*N)] out, optional */
+    int32_t tile_size, tile_width, tile_height;
+    int32_t _pad;
+} rs_project_fwd_args;
+int rs_project_fwd(const rs_project_fwd_args *a, rs_stream_t stream);
+
+/* rs_project_bwd: replaces `projection_ewa_3dgs_fused_bwd` (Ops.h:65-88, csrc/Projection.cpp:191-281, kernel
+ * csrc/ProjectionEWA3DGSFused.cu:293-531).  v_* outputs must be ZERO-initialised by the caller (the reference
+ * zero-inits them in Projection.cpp:239-250); results are accumulated with atomics.  With a rigid table the
+ * gradients are chained back to the UNtransformed means / quats (v_mean = R_k^T v_mean', v_quat = conj(q_k) (x) v_quat'). */
+typedef struct {
+    int32_t B, C, N;
+    int32_t image_width, image_height;
+    int32_t camera_model;
+    float eps2d;
+    int32_t _pad;
+    const float *means, *covars, *quats, *scales, *viewmats, *Ks;
+    rs_rigid_t rigid;
+    const int32_t *radii;        /* [B,C,N,2] fwd output */
+    const float *conics;         /* [B,C,N,3] fwd output */
+    const float *compensations;  /* optional */
+    const float *v_means2d;      /* [B,C,N,2] */
+    const float *v_depths;       /* [B,C,N] */
+    const float *v_conics;       /* [B,C,N,3] */
+    const float *v_compensations;/* optional */
+    float *v_means;              /* [B,N,3] optional */
+    float *v_covars;             /* [B,N,6] optional (when covars given) */
+    float *v_quats;              /* [B,N,4] optional */
+    float *v_scales;             /* [B,N,3] optional */
+    float *v_viewmats;           /* [B,C,4,4] optional */
+} rs_project_bwd_args;
+int rs_project_bwd(const rs_project_bwd_args *a, rs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Tile intersection.  Replaces `intersect_tile` (Ops.h:186-198, csrc/Intersect.cpp:15-149, kernels
+ * csrc/IntersectTile.cu:23-207 and the cub::DeviceRadixSort call at :296-339) and `intersect_offset`
+ * (Ops.h:199-204, csrc/Intersect.cpp:151-168, csrc/IntersectTile.cu:209-292).
+ *
+ * Key format (csrc/IntersectTile.cu:95-108): image_id << (32 + tile_n_bits) | tile_id << 32 | bits(depth),
+ * value = flatten index (image * N + gaussian, or the nnz row when packed).
+ * The reference needs one host sync to size its outputs (Intersect.cpp:79-80).  Here the count and the emission
+ * are separate calls so that a caller with a pre-sized workspace never syncs:
+ *   rs_isect_count      tiles_per_gauss + per-block sums                 (pass 1)
+ *   rs_isect_scan       exclusive scan of the block sums, writes *n_isects (device)
+ *   rs_isect_count_total  copies *n_isects to the host (THE sync of the compat path)
+ *   rs_isect_emit       unsorted keys/values                              (pass 2; load-balanced, coalesced)
+ *   rs_radix_sort_pairs hand-written stable LSD radix sort of (u64 key, i32 value) over [0, end_bit)
+ *   rs_isect_offsets    first-isect index per (image, tile)
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int32_t n_elems;             /* I*N, or nnz when packed */
+    int32_t N;                   /* Gaussians per image (unpacked); ignored when image_ids != NULL */
+    int32_t I;                   /* number of images */
+    int32_t tile_size, tile_width, tile_height;
+    const float *means2d;        /* [n_elems,2] */
+    const int32_t *radii;        /* [n_elems,2] */
+    const float *depths;         /* [n_elems] */
+    const int64_t *image_ids;    /* [nnz] optional: packed mode */
+    int32_t *tiles_per_gauss;    /* [n_elems] out (count) / in (emit) */
+    int32_t *block_sums;         /* [rs_isect_num_blocks(n_elems) + 1] scratch: sums -> exclusive offsets */
+    int32_t *n_isects;           /* [1] device, written by rs_isect_scan */
+    int64_t *isect_ids;          /* [capacity] out (emit) */
+    int32_t *flatten_ids;        /* [capacity] out (emit) */
+    int64_t capacity;            /* emit writes nothing beyond it; *overflow set when n_isects > capacity */
+    int32_t *overflow;           /* [1] device, optional */
+} rs_isect_args;
+int32_t rs_isect_num_blocks(int64_t n_elems);
+int rs_isect_count(const rs_isect_args *a, rs_stream_t stream);
+int rs_isect_scan(const rs_isect_args *a, rs_stream_t stream);
+int rs_isect_count_total(const rs_isect_args *a, rs_stream_t stream, int64_t *n_isects_host);
+int rs_isect_emit(const rs_isect_args *a, rs_stream_t stream);
+
+typedef struct {
+    int64_t n;                   /* number of pairs if n_dev == NULL, else capacity (grid sizing bound) */
+    const int32_t *n_dev;        /* optional device count (sync-free path): only the first *n_dev pairs are sorted */
+    int32_t begin_bit, end_bit;  /* sort on key bits [begin_bit, end_bit) */
+    int64_t *keys_a, *keys_b;    /* double buffer; input in keys_a */
+    int32_t *vals_a, *vals_b;    /* double buffer; input in vals_a */
+    void *workspace;             /* rs_radix_sort_workspace_bytes(n) bytes */
+    uint64_t workspace_bytes;
+    int32_t *result_in_b;        /* host out: 1 if the sorted data ended up in keys_b/vals_b, else 0 */
+} rs_sort_args;
+uint64_t rs_radix_sort_workspace_bytes(int64_t n);
+int rs_radix_sort_pairs(const rs_sort_args *a, rs_stream_t stream);
+
+int rs_isect_offsets(const int64_t *isect_ids_sorted, int64_t n_isects, const int32_t *n_isects_dev /*optional*/,
+                     int32_t I, int32_t tile_width, int32_t tile_height, int32_t *offsets /*[I*th*tw]*/,
+                     rs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Compositing.  rs_raster_fwd replaces `rasterize_to_pixels_3dgs_fwd` (Ops.h:223-238, csrc/Rasterization.cpp:20-115,
+ * kernel csrc/RasterizeToPixels3DGSFwd.cu:17-187); rs_raster_bwd replaces `rasterize_to_pixels_3dgs_bwd`
+ * (Ops.h:239-263, csrc/Rasterization.cpp:117-228, kernel csrc/RasterizeToPixels3DGSBwd.cu:15-276).
+ * Any channel count 1..RS_MAX_CHANNELS is accepted directly (the reference pads to one of 19 template
+ * instantiations in python, _wrapper.py:604-648).  tile_size must be 16 (the only value the reference exercises,
+ * rendering.py:184-185).
+ * ------------------------------------------------------------------------------------------------------------ */
+#define RS_MAX_CHANNELS 513
+typedef struct {
+    int32_t I, N;                /* images; Gaussians per image (0 when packed) */
+    int32_t channels;
+    int32_t image_width, image_height, tile_size, tile_width, tile_height;
+    int64_t n_isects;            /* used when n_isects_dev == NULL */
+    const int32_t *n_isects_dev; /* optional device count */
+    const float *means2d;        /* [I*N,2] or [nnz,2] */
+    const float *conics;         /* [I*N,3] */
+    const float *colors;         /* [I*N,channels] */
+    const float *opacities;      /* [I*N] */
+    const float *backgrounds;    /* [I,channels] optional */
+    const uint8_t *masks;        /* [I,tile_height,tile_width] bool, optional */
+    const int32_t *tile_offsets; /* [I,tile_height,tile_width] */
+    const int32_t *flatten_ids;  /* [n_isects] */
+    /* Broadcast without materialising [I,N,...] copies (rendering.py:446-448, 481-485 do torch.broadcast_to + contiguous):
+     * when > 0 the colour / opacity row of flatten id g is g % attr_mod (i.e. shared by all images). 0 = per-image rows. */
+    int32_t attr_mod_colors;
+    int32_t attr_mod_opacities;
+    float *render_colors;        /* [I,H,W,channels] out */
+    float *render_alphas;        /* [I,H,W,1] out */
+    int32_t *last_ids;           /* [I,H,W] out */
+} rs_raster_fwd_args;
+int rs_raster_fwd(const rs_raster_fwd_args *a, rs_stream_t stream);
+
+typedef struct {
+    rs_raster_fwd_args f;        /* forward inputs (render_colors unused; render_alphas/last_ids are inputs here) */
+    const float *v_render_colors;/* [I,H,W,channels] */
+    const float *v_render_alphas;/* [I,H,W,1] */
+    float *v_means2d_abs;        /* [I*N,2] optional (absgrad); zero-initialised by the caller */
+    float *v_means2d;            /* [I*N,2] zero-initialised by the caller */
+    float *v_conics;             /* [I*N,3] zero-initialised */
+    float *v_colors;             /* [I*N,channels] zero-initialised */
+    float *v_opacities;          /* [I*N] zero-initialised */
+} rs_raster_bwd_args;
+int rs_raster_bwd(const rs_raster_bwd_args *a, rs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * rs_render_frame: the whole per-frame hot path in one call with NO host synchronisation -- what the commented-out
+ * animation loop of main.py:357-409 would run per frame (apply_transform per body + rasterization(), rendering.py:33-770,
+ * packed=False, sh_degree=None).  All intermediates live in a caller-owned workspace sized by rs_frame_workspace_bytes();
+ * if a frame produces more tile intersections than `max_isects`, *status (device int32[4]: {n_isects, overflow, 0, 0})
+ * reports it and the surplus intersections are dropped (the caller re-renders with a larger workspace).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+    rs_project_fwd_args proj;    /* B must be 1; tiles_per_gauss/block_sums are taken from the workspace when NULL */
+    const float *colors;         /* [N,channels] (shared by all cameras) or [C,N,channels] if colors_per_camera */
+    int32_t channels;
+    int32_t colors_per_camera;
+    const float *backgrounds;    /* [C,channels] optional */
+    int64_t max_isects;
+    void *workspace;
+    uint64_t workspace_bytes;
+    float *render_colors;        /* [C,H,W,channels] out */
+    float *render_alphas;        /* [C,H,W,1] out */
+    int32_t *status;             /* device int32[4] out */
+    /* optional exports of the sorted intersection data (`meta` of rendering.py:651-665); NULL to skip */
+    int32_t *out_tile_offsets;   /* [C,tile_h,tile_w] */
+} rs_frame_args;
+uint64_t rs_frame_workspace_bytes(int32_t C, int32_t N, int32_t image_width, int32_t image_height, int32_t tile_size,
+                                  int32_t channels, int64_t max_isects);
+int rs_render_frame(const rs_frame_args *a, rs_stream_t stream);
+/* device pointers into a frame workspace, for tests and `meta`: which = 0 isect_ids(sorted), 1 flatten_ids(sorted),
+ * 2 tile_offsets, 3 last_ids, 4 tiles_per_gauss.  Valid after rs_render_frame on the same workspace geometry. */
+void *rs_frame_workspace_ptr(const rs_frame_args *a, int which);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RIGIDSPLAT_H_ */
