@@ -1,0 +1,168 @@
+"""FrameRenderer: the per-frame animate-and-render loop with no host synchronisation.
+
+This is the executable form of the commented-out animation loop of the reference (main.py:357-409): per frame, a new
+pose for every rigid body, then one render.  The reference does `apply_transform()` per body (cloning all splat
+tensors, main.py:200) followed by `rasterization()` with its `.item()` sync (csrc/Intersect.cpp:80); here one C-ABI call
+(`rs_render_frame`, include/rigidsplat.h) enqueues the whole pipeline on the current stream into a pre-sized workspace.
+
+Colours are post-activation per-Gaussian values [N, D] (sh_degree=None in the reference's terms).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+from ._C import PINHOLE, RigidPoses, _check
+
+
+class FrameRenderer:
+    def __init__(
+        self,
+        means: Tensor,  # [N,3]
+        quats: Tensor,  # [N,4]
+        scales: Tensor,  # [N,3]
+        opacities: Tensor,  # [N]
+        colors: Tensor,  # [N,D]
+        width: int,
+        height: int,
+        cluster_ids: Optional[Tensor] = None,  # [N] int32
+        body_centers: Optional[Tensor] = None,  # [K,3]
+        n_cameras: int = 1,
+        max_isects: Optional[int] = None,
+        near_plane: float = 0.01,
+        far_plane: float = 1e10,
+        radius_clip: float = 0.0,
+        eps2d: float = 0.3,
+        backgrounds: Optional[Tensor] = None,  # [C,D]
+        camera_model: int = PINHOLE,
+    ):
+        self.lib = _lib.load()
+        dev = means.device
+        N = means.shape[0]
+        D = colors.shape[-1]
+        _check(means, "means", torch.float32, (N, 3))
+        _check(quats, "quats", torch.float32, (N, 4), dev)
+        _check(scales, "scales", torch.float32, (N, 3), dev)
+        _check(opacities, "opacities", torch.float32, (N,), dev)
+        _check(colors, "colors", torch.float32, (N, D), dev)
+        if cluster_ids is not None:
+            _check(cluster_ids, "cluster_ids", torch.int32, (N,), dev)
+        if backgrounds is not None:
+            _check(backgrounds, "backgrounds", torch.float32, (n_cameras, D), dev)
+        self.means, self.quats, self.scales, self.opacities, self.colors = means, quats, scales, opacities, colors
+        self.cluster_ids, self.body_centers, self.backgrounds = cluster_ids, body_centers, backgrounds
+        self.N, self.D, self.C, self.W, self.H = N, D, n_cameras, int(width), int(height)
+        self.near_plane, self.far_plane, self.radius_clip, self.eps2d = near_plane, far_plane, radius_clip, eps2d
+        self.camera_model = camera_model
+        self.device = dev
+        self.tile_size = 16
+        self.tile_width = (self.W + 15) // 16
+        self.tile_height = (self.H + 15) // 16
+        if max_isects is None:
+            max_isects = max(16 * N * n_cameras, 1 << 20)
+        self._alloc(int(max_isects))
+        with torch.cuda.device(dev):
+            self.render_colors = torch.empty(self.C, self.H, self.W, D, dtype=torch.float32, device=dev)
+            self.render_alphas = torch.empty(self.C, self.H, self.W, 1, dtype=torch.float32, device=dev)
+            self.status = torch.zeros(4, dtype=torch.int32, device=dev)
+        self._args = None
+
+    def _alloc(self, max_isects: int) -> None:
+        self.max_isects = max_isects
+        nbytes = self.lib.rs_frame_workspace_bytes(self.C, self.N, self.W, self.H, self.tile_size, self.D, max_isects)
+        if nbytes == 0:
+            raise _lib.RigidSplatError("rs_frame_workspace_bytes: invalid geometry")
+        with torch.cuda.device(self.device):
+            self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.workspace_bytes = nbytes
+
+    def _fill(self, viewmats: Tensor, Ks: Tensor, body_quats: Optional[Tensor], body_trans: Optional[Tensor]):
+        a = _lib.rs_frame_args()
+        p = a.proj
+        p.B, p.C, p.N = 1, self.C, self.N
+        p.image_width, p.image_height = self.W, self.H
+        p.camera_model = self.camera_model
+        p.eps2d, p.near_plane, p.far_plane, p.radius_clip = self.eps2d, self.near_plane, self.far_plane, self.radius_clip
+        p.means, p.quats, p.scales = self.means.data_ptr(), self.quats.data_ptr(), self.scales.data_ptr()
+        p.covars = None
+        p.opacities = self.opacities.data_ptr()
+        p.viewmats, p.Ks = viewmats.data_ptr(), Ks.data_ptr()
+        if self.cluster_ids is not None and body_quats is not None:
+            RigidPoses(self.cluster_ids, body_quats, body_trans, self.body_centers).fill(p.rigid)
+        p.tile_size, p.tile_width, p.tile_height = self.tile_size, self.tile_width, self.tile_height
+        a.colors = self.colors.data_ptr()
+        a.channels = self.D
+        a.colors_per_camera = 0
+        a.backgrounds = self.backgrounds.data_ptr() if self.backgrounds is not None else None
+        a.max_isects = self.max_isects
+        a.workspace = self.workspace.data_ptr()
+        a.workspace_bytes = self.workspace_bytes
+        a.render_colors = self.render_colors.data_ptr()
+        a.render_alphas = self.render_alphas.data_ptr()
+        a.status = self.status.data_ptr()
+        a.out_tile_offsets = None
+        return a
+
+    def render(self, viewmats: Tensor, Ks: Tensor, body_quats: Optional[Tensor] = None,
+               body_trans: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+        """Enqueue one frame on the current stream.  Returns views of the renderer-owned output buffers
+        (render_colors [C,H,W,D], render_alphas [C,H,W,1]); they are overwritten by the next call."""
+        _check(viewmats, "viewmats", torch.float32, (self.C, 4, 4), self.device)
+        _check(Ks, "Ks", torch.float32, (self.C, 3, 3), self.device)
+        if self.cluster_ids is not None:
+            if body_quats is None or body_trans is None:
+                raise RuntimeError("FrameRenderer.render: body_quats and body_trans are required with cluster_ids")
+            K = body_quats.shape[0]
+            _check(body_quats, "body_quats", torch.float32, (K, 4), self.device)
+            _check(body_trans, "body_trans", torch.float32, (K, 3), self.device)
+        with torch.cuda.device(self.device):
+            a = self._fill(viewmats, Ks, body_quats, body_trans)
+            self._args = a
+            _lib.check(self.lib.rs_render_frame(ctypes.byref(a), torch.cuda.current_stream().cuda_stream))
+        return self.render_colors, self.render_alphas
+
+    # ---- introspection (each of these synchronises) ---------------------------------------------------------------
+    def n_isects(self) -> int:
+        return int(self.status[0].item())
+
+    def overflowed(self) -> bool:
+        return bool(self.status[1].item())
+
+    def ensure_capacity(self, slack: float = 1.25) -> bool:
+        """After a frame: grow the workspace if it overflowed.  Returns True if it was re-allocated (re-render then)."""
+        n = self.n_isects()
+        if n > self.max_isects:
+            self._alloc(int(n * slack) + 1024)
+            return True
+        return False
+
+    def _ws_tensor(self, which: int, dtype, numel: int) -> Tensor:
+        ptr = self.lib.rs_frame_workspace_ptr(ctypes.byref(self._args), which)
+        off = ptr - self.workspace.data_ptr()
+        nbytes = numel * torch.empty((), dtype=dtype).element_size()
+        return self.workspace[off : off + nbytes].view(dtype)
+
+    def meta(self) -> dict:
+        """The sorted intersection data of the last frame (`meta` of rendering.py:651-665), as views of the workspace."""
+        assert self._args is not None, "render() first"
+        n = min(self.n_isects(), self.max_isects)
+        E = self.C * self.N
+        return {
+            "isect_ids": self._ws_tensor(0, torch.int64, self.max_isects)[:n],
+            "flatten_ids": self._ws_tensor(1, torch.int32, self.max_isects)[:n],
+            "isect_offsets": self._ws_tensor(2, torch.int32, self.C * self.tile_height * self.tile_width).view(
+                self.C, self.tile_height, self.tile_width),
+            "last_ids": self._ws_tensor(3, torch.int32, self.C * self.H * self.W).view(self.C, self.H, self.W),
+            "tiles_per_gauss": self._ws_tensor(4, torch.int32, E).view(self.C, self.N),
+            "radii": self._ws_tensor(5, torch.int32, E * 2).view(self.C, self.N, 2),
+            "means2d": self._ws_tensor(6, torch.float32, E * 2).view(self.C, self.N, 2),
+            "depths": self._ws_tensor(7, torch.float32, E).view(self.C, self.N),
+            "conics": self._ws_tensor(8, torch.float32, E * 3).view(self.C, self.N, 3),
+            "n_isects": n,
+            "tile_width": self.tile_width,
+            "tile_height": self.tile_height,
+        }
