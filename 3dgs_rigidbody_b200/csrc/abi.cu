@@ -14,6 +14,10 @@ void rs_set_error(const char *fmt, ...) {
 }
 
 extern "C" const char *rs_last_error(void) { return g_err; }
+
+static uint64_t g_launches = 0;
+void rs_count_launch() { __atomic_fetch_add(&g_launches, 1, __ATOMIC_RELAXED); }
+extern "C" uint64_t rs_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 extern "C" int rs_abi_version(void) { return RS_ABI_VERSION; }
 
 extern "C" uint64_t rs_sizeof_args(int which) {

@@ -33,8 +33,10 @@ void rs_set_error(const char *fmt, ...);
         }                                                                                                              \
     } while (0)
 
+void rs_count_launch();
 #define RS_LAUNCH_CHECK(name)                                                                                          \
     do {                                                                                                               \
+        rs_count_launch();                                                                                             \
         cudaError_t err__ = cudaGetLastError();                                                                        \
         if (err__ != cudaSuccess) {                                                                                    \
             rs_set_error("launch of %s failed: %s", name, cudaGetErrorString(err__));                                  \

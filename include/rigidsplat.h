@@ -36,6 +36,9 @@ const char *rs_last_error(void);
 /* sizeof() of every args struct, for binding self-checks: which = 0 project_fwd, 1 project_bwd, 2 isect,
  * 3 sort, 4 raster_fwd, 5 raster_bwd, 6 frame.  Returns 0 for an unknown id. */
 uint64_t rs_sizeof_args(int which);
+/* number of kernels this library has launched in this process (all threads); bench.py reports its delta over the
+ * timed region as `gpu_launches`. */
+uint64_t rs_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Rigid pose table.  Replaces main.py:183-228 (apply_transform) + main.py:173-181 (quat_multiply) +

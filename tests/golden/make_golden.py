@@ -116,7 +116,9 @@ def main():
         m, q, s, o, c, _, _, _ = scene(7, 2 * N, 2, s_max=0.1)
         m, q, s = m.reshape(2, N, 3), q.reshape(2, N, 4), s.reshape(2, N, 3)
         if model == "ortho":
-            s = s * 0.02
+            # keep the projected footprint comparable to eps2d: the reference CUDA backward divides by
+            # (compensation + 1e-6) (Utils.cuh:406) which departs from autograd when compensation -> 0
+            s = s * 0.5
         vm, K3 = cameras(2, W, H)
         vm, K3 = vm[None].repeat(2, 1, 1, 1), K3[None].repeat(2, 1, 1, 1)
         if model == "ortho":
