@@ -266,29 +266,18 @@ def intersect_tile(
         flatten_ids = torch.empty(n_isects, dtype=torch.int32, device=dev)
         if n_isects > 0:
             a.isect_ids, a.flatten_ids, a.capacity = _ptr(isect_ids), _ptr(flatten_ids), n_isects
-            _lib.check(lib.rs_isect_emit(ctypes.byref(a), s))
-        if n_isects > 0 and sort:
-            n_tiles = tile_width * tile_height
-            image_n_bits = int(I).bit_length()
-            tile_n_bits = int(n_tiles).bit_length()
-            isect_ids_b = torch.empty_like(isect_ids)
-            flatten_ids_b = torch.empty_like(flatten_ids)
-            ws_bytes = lib.rs_radix_sort_workspace_bytes(n_isects)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            in_b = ctypes.c_int32(0)
-            sa = _lib.rs_sort_args()
-            sa.n = n_isects
-            sa.n_dev = None
-            # `segmented` sorts bits [0, 32 + tile_n_bits) inside each image segment (IntersectTile.cu:368-379); the
-            # emitted keys are already grouped by image, so one stable sort over all bits gives the identical order.
-            sa.begin_bit, sa.end_bit = 0, 32 + tile_n_bits + image_n_bits
-            sa.keys_a, sa.keys_b = _ptr(isect_ids), _ptr(isect_ids_b)
-            sa.vals_a, sa.vals_b = _ptr(flatten_ids), _ptr(flatten_ids_b)
-            sa.workspace, sa.workspace_bytes = ws.data_ptr(), ws_bytes
-            sa.result_in_b = ctypes.cast(ctypes.pointer(in_b), ctypes.c_void_p)
-            _lib.check(lib.rs_radix_sort_pairs(ctypes.byref(sa), s))
-            if in_b.value:
-                isect_ids, flatten_ids = isect_ids_b, flatten_ids_b
+            if not sort:
+                _lib.check(lib.rs_isect_emit(ctypes.byref(a), s))
+            else:
+                # `segmented` sorts inside each image segment (IntersectTile.cu:368-379); the order is the same as one
+                # stable sort over (image | tile | depth), which is what rs_isect_sorted produces.
+                sa = _lib.rs_isect_sorted_args()
+                ctypes.memmove(ctypes.byref(sa.isect), ctypes.byref(a), ctypes.sizeof(a))
+                ws_bytes = lib.rs_isect_sorted_workspace_bytes(n_elems, n_isects)
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+                sa.tile_offsets = None
+                sa.workspace, sa.workspace_bytes = ws.data_ptr(), ws_bytes
+                _lib.check(lib.rs_isect_sorted(ctypes.byref(sa), s))
     return tiles_per_gauss, isect_ids, flatten_ids
 
 

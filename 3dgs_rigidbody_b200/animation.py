@@ -151,6 +151,9 @@ class FrameRenderer:
         assert self._args is not None, "render() first"
         n = min(self.n_isects(), self.max_isects)
         E = self.C * self.N
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.rs_frame_export_isect_ids(ctypes.byref(self._args),
+                                                          torch.cuda.current_stream().cuda_stream))
         return {
             "isect_ids": self._ws_tensor(0, torch.int64, self.max_isects)[:n],
             "flatten_ids": self._ws_tensor(1, torch.int32, self.max_isects)[:n],

@@ -38,6 +38,8 @@ extern "C" uint64_t rs_sizeof_args(int which) {
         return sizeof(rs_frame_args);
     case 7:
         return sizeof(rs_rigid_t);
+    case 8:
+        return sizeof(rs_isect_sorted_args);
     default:
         return 0;
     }

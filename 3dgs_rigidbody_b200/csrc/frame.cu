@@ -6,14 +6,14 @@
 
 #include "common.cuh"
 
-int rs_sort_pairs_u64_internal(int64_t n_bound, const int32_t *n_dev, int begin_bit, int end_bit, uint64_t *keys_a,
-                               uint64_t *keys_b, int32_t *vals_a, int32_t *vals_b, void *workspace,
-                               uint64_t workspace_bytes, int32_t *result_in_b, cudaStream_t s);
+int rs_isect_ids_from_offsets(const int32_t *offsets, const int32_t *flatten_ids, const float *depths, int64_t n_bound,
+                              const int32_t *n_dev, int32_t I, int32_t tile_width, int32_t tile_height,
+                              int64_t *isect_ids, rs_stream_t stream);
 
 namespace {
 struct FrameLayout {
-    size_t radii, means2d, depths, conics, tiles_per_gauss, block_sums, keys_a, keys_b, vals_a, vals_b, sort_ws,
-        sort_ws_bytes, tile_offsets, last_ids, total;
+    size_t radii, means2d, depths, conics, tiles_per_gauss, block_sums, isect_ids, flatten_ids, bin_ws, bin_ws_bytes,
+        tile_offsets, last_ids, total;
 };
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -33,12 +33,10 @@ FrameLayout make_layout(int32_t C, int32_t N, int32_t W, int32_t H, int32_t tile
     L.conics = take(E * 3 * 4);
     L.tiles_per_gauss = take(E * 4);
     L.block_sums = take(((size_t)rs_isect_num_blocks((int64_t)E) + 1) * 4);
-    L.keys_a = take((size_t)max_isects * 8);
-    L.keys_b = take((size_t)max_isects * 8);
-    L.vals_a = take((size_t)max_isects * 4);
-    L.vals_b = take((size_t)max_isects * 4);
-    L.sort_ws_bytes = rs_radix_sort_workspace_bytes(max_isects);
-    L.sort_ws = take(L.sort_ws_bytes);
+    L.isect_ids = take((size_t)max_isects * 8); // only written by rs_frame_export_isect_ids
+    L.flatten_ids = take((size_t)max_isects * 4);
+    L.bin_ws_bytes = rs_isect_sorted_workspace_bytes((int64_t)E, max_isects);
+    L.bin_ws = take(L.bin_ws_bytes);
     L.tile_offsets = take((size_t)C * tw * th * 4);
     L.last_ids = take((size_t)C * W * H * 4);
     L.total = o;
@@ -54,25 +52,17 @@ extern "C" uint64_t rs_frame_workspace_bytes(int32_t C, int32_t N, int32_t image
     return make_layout(C, N, image_width, image_height, tile_size, max_isects).total;
 }
 
-static int frame_end_bit(const rs_frame_args *a) {
-    const rs_project_fwd_args &p = a->proj;
-    const int tw = (p.image_width + p.tile_size - 1) / p.tile_size, th = (p.image_height + p.tile_size - 1) / p.tile_size;
-    return 32 + (int)rs_bit_width((uint32_t)(tw * th)) + (int)rs_bit_width((uint32_t)p.C);
-}
-
 extern "C" void *rs_frame_workspace_ptr(const rs_frame_args *a, int which) {
     if (a == nullptr || a->workspace == nullptr)
         return nullptr;
     const rs_project_fwd_args &p = a->proj;
     const FrameLayout L = make_layout(p.C, p.N, p.image_width, p.image_height, p.tile_size, a->max_isects);
     char *w = reinterpret_cast<char *>(a->workspace);
-    const int passes = (frame_end_bit(a) + 7) / 8;
-    const bool in_b = passes & 1;
     switch (which) {
     case 0:
-        return w + (in_b ? L.keys_b : L.keys_a);
+        return w + L.isect_ids;
     case 1:
-        return w + (in_b ? L.vals_b : L.vals_a);
+        return w + L.flatten_ids;
     case 2:
         return w + L.tile_offsets;
     case 3:
@@ -90,6 +80,39 @@ extern "C" void *rs_frame_workspace_ptr(const rs_frame_args *a, int which) {
     default:
         return nullptr;
     }
+}
+
+static void fill_isect(rs_isect_args &ia, const rs_project_fwd_args &p, const rs_frame_args *a, char *w,
+                       const FrameLayout &L) {
+    ia.n_elems = p.C * p.N;
+    ia.N = p.N;
+    ia.I = p.C;
+    ia.tile_size = p.tile_size;
+    ia.tile_width = (p.image_width + p.tile_size - 1) / p.tile_size;
+    ia.tile_height = (p.image_height + p.tile_size - 1) / p.tile_size;
+    ia.means2d = reinterpret_cast<const float *>(w + L.means2d);
+    ia.radii = reinterpret_cast<const int32_t *>(w + L.radii);
+    ia.depths = reinterpret_cast<const float *>(w + L.depths);
+    ia.tiles_per_gauss = reinterpret_cast<int32_t *>(w + L.tiles_per_gauss);
+    ia.n_isects = a->status;     // status[0]
+    ia.overflow = a->status + 1; // status[1]
+    ia.isect_ids = nullptr;      // 64-bit ids are not needed to composite; see rs_frame_export_isect_ids
+    ia.flatten_ids = reinterpret_cast<int32_t *>(w + L.flatten_ids);
+    ia.capacity = a->max_isects;
+}
+
+// Rebuilds the sorted 64-bit isect ids of the last frame rendered into this workspace (`meta["isect_ids"]`,
+// rendering.py:651-665): key = (image | tile) << 32 | depth bits, recovered from the offsets table and flatten ids.
+extern "C" int rs_frame_export_isect_ids(const rs_frame_args *a, rs_stream_t stream) {
+    RS_CHECK(a != nullptr && a->workspace != nullptr && a->status != nullptr, "rs_frame_export_isect_ids: null args");
+    const rs_project_fwd_args &p = a->proj;
+    const FrameLayout L = make_layout(p.C, p.N, p.image_width, p.image_height, p.tile_size, a->max_isects);
+    char *w = reinterpret_cast<char *>(a->workspace);
+    const int tw = (p.image_width + p.tile_size - 1) / p.tile_size, th = (p.image_height + p.tile_size - 1) / p.tile_size;
+    const int32_t *offsets = a->out_tile_offsets != nullptr ? a->out_tile_offsets : reinterpret_cast<const int32_t *>(w + L.tile_offsets);
+    return rs_isect_ids_from_offsets(offsets, reinterpret_cast<const int32_t *>(w + L.flatten_ids),
+                                     reinterpret_cast<const float *>(w + L.depths), a->max_isects, a->status, p.C, tw, th,
+                                     reinterpret_cast<int64_t *>(w + L.isect_ids), stream);
 }
 
 extern "C" int rs_render_frame(const rs_frame_args *a, rs_stream_t stream) {
@@ -122,42 +145,16 @@ extern "C" int rs_render_frame(const rs_frame_args *a, rs_stream_t stream) {
     if (int e = rs_project_fwd(&p, stream))
         return e;
 
-    rs_isect_args ia;
-    memset(&ia, 0, sizeof(ia));
-    ia.n_elems = p.C * p.N;
-    ia.N = p.N;
-    ia.I = p.C;
-    ia.tile_size = p.tile_size;
-    ia.tile_width = p.tile_width;
-    ia.tile_height = p.tile_height;
-    ia.means2d = p.means2d;
-    ia.radii = p.radii;
-    ia.depths = p.depths;
-    ia.tiles_per_gauss = p.tiles_per_gauss;
-    ia.block_sums = p.block_sums;
-    ia.n_isects = a->status;      // status[0]
-    ia.overflow = a->status + 1;  // status[1]
-    ia.isect_ids = reinterpret_cast<int64_t *>(w + L.keys_a);
-    ia.flatten_ids = reinterpret_cast<int32_t *>(w + L.vals_a);
-    ia.capacity = a->max_isects;
-    if (int e = rs_isect_scan(&ia, stream))
-        return e;
-    if (int e = rs_isect_emit(&ia, stream))
-        return e;
-
-    int32_t in_b = 0;
-    if (int e = rs_sort_pairs_u64_internal(a->max_isects, a->status, 0, frame_end_bit(a),
-                                           reinterpret_cast<uint64_t *>(w + L.keys_a),
-                                           reinterpret_cast<uint64_t *>(w + L.keys_b),
-                                           reinterpret_cast<int32_t *>(w + L.vals_a),
-                                           reinterpret_cast<int32_t *>(w + L.vals_b), w + L.sort_ws, L.sort_ws_bytes,
-                                           &in_b, s))
-        return e;
-    const int64_t *keys_sorted = reinterpret_cast<const int64_t *>(w + (in_b ? L.keys_b : L.keys_a));
-    const int32_t *vals_sorted = reinterpret_cast<const int32_t *>(w + (in_b ? L.vals_b : L.vals_a));
+    rs_isect_sorted_args sa;
+    memset(&sa, 0, sizeof(sa));
+    fill_isect(sa.isect, p, a, w, L);
     int32_t *offsets = a->out_tile_offsets != nullptr ? a->out_tile_offsets : reinterpret_cast<int32_t *>(w + L.tile_offsets);
-    if (int e = rs_isect_offsets(keys_sorted, a->max_isects, a->status, p.C, p.tile_width, p.tile_height, offsets, stream))
+    sa.tile_offsets = offsets;
+    sa.workspace = w + L.bin_ws;
+    sa.workspace_bytes = L.bin_ws_bytes;
+    if (int e = rs_isect_sorted(&sa, stream))
         return e;
+    const int32_t *vals_sorted = sa.isect.flatten_ids;
 
     rs_raster_fwd_args r;
     memset(&r, 0, sizeof(r));

@@ -183,10 +183,13 @@ __global__ void __launch_bounds__(RS_ISECT_THREADS) rs_isect_emit_kernel(const r
     }
 }
 
-// csrc/IntersectTile.cu:209-257
+// csrc/IntersectTile.cu:209-257.  KeyT = int64_t: full isect ids (image | tile | depth); KeyT = uint32_t: the
+// (image | tile) half alone, as kept by the depth-ordered binning path below.
+template <typename KeyT>
 __global__ void __launch_bounds__(256)
-rs_isect_offsets_kernel(const int64_t *__restrict__ isect_ids, int64_t n_bound, const int32_t *__restrict__ n_dev,
+rs_isect_offsets_kernel(const KeyT *__restrict__ isect_ids, int64_t n_bound, const int32_t *__restrict__ n_dev,
                         uint32_t I, uint32_t n_tiles, uint32_t tile_n_bits, int32_t *__restrict__ offsets) {
+    constexpr int HI = sizeof(KeyT) == 8 ? 32 : 0;
     const int64_t n_isects = (n_dev != nullptr) ? min((int64_t)*n_dev, n_bound) : n_bound;
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n_isects == 0) { // Intersect.cpp:273-276: offsets.fill_(0)
@@ -196,7 +199,7 @@ rs_isect_offsets_kernel(const int64_t *__restrict__ isect_ids, int64_t n_bound, 
     }
     if (idx >= n_isects)
         return;
-    const int64_t cur = isect_ids[idx] >> 32;
+    const int64_t cur = (int64_t)(isect_ids[idx] >> HI);
     const int64_t id_curr = (cur >> tile_n_bits) * n_tiles + (cur & ((1ll << tile_n_bits) - 1));
     if (idx == 0) {
         for (int64_t i = 0; i < id_curr + 1; ++i)
@@ -207,7 +210,7 @@ rs_isect_offsets_kernel(const int64_t *__restrict__ isect_ids, int64_t n_bound, 
             offsets[i] = (int32_t)n_isects;
     }
     if (idx > 0) {
-        const int64_t prev = isect_ids[idx - 1] >> 32;
+        const int64_t prev = (int64_t)(isect_ids[idx - 1] >> HI);
         if (prev == cur)
             return;
         const int64_t id_prev = (prev >> tile_n_bits) * n_tiles + (prev & ((1ll << tile_n_bits) - 1));
@@ -291,8 +294,311 @@ extern "C" int rs_isect_offsets(const int64_t *isect_ids_sorted, int64_t n_isect
     // a device-side count of zero needs enough threads to clear the table
     if (n_isects_dev != nullptr)
         grid = max(grid, (int64_t)rs_num_sms());
-    rs_isect_offsets_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(isect_ids_sorted, n_isects, n_isects_dev,
-                                                                             (uint32_t)I, n_tiles, tile_n_bits, offsets);
+    rs_isect_offsets_kernel<int64_t><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+        isect_ids_sorted, n_isects, n_isects_dev, (uint32_t)I, n_tiles, tile_n_bits, offsets);
     RS_LAUNCH_CHECK("rs_isect_offsets_kernel");
+    return 0;
+}
+
+// =====================================================================================================================
+// Depth-ordered binning: rs_isect_sorted.
+//
+// The reference sorts M 64-bit (image | tile | depth) keys with cub (csrc/IntersectTile.cu:296-339): ceil(46/8) = 6 LSD
+// passes over 12 B pairs for a 1080p frame.  The same order -- (image, tile, depth bits, flatten index), stable --
+// is produced here with far less traffic by sorting the two halves of the key separately:
+//   1. stable LSD sort of the E = I*N (depth bits, flatten index) pairs          4 passes over E 8-byte pairs
+//   2. count / scan / emit in that depth order: (image | tile) 32-bit keys, flatten-index values
+//   3. stable LSD sort of the M (image | tile, flatten index) pairs on the tile + image bits only
+//                                                                                 ceil(14/8) = 2 passes over M 8-byte pairs
+//   4. offsets from the sorted 32-bit keys; the 64-bit isect ids are rebuilt (tile key << 32 | depth bits of the
+//      flatten id) only when the caller asks for them.
+// Ties: equal depths keep ascending flatten index through 1 (stable), every Gaussian contributes at most one
+// intersection per tile, and 3 is stable, so equal (image, tile, depth) keys stay in ascending flatten-index order --
+// exactly the order the reference's stable sort of its emission order gives.
+// =====================================================================================================================
+int rs_sort_pairs_u32_internal(int64_t n_bound, const int32_t *n_dev, int begin_bit, int end_bit, uint32_t *keys_a,
+                               uint32_t *keys_b, int32_t *vals_a, int32_t *vals_b, void *workspace,
+                               uint64_t workspace_bytes, int32_t *result_in_b, cudaStream_t s);
+
+__global__ void __launch_bounds__(256)
+rs_bin_init_kernel(int64_t n_elems, const float *__restrict__ depths, uint32_t *__restrict__ keys,
+                   int32_t *__restrict__ elems) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_elems) {
+        keys[i] = __float_as_uint(depths[i]);
+        elems[i] = (int32_t)i;
+    }
+}
+
+// block sums of the tile counts taken in depth order
+__global__ void __launch_bounds__(RS_ISECT_THREADS)
+rs_bin_count_kernel(int64_t n_elems, const int32_t *__restrict__ elems, const int32_t *__restrict__ tiles_per_gauss,
+                    int32_t *__restrict__ block_sums) {
+    __shared__ int sums[8];
+    const int64_t base = (int64_t)blockIdx.x * RS_ISECT_BLOCK;
+    int mine = 0;
+#pragma unroll
+    for (int it = 0; it < RS_ISECT_BLOCK / RS_ISECT_THREADS; ++it) {
+        const int64_t i = base + it * RS_ISECT_THREADS + threadIdx.x;
+        if (i < n_elems)
+            mine += tiles_per_gauss[elems[i]];
+    }
+    const int s = rs_block_sum_256(mine, sums);
+    if (threadIdx.x == 0)
+        block_sums[blockIdx.x] = s;
+}
+
+struct BinEmitSmem {
+    int32_t excl[RS_ISECT_BLOCK + 1];
+    uint32_t rect[RS_ISECT_BLOCK];  // x0 | y0 << 16
+    uint32_t width[RS_ISECT_BLOCK]; // x1 - x0
+    uint32_t hi[RS_ISECT_BLOCK];    // image id << tile_n_bits
+    int32_t elem[RS_ISECT_BLOCK];
+    int32_t warp_tot[8];
+};
+
+__global__ void __launch_bounds__(RS_ISECT_THREADS)
+rs_bin_emit_kernel(const rs_isect_args a, const int32_t *__restrict__ elems, uint32_t tile_n_bits,
+                   uint32_t *__restrict__ tile_keys, int32_t *__restrict__ vals) {
+    __shared__ BinEmitSmem sm;
+    const int64_t base = (int64_t)blockIdx.x * RS_ISECT_BLOCK;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int cnt[4];
+    int tsum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int slot = threadIdx.x * 4 + k;
+        const int64_t i = base + slot;
+        int c = 0;
+        if (i < a.n_elems) {
+            const int32_t e = elems[i];
+            c = a.tiles_per_gauss[e];
+            if (c > 0) {
+                const int2 r = reinterpret_cast<const int2 *>(a.radii)[e];
+                const float2 m = reinterpret_cast<const float2 *>(a.means2d)[e];
+                const RsTileRect tr = rs_tile_rect(m.x, m.y, (float)r.x, (float)r.y, (uint32_t)a.tile_size,
+                                                   (uint32_t)a.tile_width, (uint32_t)a.tile_height);
+                sm.rect[slot] = tr.x0 | (tr.y0 << 16);
+                sm.width[slot] = tr.x1 - tr.x0;
+                const uint32_t iid = (a.image_ids != nullptr) ? (uint32_t)a.image_ids[e] : (uint32_t)(e / a.N);
+                sm.hi[slot] = iid << tile_n_bits;
+                sm.elem[slot] = e;
+            }
+        }
+        cnt[k] = c;
+        tsum += c;
+    }
+    int incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o)
+            incl += n;
+    }
+    if (lane == 31)
+        sm.warp_tot[warp] = incl;
+    __syncthreads();
+    int wbase = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w)
+        wbase += (w < warp) ? sm.warp_tot[w] : 0;
+    int run = wbase + incl - tsum;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        sm.excl[threadIdx.x * 4 + k] = run;
+        run += cnt[k];
+    }
+    if (threadIdx.x == RS_ISECT_THREADS - 1)
+        sm.excl[RS_ISECT_BLOCK] = run;
+    __syncthreads();
+
+    const int total = sm.excl[RS_ISECT_BLOCK];
+    const int64_t out_base = a.block_sums[blockIdx.x];
+    for (int j = threadIdx.x; j < total; j += RS_ISECT_THREADS) {
+        int lo = 0, hi = RS_ISECT_BLOCK;
+#pragma unroll
+        for (int step = 0; step < 10; ++step) {
+            const int mid = (lo + hi) >> 1;
+            if (sm.excl[mid] <= j)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const int slot = lo;
+        const uint32_t r = (uint32_t)(j - sm.excl[slot]);
+        const uint32_t w = sm.width[slot];
+        const uint32_t ty = (sm.rect[slot] >> 16) + r / w;
+        const uint32_t tx = (sm.rect[slot] & 0xffffu) + r % w;
+        const int64_t o = out_base + j;
+        if (o < a.capacity) {
+            tile_keys[o] = sm.hi[slot] | (ty * (uint32_t)a.tile_width + tx);
+            vals[o] = sm.elem[slot];
+        }
+    }
+}
+
+// isect_ids[i] = tile_key[i] << 32 | depth bits of flatten id i (csrc/IntersectTile.cu:95-108)
+__global__ void __launch_bounds__(256)
+rs_bin_keys64_kernel(int64_t n_bound, const int32_t *__restrict__ n_dev, const uint32_t *__restrict__ tile_keys,
+                     const int32_t *__restrict__ vals, const float *__restrict__ depths, int64_t *__restrict__ isect_ids) {
+    const int64_t n = (n_dev != nullptr) ? min((int64_t)*n_dev, n_bound) : n_bound;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        isect_ids[i] = ((int64_t)tile_keys[i] << 32) | (int64_t)__float_as_uint(depths[vals[i]]);
+}
+
+namespace {
+struct BinLayout {
+    size_t dkeys_a, dkeys_b, elems_a, elems_b, block_sums, tkeys_a, tkeys_b, vals_b, sort_ws, sort_ws_bytes, total;
+};
+inline size_t bin_align(size_t x) { return (x + 255) & ~(size_t)255; }
+BinLayout bin_layout(int64_t n_elems, int64_t capacity) {
+    BinLayout L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        size_t at = o;
+        o = bin_align(o + bytes);
+        return at;
+    };
+    const size_t E = (size_t)(n_elems > 0 ? n_elems : 1), M = (size_t)(capacity > 0 ? capacity : 1);
+    L.dkeys_a = take(E * 4);
+    L.dkeys_b = take(E * 4);
+    L.elems_a = take(E * 4);
+    L.elems_b = take(E * 4);
+    L.block_sums = take(((size_t)rs_isect_num_blocks((int64_t)E) + 1) * 4);
+    L.tkeys_a = take(M * 4);
+    L.tkeys_b = take(M * 4);
+    L.vals_b = take(M * 4);
+    const uint64_t w1 = rs_radix_sort_workspace_bytes((int64_t)E), w2 = rs_radix_sort_workspace_bytes((int64_t)M);
+    L.sort_ws_bytes = w1 > w2 ? w1 : w2;
+    L.sort_ws = take(L.sort_ws_bytes);
+    L.total = o;
+    return L;
+}
+} // namespace
+
+extern "C" uint64_t rs_isect_sorted_workspace_bytes(int64_t n_elems, int64_t capacity) {
+    if (n_elems < 0 || capacity < 0)
+        return 0;
+    return bin_layout(n_elems, capacity).total;
+}
+
+extern "C" int rs_isect_sorted(const rs_isect_sorted_args *b, rs_stream_t stream) {
+    RS_CHECK(b != nullptr, "rs_isect_sorted: null args");
+    const rs_isect_args *a = &b->isect;
+    if (int e = check_isect_args(a, "rs_isect_sorted"))
+        return e;
+    RS_CHECK(a->n_elems < ((int64_t)1 << 31), "rs_isect_sorted: too many elements");
+    RS_CHECK(a->capacity >= 0 && a->capacity < ((int64_t)1 << 31), "rs_isect_sorted: bad capacity");
+    RS_CHECK(a->n_isects != nullptr, "rs_isect_sorted: n_isects (device) required");
+    RS_CHECK(a->n_elems == 0 || (a->means2d && a->radii && a->depths && a->tiles_per_gauss),
+             "rs_isect_sorted: null input pointer");
+    RS_CHECK(a->capacity == 0 || a->flatten_ids != nullptr, "rs_isect_sorted: null flatten_ids");
+    RS_CHECK(a->image_ids != nullptr || a->N > 0 || a->n_elems == 0, "rs_isect_sorted: N required when not packed");
+    const BinLayout L = bin_layout(a->n_elems, a->capacity);
+    RS_CHECK(b->workspace != nullptr && b->workspace_bytes >= L.total, "rs_isect_sorted: workspace too small (%llu < %llu)",
+             (unsigned long long)b->workspace_bytes, (unsigned long long)L.total);
+    cudaStream_t s = (cudaStream_t)stream;
+    char *w = reinterpret_cast<char *>(b->workspace);
+    const uint32_t n_tiles = (uint32_t)(a->tile_width * a->tile_height);
+    const uint32_t tile_n_bits = rs_bit_width(n_tiles);
+    const uint32_t image_n_bits = rs_bit_width((uint32_t)a->I);
+    int32_t *block_sums = reinterpret_cast<int32_t *>(w + L.block_sums);
+    const int nb = rs_isect_num_blocks(a->n_elems);
+
+    // the tile sort ping-pongs between (tkeys_a, caller's flatten_ids) and (tkeys_b, vals_b); start on the side that makes
+    // the last pass land in the caller's flatten_ids
+    const int tile_bits = (int)(tile_n_bits + image_n_bits);
+    const int tile_passes = (tile_bits + 7) / 8;
+    uint32_t *tk_final = reinterpret_cast<uint32_t *>(w + L.tkeys_a), *tk_other = reinterpret_cast<uint32_t *>(w + L.tkeys_b);
+    int32_t *tv_final = a->flatten_ids, *tv_other = reinterpret_cast<int32_t *>(w + L.vals_b);
+    uint32_t *tk_start = (tile_passes & 1) ? tk_other : tk_final;
+    int32_t *tv_start = (tile_passes & 1) ? tv_other : tv_final;
+    const uint32_t *tkeys = tk_final;
+
+    const int32_t *elems = nullptr;
+    if (a->n_elems > 0) {
+        // 1. depth order: stable LSD sort of (depth bits, flatten index)
+        uint32_t *dk_a = reinterpret_cast<uint32_t *>(w + L.dkeys_a), *dk_b = reinterpret_cast<uint32_t *>(w + L.dkeys_b);
+        int32_t *el_a = reinterpret_cast<int32_t *>(w + L.elems_a), *el_b = reinterpret_cast<int32_t *>(w + L.elems_b);
+        rs_bin_init_kernel<<<rs_cdiv(a->n_elems, 256), 256, 0, s>>>(a->n_elems, a->depths, dk_a, el_a);
+        RS_LAUNCH_CHECK("rs_bin_init_kernel");
+        int32_t in_b = 0;
+        if (int e = rs_sort_pairs_u32_internal(a->n_elems, nullptr, 0, 32, dk_a, dk_b, el_a, el_b, w + L.sort_ws,
+                                               L.sort_ws_bytes, &in_b, s))
+            return e;
+        elems = in_b ? el_b : el_a;
+        // 2a. block sums of the tile counts in depth order
+        rs_bin_count_kernel<<<nb, RS_ISECT_THREADS, 0, s>>>(a->n_elems, elems, a->tiles_per_gauss, block_sums);
+        RS_LAUNCH_CHECK("rs_bin_count_kernel");
+    }
+    // 2b. exclusive block offsets, device-side total and overflow flag
+    rs_isect_scan_kernel<<<1, RS_SCAN_THREADS, 0, s>>>(block_sums, a->n_elems > 0 ? nb : 0, a->n_isects,
+                                                       a->capacity, a->overflow);
+    RS_LAUNCH_CHECK("rs_isect_scan_kernel");
+    if (a->n_elems > 0 && a->capacity > 0) {
+        // 2c. emission in depth order
+        rs_isect_args e = *a;
+        e.block_sums = block_sums;
+        rs_bin_emit_kernel<<<nb, RS_ISECT_THREADS, 0, s>>>(e, elems, tile_n_bits, tk_start, tv_start);
+        RS_LAUNCH_CHECK("rs_bin_emit_kernel");
+        // 3. stable sort on the (image | tile) bits only
+        int32_t in_b = 0;
+        if (int err = rs_sort_pairs_u32_internal(a->capacity, a->n_isects, 0, tile_bits, tk_start,
+                                                 (tile_passes & 1) ? tk_final : tk_other, tv_start,
+                                                 (tile_passes & 1) ? tv_final : tv_other, w + L.sort_ws, L.sort_ws_bytes,
+                                                 &in_b, s))
+            return err;
+    }
+    // 4. offsets (+ 64-bit ids on request)
+    if (b->tile_offsets != nullptr && (int64_t)a->I * n_tiles > 0) {
+        int64_t grid = (a->capacity + 255) / 256;
+        grid = max(grid, (int64_t)rs_num_sms());
+        rs_isect_offsets_kernel<uint32_t><<<(unsigned)grid, 256, 0, s>>>(tkeys, a->capacity, a->n_isects, (uint32_t)a->I,
+                                                                        n_tiles, tile_n_bits, b->tile_offsets);
+        RS_LAUNCH_CHECK("rs_isect_offsets_kernel");
+    }
+    if (a->isect_ids != nullptr && a->capacity > 0) {
+        rs_bin_keys64_kernel<<<rs_cdiv(a->capacity, 256), 256, 0, s>>>(a->capacity, a->n_isects, tkeys, a->flatten_ids,
+                                                                       a->depths, a->isect_ids);
+        RS_LAUNCH_CHECK("rs_bin_keys64_kernel");
+    }
+    return 0;
+}
+
+// Sorted 64-bit isect ids recovered from (offsets, sorted flatten ids, depths): entry i belongs to the last (image, tile)
+// whose offset is <= i.  Used to export `meta["isect_ids"]` from the frame path, which never materialises 64-bit keys.
+__global__ void __launch_bounds__(256)
+rs_isect_ids_from_offsets_kernel(const int32_t *__restrict__ offsets, const int32_t *__restrict__ flatten_ids,
+                                 const float *__restrict__ depths, int64_t n_bound, const int32_t *__restrict__ n_dev,
+                                 uint32_t n_total_tiles, uint32_t n_tiles, uint32_t tile_n_bits,
+                                 int64_t *__restrict__ isect_ids) {
+    const int64_t n = (n_dev != nullptr) ? min((int64_t)*n_dev, n_bound) : n_bound;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    uint32_t lo = 0, hi = n_total_tiles; // invariant: offsets[lo] <= i, (hi == n_total_tiles or offsets[hi] > i)
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if ((int64_t)offsets[mid] <= i)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    const uint32_t image = lo / n_tiles, tile = lo - image * n_tiles;
+    const int64_t hi32 = ((int64_t)image << tile_n_bits) | (int64_t)tile;
+    isect_ids[i] = (hi32 << 32) | (int64_t)__float_as_uint(depths[flatten_ids[i]]);
+}
+
+int rs_isect_ids_from_offsets(const int32_t *offsets, const int32_t *flatten_ids, const float *depths, int64_t n_bound,
+                              const int32_t *n_dev, int32_t I, int32_t tile_width, int32_t tile_height,
+                              int64_t *isect_ids, rs_stream_t stream) {
+    RS_CHECK(offsets && flatten_ids && depths && isect_ids, "rs_isect_ids_from_offsets: null pointer");
+    if (n_bound <= 0)
+        return 0;
+    const uint32_t n_tiles = (uint32_t)(tile_width * tile_height);
+    rs_isect_ids_from_offsets_kernel<<<rs_cdiv(n_bound, 256), 256, 0, (cudaStream_t)stream>>>(
+        offsets, flatten_ids, depths, n_bound, n_dev, (uint32_t)I * n_tiles, n_tiles, rs_bit_width(n_tiles), isect_ids);
+    RS_LAUNCH_CHECK("rs_isect_ids_from_offsets_kernel");
     return 0;
 }

@@ -57,6 +57,8 @@ sort_hist_kernel(const KeyT *__restrict__ keys, int64_t n_bound, const int32_t *
                  uint32_t mask, int32_t *__restrict__ hist, int nblocks) {
     __shared__ int h[SORT_WARPS][RADIX];
     const int64_t n = sort_count(n_bound, n_dev);
+    if ((int64_t)blockIdx.x * SORT_TILE >= n)
+        return; // the grid is sized for n_bound; rows are only scanned up to ceil(n / SORT_TILE)
     const int warp = threadIdx.x >> 5;
 #pragma unroll
     for (int w = 0; w < SORT_WARPS; ++w)
@@ -83,16 +85,18 @@ sort_hist_kernel(const KeyT *__restrict__ keys, int64_t n_bound, const int32_t *
 
 // grid = RADIX CTAs; CTA d scans row d of hist (nblocks entries) in place (exclusive) and writes bin_tot[d].
 __global__ void __launch_bounds__(SORT_THREADS)
-sort_scan_rows_kernel(int32_t *__restrict__ hist, int nblocks, int32_t *__restrict__ bin_tot) {
+sort_scan_rows_kernel(int32_t *__restrict__ hist, int nblocks, int64_t n_bound, const int32_t *__restrict__ n_dev,
+                      int32_t *__restrict__ bin_tot) {
     __shared__ int wsum[SORT_WARPS];
     int32_t *row = hist + (size_t)blockIdx.x * nblocks;
+    const int nb_eff = (int)((sort_count(n_bound, n_dev) + SORT_TILE - 1) / SORT_TILE);
     int carry = 0;
-    for (int start = 0; start < nblocks; start += SORT_THREADS) {
+    for (int start = 0; start < nb_eff; start += SORT_THREADS) {
         const int i = start + threadIdx.x;
-        const int v = (i < nblocks) ? row[i] : 0;
+        const int v = (i < nb_eff) ? row[i] : 0;
         int tot;
         const int ex = block_excl_scan_256(v, wsum, &tot);
-        if (i < nblocks)
+        if (i < nb_eff)
             row[i] = carry + ex;
         carry += tot;
     }
@@ -236,7 +240,7 @@ static int radix_sort_impl(int64_t n_bound, const int32_t *n_dev, int begin_bit,
         const uint32_t mask = (1u << bits) - 1u;
         sort_hist_kernel<KeyT><<<nb, SORT_THREADS, 0, s>>>(kin, n_bound, n_dev, shift, mask, hist, nb);
         RS_LAUNCH_CHECK("sort_hist_kernel");
-        sort_scan_rows_kernel<<<RADIX, SORT_THREADS, 0, s>>>(hist, nb, bin_tot);
+        sort_scan_rows_kernel<<<RADIX, SORT_THREADS, 0, s>>>(hist, nb, n_bound, n_dev, bin_tot);
         RS_LAUNCH_CHECK("sort_scan_rows_kernel");
         sort_scatter_kernel<KeyT><<<nb, SORT_THREADS, smem, s>>>(kin, vin, kout, vout, n_bound, n_dev, shift, mask,
                                                                  hist, nb, bin_tot);
@@ -260,6 +264,13 @@ extern "C" int rs_radix_sort_pairs(const rs_sort_args *a, rs_stream_t stream) {
     return radix_sort_impl<uint64_t>(a->n, a->n_dev, a->begin_bit, a->end_bit, reinterpret_cast<uint64_t *>(a->keys_a),
                                      reinterpret_cast<uint64_t *>(a->keys_b), a->vals_a, a->vals_b, a->workspace,
                                      a->workspace_bytes, a->result_in_b, (cudaStream_t)stream);
+}
+
+int rs_sort_pairs_u32_internal(int64_t n_bound, const int32_t *n_dev, int begin_bit, int end_bit, uint32_t *keys_a,
+                               uint32_t *keys_b, int32_t *vals_a, int32_t *vals_b, void *workspace,
+                               uint64_t workspace_bytes, int32_t *result_in_b, cudaStream_t s) {
+    return radix_sort_impl<uint32_t>(n_bound, n_dev, begin_bit, end_bit, keys_a, keys_b, vals_a, vals_b, workspace,
+                                     workspace_bytes, result_in_b, s);
 }
 
 // internal entry for the fused frame path

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RS_ABI_VERSION 3
+#define RS_ABI_VERSION 4
 
 /* gsplat/cuda/include/Common.h:46-51 (CameraModelType) */
 enum { RS_PINHOLE = 0, RS_ORTHO = 1, RS_FISHEYE = 2, RS_FTHETA = 3 };
@@ -34,7 +34,7 @@ typedef void *rs_stream_t; /* cudaStream_t */
 int rs_abi_version(void);
 const char *rs_last_error(void);
 /* sizeof() of every args struct, for binding self-checks: which = 0 project_fwd, 1 project_bwd, 2 isect,
- * 3 sort, 4 raster_fwd, 5 raster_bwd, 6 frame.  Returns 0 for an unknown id. */
+ * 3 sort, 4 raster_fwd, 5 raster_bwd, 6 frame, 7 rigid, 8 isect_sorted.  Returns 0 for an unknown id. */
 uint64_t rs_sizeof_args(int which);
 /* number of kernels this library has launched in this process (all threads); bench.py reports its delta over the
  * timed region as `gpu_launches`. */
@@ -155,6 +155,21 @@ int rs_isect_scan(const rs_isect_args *a, rs_stream_t stream);
 int rs_isect_count_total(const rs_isect_args *a, rs_stream_t stream, int64_t *n_isects_host);
 int rs_isect_emit(const rs_isect_args *a, rs_stream_t stream);
 
+/* rs_isect_sorted: emission + sort + offsets in one sync-free call, producing exactly what `intersect_tile(sort=True)`
+ * + `intersect_offset` produce (same key order, same tie order) without ever sorting 64-bit keys: the (depth, flatten
+ * index) pairs are ordered first, intersections are emitted in that order and only their (image | tile) bits are sorted
+ * (see csrc/isect.cu).  Inputs: isect.{means2d,radii,depths,tiles_per_gauss (from rs_isect_count or rs_project_fwd),
+ * image_ids}; outputs: isect.flatten_ids [capacity] (sorted), isect.isect_ids [capacity] (sorted, optional),
+ * tile_offsets (optional), *isect.n_isects and *isect.overflow (device).  isect.block_sums is not used. */
+typedef struct {
+    rs_isect_args isect;
+    int32_t *tile_offsets;       /* [I,tile_height,tile_width] out, optional */
+    void *workspace;             /* rs_isect_sorted_workspace_bytes(n_elems, capacity) bytes */
+    uint64_t workspace_bytes;
+} rs_isect_sorted_args;
+uint64_t rs_isect_sorted_workspace_bytes(int64_t n_elems, int64_t capacity);
+int rs_isect_sorted(const rs_isect_sorted_args *a, rs_stream_t stream);
+
 typedef struct {
     int64_t n;                   /* number of pairs if n_dev == NULL, else capacity (grid sizing bound) */
     const int32_t *n_dev;        /* optional device count (sync-free path): only the first *n_dev pairs are sorted */
@@ -245,6 +260,9 @@ int rs_render_frame(const rs_frame_args *a, rs_stream_t stream);
 /* device pointers into a frame workspace, for tests and `meta`: which = 0 isect_ids(sorted), 1 flatten_ids(sorted),
  * 2 tile_offsets, 3 last_ids, 4 tiles_per_gauss.  Valid after rs_render_frame on the same workspace geometry. */
 void *rs_frame_workspace_ptr(const rs_frame_args *a, int which);
+/* The frame path never materialises 64-bit keys; this rebuilds the sorted isect ids of the last frame (which = 0 above)
+ * from its offsets table, flatten ids and depths.  Enqueued on `stream`, no sync. */
+int rs_frame_export_isect_ids(const rs_frame_args *a, rs_stream_t stream);
 
 #ifdef __cplusplus
 }
