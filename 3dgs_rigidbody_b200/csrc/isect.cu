@@ -191,31 +191,33 @@ rs_isect_offsets_kernel(const KeyT *__restrict__ isect_ids, int64_t n_bound, con
                         uint32_t I, uint32_t n_tiles, uint32_t tile_n_bits, int32_t *__restrict__ offsets) {
     constexpr int HI = sizeof(KeyT) == 8 ? 32 : 0;
     const int64_t n_isects = (n_dev != nullptr) ? min((int64_t)*n_dev, n_bound) : n_bound;
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (n_isects == 0) { // Intersect.cpp:273-276: offsets.fill_(0)
-        for (int64_t i = idx; i < (int64_t)I * n_tiles; i += (int64_t)gridDim.x * blockDim.x)
+        for (int64_t i = first; i < (int64_t)I * n_tiles; i += stride)
             offsets[i] = 0;
         return;
     }
-    if (idx >= n_isects)
-        return;
-    const int64_t cur = (int64_t)(isect_ids[idx] >> HI);
-    const int64_t id_curr = (cur >> tile_n_bits) * n_tiles + (cur & ((1ll << tile_n_bits) - 1));
-    if (idx == 0) {
-        for (int64_t i = 0; i < id_curr + 1; ++i)
-            offsets[i] = 0;
-    }
-    if (idx == n_isects - 1) {
-        for (int64_t i = id_curr + 1; i < (int64_t)I * n_tiles; ++i)
-            offsets[i] = (int32_t)n_isects;
-    }
-    if (idx > 0) {
-        const int64_t prev = (int64_t)(isect_ids[idx - 1] >> HI);
-        if (prev == cur)
-            return;
-        const int64_t id_prev = (prev >> tile_n_bits) * n_tiles + (prev & ((1ll << tile_n_bits) - 1));
-        for (int64_t i = id_prev + 1; i < id_curr + 1; ++i)
-            offsets[i] = (int32_t)idx;
+    // grid-stride: the grid is sized for the SM count, not for n_bound (which may be a loose capacity)
+    for (int64_t idx = first; idx < n_isects; idx += stride) {
+        const int64_t cur = (int64_t)(isect_ids[idx] >> HI);
+        const int64_t id_curr = (cur >> tile_n_bits) * n_tiles + (cur & ((1ll << tile_n_bits) - 1));
+        if (idx == 0) {
+            for (int64_t i = 0; i < id_curr + 1; ++i)
+                offsets[i] = 0;
+        }
+        if (idx == n_isects - 1) {
+            for (int64_t i = id_curr + 1; i < (int64_t)I * n_tiles; ++i)
+                offsets[i] = (int32_t)n_isects;
+        }
+        if (idx > 0) {
+            const int64_t prev = (int64_t)(isect_ids[idx - 1] >> HI);
+            if (prev != cur) {
+                const int64_t id_prev = (prev >> tile_n_bits) * n_tiles + (prev & ((1ll << tile_n_bits) - 1));
+                for (int64_t i = id_prev + 1; i < id_curr + 1; ++i)
+                    offsets[i] = (int32_t)idx;
+            }
+        }
     }
 }
 
@@ -288,11 +290,11 @@ extern "C" int rs_isect_offsets(const int64_t *isect_ids_sorted, int64_t n_isect
     RS_CHECK(n_isects == 0 || isect_ids_sorted != nullptr, "rs_isect_offsets: null isect_ids");
     const uint32_t n_tiles = (uint32_t)(tile_width * tile_height);
     const uint32_t tile_n_bits = rs_bit_width(n_tiles);
+    // grid-stride kernel: at most 8 CTAs per SM; at least one CTA per SM so that a device-side count of zero still
+    // clears the table quickly
     int64_t grid = (n_isects + 255) / 256;
-    if (grid < 1)
-        grid = 1;
-    // a device-side count of zero needs enough threads to clear the table
-    if (n_isects_dev != nullptr)
+    grid = min(grid, (int64_t)rs_num_sms() * 8);
+    if (grid < 1 || n_isects_dev != nullptr)
         grid = max(grid, (int64_t)rs_num_sms());
     rs_isect_offsets_kernel<int64_t><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
         isect_ids_sorted, n_isects, n_isects_dev, (uint32_t)I, n_tiles, tile_n_bits, offsets);
@@ -552,7 +554,7 @@ extern "C" int rs_isect_sorted(const rs_isect_sorted_args *b, rs_stream_t stream
     }
     // 4. offsets (+ 64-bit ids on request)
     if (b->tile_offsets != nullptr && (int64_t)a->I * n_tiles > 0) {
-        int64_t grid = (a->capacity + 255) / 256;
+        int64_t grid = min((a->capacity + 255) / 256, (int64_t)rs_num_sms() * 8);
         grid = max(grid, (int64_t)rs_num_sms());
         rs_isect_offsets_kernel<uint32_t><<<(unsigned)grid, 256, 0, s>>>(tkeys, a->capacity, a->n_isects, (uint32_t)a->I,
                                                                         n_tiles, tile_n_bits, b->tile_offsets);

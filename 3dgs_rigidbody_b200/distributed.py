@@ -1,0 +1,116 @@
+"""Gaussian-sharded rendering: the one exchange step of the path (BASELINE.json config c5).
+
+Scheme (the reference's, gsplat/rendering.py:366-381 + 527-611 on top of gsplat/distributed.py:10-257): every rank owns a
+shard of the Gaussians and an equal number of cameras.  Cameras are all-gathered, every rank projects ITS Gaussians to
+ALL cameras, and the projected splats are sent to the rank that owns the camera; binning and compositing are then purely
+local.  Backward is the transposed exchange.
+
+What differs from the reference: it ships each attribute in its own all-to-all (radii; then means2d, depths, conics,
+opacities, colours as a list; then the two id tensors, plus a count exchange when packed).  Here every projected splat is
+ONE row -- [means2d 2 | depth 1 | conic 3 | opacity 1 | colour D] float32 -- sent by ONE differentiable
+`all_to_all_single`, and one more for the integer columns (radii, and the ids when packed), so a frame costs two NCCL
+collectives over NVLink instead of four to eight.  Frames / cameras sharding (c2, c4) needs no collective at all and does
+not come through here.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.distributed.nn.functional as dist_fn
+from torch import Tensor
+
+
+def _world() -> Tuple[int, int]:
+    assert dist.is_available() and dist.is_initialized(), "distributed=True needs an initialised process group"
+    return dist.get_rank(), dist.get_world_size()
+
+
+class GaussianShardExchange:
+    """Bookkeeping + collectives of one distributed `rasterization()` call."""
+
+    def __init__(self, n_local: int, c_local: int, device: torch.device, group=None):
+        self.group = group
+        self.rank, self.world = _world()
+        self.device = device
+        mine = torch.tensor([n_local, c_local], dtype=torch.int64, device=device)
+        table = torch.empty(self.world * 2, dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(table, mine, group=group)
+        table = table.reshape(self.world, 2).cpu()
+        self.n_per_rank: List[int] = table[:, 0].tolist()
+        self.c_per_rank: List[int] = table[:, 1].tolist()
+        # the reference requires the same number of cameras on every rank (rendering.py:374-375)
+        assert len(set(self.c_per_rank)) == 1, f"every rank must own the same number of cameras, got {self.c_per_rank}"
+        self.local_cameras = c_local
+        self.total_cameras = sum(self.c_per_rank)
+        self.n_local = n_local
+        self.gaussian_base = sum(self.n_per_rank[: self.rank])  # first global index of this rank's shard
+
+    # ---- cameras ---------------------------------------------------------------------------------------------------------
+    def gather_cameras(self, viewmats: Tensor, Ks: Tensor) -> Tuple[Tensor, Tensor]:
+        """[C_local, ...] on every rank -> [C_total, ...] in rank order (differentiable w.r.t. the local cameras)."""
+        if self.world == 1:
+            return viewmats, Ks
+        flat = torch.cat([viewmats.reshape(self.local_cameras, 16), Ks.reshape(self.local_cameras, 9)], dim=1).contiguous()
+        parts = dist_fn.all_gather(flat, group=self.group)
+        every = torch.cat(list(parts), dim=0)
+        return every[:, :16].reshape(-1, 4, 4), every[:, 16:].reshape(-1, 3, 3)
+
+    # ---- projected splats ---------------------------------------------------------------------------------------------------
+    def _swap(self, rows: Tensor, send: List[int], recv: List[int], differentiable: bool) -> Tensor:
+        rows = rows.contiguous()
+        if self.world == 1:
+            return rows
+        if differentiable:
+            out = torch.empty((sum(recv),) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+            return dist_fn.all_to_all_single(out, rows, output_split_sizes=recv, input_split_sizes=send, group=self.group)
+        out = torch.empty((sum(recv),) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+        dist.all_to_all_single(out, rows, output_split_sizes=recv, input_split_sizes=send, group=self.group)
+        return out
+
+    def exchange(self, packed: bool, radii: Tensor, means2d: Tensor, depths: Tensor, conics: Tensor, opacities: Tensor,
+                 colors: Tensor, camera_ids: Optional[Tensor], gaussian_ids: Optional[Tensor]):
+        """Moves every projected splat to the rank owning its camera.
+
+        Dense (packed=False): inputs are [C_total, N_local, ...]; outputs are [C_local, N_total, ...] with the Gaussians of
+        rank 0 first, then rank 1, ... (so global Gaussian index = shard base + local index).
+        Packed: inputs are [nnz, ...] rows ordered by camera; outputs are the rows of this rank's cameras from every source
+        rank in rank order, `camera_ids` made local and `gaussian_ids` made global.
+        Returns (radii, means2d, depths, conics, opacities, colors, camera_ids, gaussian_ids)."""
+        D = colors.shape[-1]
+        Cl = self.local_cameras
+        if packed:
+            owner = torch.div(camera_ids, Cl, rounding_mode="floor")
+            send_t = torch.bincount(owner, minlength=self.world)[: self.world]
+            recv_t = torch.empty_like(send_t)
+            if self.world > 1:
+                dist.all_to_all_single(recv_t, send_t, group=self.group)
+            else:
+                recv_t.copy_(send_t)
+            send, recv = send_t.tolist(), recv_t.tolist()  # the one host sync of the packed exchange
+            nnz = means2d.shape[0]
+            fl = torch.cat([means2d, depths.reshape(nnz, 1), conics, opacities.reshape(nnz, 1), colors.reshape(nnz, D)],
+                           dim=1)
+            ints = torch.stack([radii[:, 0].long(), radii[:, 1].long(), camera_ids - owner * Cl,
+                                gaussian_ids + self.gaussian_base], dim=1)
+            fl = self._swap(fl, send, recv, True)
+            ints = self._swap(ints, send, recv, False)
+            return (ints[:, :2].to(torch.int32).contiguous(), fl[:, 0:2], fl[:, 2], fl[:, 3:6], fl[:, 6], fl[:, 7:],
+                    ints[:, 2].contiguous(), ints[:, 3].contiguous())
+
+        Ct, Nl = self.total_cameras, self.n_local
+        assert means2d.shape[:2] == (Ct, Nl), means2d.shape
+        send = [c * Nl for c in self.c_per_rank]
+        recv = [Cl * n for n in self.n_per_rank]
+        fl = torch.cat([means2d, depths.unsqueeze(-1), conics, opacities.unsqueeze(-1), colors.expand(Ct, Nl, D)],
+                       dim=-1).reshape(Ct * Nl, 7 + D)
+        fl = self._swap(fl, send, recv, True)
+        ri = self._swap(radii.reshape(Ct * Nl, 2), send, recv, False)
+
+        def regroup(t: Tensor) -> Tensor:  # chunks [Cl * N_s, k] per source s -> [Cl, sum N_s, k]
+            chunks = torch.split(t, recv, dim=0)
+            return torch.cat([c.reshape(Cl, n, t.shape[-1]) for c, n in zip(chunks, self.n_per_rank)], dim=1)
+
+        fl, ri = regroup(fl), regroup(ri)
+        return (ri.contiguous(), fl[..., 0:2], fl[..., 2], fl[..., 3:6], fl[..., 6], fl[..., 7:], None, None)

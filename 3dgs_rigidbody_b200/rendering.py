@@ -1,16 +1,21 @@
-"""`rasterization()`: the API boundary of the hot path, signature-compatible with gsplat.rendering.rasterization()
-(gsplat/rendering.py:33-770), so it drops into main.py:328-339 and examples/simple_trainer.py:601-624 unchanged.
+"""`rasterization()`: the API boundary of the hot path.
 
-Extra optional keyword arguments (defaults reproduce the reference exactly):
-    cluster_ids  int32 [N]   body index per Gaussian (< 0 = static)
-    body_quats   [K, 4]      wxyz rotation of each body (normalised internally, main.py:207)
-    body_trans   [K, 3]      translation of each body
-    body_centers [K, 3]      pivot of each body (apply_transform() uses the body's mean centre, main.py:210)
-With them the per-body `apply_transform()` calls of the animation loop (main.py:366-400) collapse into the projection
-kernel: no clones of the splat tensors, no extra pass over HBM.
+Call-compatible with gsplat.rendering.rasterization() (gsplat/rendering.py:33-770: same positional / keyword arguments,
+defaults, return triple and `meta` keys), so the reference's callers -- main.py:328-339, examples/simple_trainer.py:601-624,
+examples/simple_viewer.py:60-73 -- run unchanged.  Four optional keyword arguments are new; left at None the behaviour is
+the reference's:
 
-Out of scope (raise NotImplementedError): with_ut / with_eval3d / lens distortion / rolling shutter (the 3DGUT path,
-SURVEY.md section 2 rows 17) -- `with_ut=False` on every hot-path call of the reference.
+    cluster_ids  int32 [N]   body index of every Gaussian (< 0: static background)
+    body_quats   [K, 4]      per-body rotation, wxyz, normalised inside the kernel (main.py:207)
+    body_trans   [K, 3]      per-body translation
+    body_centers [K, 3]      per-body pivot (apply_transform() rotates about the body's mean centre, main.py:210)
+
+They replace the animation loop's per-body `apply_transform()` calls (main.py:366-400): the pose table is consumed inside
+the projection kernel, so no splat tensor is cloned and no extra pass over HBM is made.
+
+The body is organised as five stages -- project, shade, (exchange), bin, composite -- each a thin call into the operator
+layer (`wrapper.py` -> `_C.py` -> C ABI).  Not supported (NotImplementedError): the 3DGUT options (`with_ut`,
+`with_eval3d`, distortion coefficients, rolling shutter); no hot-path caller of the reference enables them.
 """
 from __future__ import annotations
 
@@ -25,6 +30,93 @@ from typing_extensions import Literal
 from .rigid import make_rigid
 from .sh import spherical_harmonics
 from .wrapper import fully_fused_projection, isect_offset_encode, isect_tiles, rasterize_to_pixels
+
+_DEPTH_MODES = ("D", "ED", "RGB+D", "RGB+ED")
+_MODES = ("RGB",) + _DEPTH_MODES
+
+
+class _Dims:
+    """Leading batch dims [...], B = prod(...), N Gaussians, C cameras of one call."""
+
+    def __init__(self, means: Tensor, viewmats: Tensor):
+        self.batch = tuple(means.shape[:-2])
+        self.nb = len(self.batch)
+        self.B = math.prod(self.batch)
+        self.N = means.shape[-2]
+        self.C = viewmats.shape[-3]
+
+    def expect(self, t: Tensor, tail: Tuple[int, ...], what: str) -> None:
+        assert tuple(t.shape) == self.batch + tail, f"{what}: {tuple(t.shape)}"
+
+
+def _reject_3dgut(with_ut, with_eval3d, radial, tangential, prism, ftheta, shutter, viewmats_rs) -> None:
+    if with_ut or with_eval3d:
+        raise NotImplementedError("with_ut / with_eval3d (3DGUT) are outside this framework's hot path")
+    global_shutter = shutter is None or getattr(shutter, "name", str(shutter)) == "GLOBAL"
+    if any(x is not None for x in (radial, tangential, prism, ftheta, viewmats_rs)) or not global_shutter:
+        raise AssertionError("Distortion and rolling shutter are only supported with `with_ut=True`.")
+
+
+def _check_colors(d: _Dims, colors: Tensor, sh_degree: Optional[int], distributed: bool) -> bool:
+    """Validates the colour tensor; returns True when it carries a camera dimension."""
+    extra = 2 if sh_degree is None else 3  # trailing dims after the (C,) N part: [D] or [K, 3]
+    per_camera = colors.dim() == d.nb + extra + 1
+    lead = d.batch + ((d.C, d.N) if per_camera else (d.N,))
+    assert colors.dim() in (d.nb + extra, d.nb + extra + 1) and tuple(colors.shape[: len(lead)]) == lead, colors.shape
+    if sh_degree is not None:
+        assert colors.shape[-1] == 3 and (sh_degree + 1) ** 2 <= colors.shape[-2], colors.shape
+    if distributed:
+        assert not per_camera, "Distributed mode only supports per-Gaussian colors."
+    return per_camera
+
+
+def _view_dependent_colors(d, colors, per_camera, sh_degree, means, rigid, viewmats, radii, packed, rows):
+    """SH colours for the view directions of the (moved) Gaussians: rendering.py:491-525.  apply_transform() moves the
+    means but leaves sh0 / shN untouched (main.py:200-226), so directions follow the moved means and the coefficients are
+    NOT rotated with the body -- reproduced here on purpose."""
+    if rigid is not None:
+        from .torch_ref import apply_rigid_torch
+
+        means = apply_rigid_torch(means, None, rigid)[0]
+    cam_origin = torch.linalg.inv(viewmats)[..., :3, 3]  # [..., C, 3]
+    visible = (radii > 0).all(dim=-1)
+    if packed:
+        b, c, g = rows
+        dirs = means.reshape(d.B, d.N, 3)[b, g] - cam_origin.reshape(d.B, d.C, 3)[b, c]
+        coeffs = (colors.reshape(d.B, d.C, d.N, -1, 3)[b, c, g] if per_camera
+                  else colors.reshape(d.B, d.N, -1, 3)[b, g])
+    else:
+        dirs = means.unsqueeze(-3) - cam_origin.unsqueeze(-2)  # [..., C, N, 3]
+        coeffs = colors if per_camera else colors.unsqueeze(-4).expand(d.batch + (d.C,) + tuple(colors.shape[-3:]))
+    rgb = spherical_harmonics(sh_degree, dirs, coeffs, masks=visible)
+    return (rgb + 0.5).clamp_min(0.0)
+
+
+def _plain_colors(d, colors, per_camera, packed, rows):
+    if packed:
+        b, c, g = rows
+        return colors.reshape(d.B, d.C, d.N, -1)[b, c, g] if per_camera else colors.reshape(d.B, d.N, -1)[b, g]
+    if per_camera:
+        return colors
+    # a stride-0 view: the compositing kernels read one row per Gaussian for every camera (no [C,N,D] copy)
+    return colors.unsqueeze(-3).expand(d.batch + (d.C,) + tuple(colors.shape[-2:]))
+
+
+def _attach_depth(render_mode, colors, depths, backgrounds, lead_shape):
+    """RGB+D / RGB+ED append the depth as one more channel, D / ED render it alone (rendering.py:614-629); the extra
+    channel's background is zero."""
+    if render_mode not in _DEPTH_MODES:
+        return colors, backgrounds
+    depth_col = depths.unsqueeze(-1)
+    zero_bg = None if backgrounds is None else torch.zeros(lead_shape + (1,), device=backgrounds.device,
+                                                           dtype=backgrounds.dtype)
+    if render_mode.startswith("RGB"):
+        colors = torch.cat([colors, depth_col], dim=-1)
+        if backgrounds is not None:
+            backgrounds = torch.cat([backgrounds, zero_bg], dim=-1)
+    else:
+        colors, backgrounds = depth_col, zero_bg
+    return colors, backgrounds
 
 
 def rasterization(
@@ -68,217 +160,112 @@ def rasterization(
     body_trans: Optional[Tensor] = None,  # [K, 3]
     body_centers: Optional[Tensor] = None,  # [K, 3]
 ) -> Tuple[Tensor, Tensor, Dict]:
-    """Rasterize a set of 3D Gaussians (N) to a batch of image planes (C).
+    """Rasterize N 3D Gaussians to C image planes.
 
-    Returns (render_colors [..., C, H, W, X], render_alphas [..., C, H, W, 1], meta) with the reference's `meta` keys
-    (rendering.py:455-468, 651-665); `meta["means2d"]` is a grad-tracking non-leaf ([..., C, N, 2] or [nnz, 2]).
+    Returns (render_colors [..., C, H, W, X], render_alphas [..., C, H, W, 1], meta); `meta` carries the reference's keys
+    (rendering.py:455-468, 651-665) and `meta["means2d"]` is a grad-tracking non-leaf ([..., C, N, 2], or [nnz, 2] when
+    packed) so that `retain_grad()` / `.absgrad` work as in the reference's training loop.
     """
-    meta: Dict = {}
-
-    batch_dims = means.shape[:-2]
-    num_batch_dims = len(batch_dims)
-    B = math.prod(batch_dims)
-    N = means.shape[-2]
-    C = viewmats.shape[-3]
-    I = B * C
-    device = means.device
-    assert means.shape == batch_dims + (N, 3), means.shape
-    if covars is None:
-        assert quats.shape == batch_dims + (N, 4), quats.shape
-        assert scales.shape == batch_dims + (N, 3), scales.shape
+    # ---- 0. validation -------------------------------------------------------------------------------------------------
+    d = _Dims(means, viewmats)
+    d.expect(means, (d.N, 3), "means")
+    d.expect(opacities, (d.N,), "opacities")
+    d.expect(viewmats, (d.C, 4, 4), "viewmats")
+    d.expect(Ks, (d.C, 3, 3), "Ks")
+    if covars is not None:
+        d.expect(covars, (d.N, 3, 3), "covars")
+        rows6, cols6 = (0, 0, 0, 1, 1, 2), (0, 1, 2, 1, 2, 2)
+        covars = covars[..., rows6, cols6]  # upper triangle, as the projection operator expects
+        quats = scales = None
     else:
-        assert covars.shape == batch_dims + (N, 3, 3), covars.shape
-        quats, scales = None, None
-        tri_indices = ([0, 0, 0, 1, 1, 2], [0, 1, 2, 1, 2, 2])
-        covars = covars[..., tri_indices[0], tri_indices[1]]
-    assert opacities.shape == batch_dims + (N,), opacities.shape
-    assert viewmats.shape == batch_dims + (C, 4, 4), viewmats.shape
-    assert Ks.shape == batch_dims + (C, 3, 3), Ks.shape
-    assert render_mode in ["RGB", "D", "ED", "RGB+D", "RGB+ED"], render_mode
+        d.expect(quats, (d.N, 4), "quats")
+        d.expect(scales, (d.N, 3), "scales")
+    assert render_mode in _MODES, render_mode
     assert tile_size == 16, "tile_size must be 16 (the only value the reference exercises, rendering.py:184-185)"
-
-    if with_ut or with_eval3d:
-        raise NotImplementedError("with_ut / with_eval3d (3DGUT) are outside this framework's hot path")
-    if (radial_coeffs is not None or tangential_coeffs is not None or thin_prism_coeffs is not None
-            or ftheta_coeffs is not None or viewmats_rs is not None
-            or (rolling_shutter is not None and getattr(rolling_shutter, "name", str(rolling_shutter)) != "GLOBAL")):
-        raise AssertionError("Distortion and rolling shutter are only supported with `with_ut=True`.")
-
-    if sh_degree is None:
-        assert (colors.dim() == num_batch_dims + 2 and colors.shape[:-1] == batch_dims + (N,)) or (
-            colors.dim() == num_batch_dims + 3 and colors.shape[:-1] == batch_dims + (C, N)
-        ), colors.shape
-        if distributed:
-            assert colors.dim() == num_batch_dims + 2, "Distributed mode only supports per-Gaussian colors."
-    else:
-        assert (
-            colors.dim() == num_batch_dims + 3 and colors.shape[:-2] == batch_dims + (N,) and colors.shape[-1] == 3
-        ) or (
-            colors.dim() == num_batch_dims + 4 and colors.shape[:-2] == batch_dims + (C, N) and colors.shape[-1] == 3
-        ), colors.shape
-        assert (sh_degree + 1) ** 2 <= colors.shape[-2], colors.shape
-        if distributed:
-            assert colors.dim() == num_batch_dims + 3, "Distributed mode only supports per-Gaussian colors."
-    if absgrad:
-        assert not distributed, "AbsGrad is not supported in distributed mode."
-
+    _reject_3dgut(with_ut, with_eval3d, radial_coeffs, tangential_coeffs, thin_prism_coeffs, ftheta_coeffs,
+                  rolling_shutter, viewmats_rs)
+    per_camera_colors = _check_colors(d, colors, sh_degree, distributed)
+    assert not (absgrad and distributed), "AbsGrad is not supported in distributed mode."
     rigid = make_rigid(cluster_ids, body_quats, body_trans, body_centers)
     if rigid is not None:
-        assert cluster_ids.shape == (N,), cluster_ids.shape
+        assert tuple(cluster_ids.shape) == (d.N,), cluster_ids.shape
+    device = means.device
 
+    shard = None
     if distributed:
-        from .distributed import all_gather_int32, all_gather_tensor_list
+        # Gaussian-sharded scene (rendering.py:366-381): every rank projects its Gaussians to ALL cameras, then the
+        # projected splats travel to the rank that owns the camera.
+        from .distributed import GaussianShardExchange
 
-        assert batch_dims == (), "Distributed mode does not support batch dimensions"
-        world_rank = torch.distributed.get_rank()
-        world_size = torch.distributed.get_world_size()
-        N_world = all_gather_int32(world_size, N, device=device)
-        C_world = [C] * world_size
-        viewmats, Ks = all_gather_tensor_list(world_size, [viewmats, Ks])
-        C = len(viewmats)
+        assert d.batch == (), "Distributed mode does not support batch dimensions"
+        shard = GaussianShardExchange(d.N, d.C, device)
+        viewmats, Ks = shard.gather_cameras(viewmats, Ks)
+        d.C = viewmats.shape[0]
 
-    proj_results = fully_fused_projection(
-        means, covars, quats, scales, viewmats, Ks, width, height,
-        eps2d=eps2d, packed=packed, near_plane=near_plane, far_plane=far_plane, radius_clip=radius_clip,
-        sparse_grad=sparse_grad, calc_compensations=(rasterize_mode == "antialiased"), camera_model=camera_model,
-        opacities=opacities, rigid=rigid,
-    )
-
+    # ---- 1. project (rigid transform fused in) ---------------------------------------------------------------------------
+    projected = fully_fused_projection(
+        means, covars, quats, scales, viewmats, Ks, width, height, eps2d=eps2d, packed=packed, near_plane=near_plane,
+        far_plane=far_plane, radius_clip=radius_clip, sparse_grad=sparse_grad,
+        calc_compensations=(rasterize_mode == "antialiased"), camera_model=camera_model, opacities=opacities, rigid=rigid)
     if packed:
-        batch_ids, camera_ids, gaussian_ids, radii, means2d, depths, conics, compensations = proj_results
-        opacities = opacities.view(B, N)[batch_ids, gaussian_ids]  # [nnz]
-        image_ids = batch_ids * C + camera_ids
+        batch_ids, camera_ids, gaussian_ids, radii, means2d, depths, conics, compensations = projected
+        rows = (batch_ids, camera_ids, gaussian_ids)
+        alpha_in = opacities.reshape(d.B, d.N)[batch_ids, gaussian_ids]  # [nnz]
+        image_ids = batch_ids * d.C + camera_ids
     else:
-        radii, means2d, depths, conics, compensations = proj_results
-        opacities = torch.broadcast_to(opacities[..., None, :], batch_dims + (C, N))  # [..., C, N]
-        batch_ids, camera_ids, gaussian_ids = None, None, None
-        image_ids = None
-
+        radii, means2d, depths, conics, compensations = projected
+        batch_ids = camera_ids = gaussian_ids = image_ids = rows = None
+        alpha_in = opacities.unsqueeze(-2).expand(d.batch + (d.C, d.N))  # stride-0 view, consumed without a copy
     if compensations is not None:
-        opacities = opacities * compensations
+        alpha_in = alpha_in * compensations
+    meta: Dict = dict(batch_ids=batch_ids, camera_ids=camera_ids, gaussian_ids=gaussian_ids, radii=radii, means2d=means2d,
+                      depths=depths, conics=conics, opacities=alpha_in)
 
-    meta.update(
-        {
-            "batch_ids": batch_ids,
-            "camera_ids": camera_ids,
-            "gaussian_ids": gaussian_ids,
-            "radii": radii,
-            "means2d": means2d,
-            "depths": depths,
-            "conics": conics,
-            "opacities": opacities,
-        }
-    )
-
+    # ---- 2. shade ----------------------------------------------------------------------------------------------------------
     if sh_degree is None:
-        if packed:
-            if colors.dim() == num_batch_dims + 2:
-                colors = colors.view(B, N, -1)[batch_ids, gaussian_ids]
-            else:
-                colors = colors.view(B, C, N, -1)[batch_ids, camera_ids, gaussian_ids]
-        else:
-            if colors.dim() == num_batch_dims + 2:
-                colors = torch.broadcast_to(colors[..., None, :, :], batch_dims + (C, N, colors.shape[-1]))
+        shaded = _plain_colors(d, colors, per_camera_colors, packed, rows)
     else:
-        # apply_transform() moves the means but leaves sh0/shN untouched (main.py:200-226), so the view directions of
-        # rendering.py:491-525 follow the MOVED means while the SH coefficients are not rotated with the body.
-        world_means = means if rigid is None else _transformed_means(means, rigid)
-        campos = torch.inverse(viewmats)[..., :3, 3]  # [..., C, 3]
+        shaded = _view_dependent_colors(d, colors, per_camera_colors, sh_degree, means, rigid, viewmats, radii, packed, rows)
+
+    # ---- 2b. exchange (Gaussian-sharded scenes only) ---------------------------------------------------------------------
+    n_images = d.B * d.C
+    if shard is not None:
+        out = shard.exchange(packed, radii, means2d, depths, conics, alpha_in, shaded, camera_ids, gaussian_ids)
+        radii, means2d, depths, conics, alpha_in, shaded, camera_ids, gaussian_ids = out
+        d.C = shard.local_cameras
+        n_images = d.C
         if packed:
-            dirs = world_means.view(B, N, 3)[batch_ids, gaussian_ids] - campos.view(B, C, 3)[batch_ids, camera_ids]
-            masks = (radii > 0).all(dim=-1)
-            if colors.dim() == num_batch_dims + 3:
-                shs = colors.view(B, N, -1, 3)[batch_ids, gaussian_ids]
-            else:
-                shs = colors.view(B, C, N, -1, 3)[batch_ids, camera_ids, gaussian_ids]
-            colors = spherical_harmonics(sh_degree, dirs, shs, masks=masks)
-        else:
-            dirs = world_means[..., None, :, :] - campos[..., None, :]  # [..., C, N, 3]
-            masks = (radii > 0).all(dim=-1)
-            if colors.dim() == num_batch_dims + 3:
-                shs = torch.broadcast_to(colors[..., None, :, :, :], batch_dims + (C, N) + colors.shape[-2:])
-            else:
-                shs = colors
-            colors = spherical_harmonics(sh_degree, dirs, shs, masks=masks)
-        colors = torch.clamp_min(colors + 0.5, 0.0)
+            image_ids = camera_ids
 
-    if distributed:
-        from .distributed import exchange_projected
+    shaded, backgrounds = _attach_depth(render_mode, shaded, depths, backgrounds, d.batch + (d.C,))
 
-        (radii, means2d, depths, conics, opacities, colors, camera_ids, gaussian_ids, C) = exchange_projected(
-            world_rank, world_size, packed, N, N_world, C_world, radii, means2d, depths, conics, opacities, colors,
-            camera_ids, gaussian_ids,
-        )
-        if packed:
-            image_ids = camera_ids  # B == 1 in distributed mode
-        I = C
-
-    if render_mode in ["RGB+D", "RGB+ED"]:
-        colors = torch.cat((colors, depths[..., None]), dim=-1)
-        if backgrounds is not None:
-            backgrounds = torch.cat(
-                [backgrounds, torch.zeros(batch_dims + (C, 1), device=backgrounds.device)], dim=-1
-            )
-    elif render_mode in ["D", "ED"]:
-        colors = depths[..., None]
-        if backgrounds is not None:
-            backgrounds = torch.zeros(batch_dims + (C, 1), device=backgrounds.device)
-
-    tile_width = math.ceil(width / float(tile_size))
-    tile_height = math.ceil(height / float(tile_size))
+    # ---- 3. bin: tile intersection, ordering, per-tile offsets ------------------------------------------------------------
+    tile_w, tile_h = -(-width // tile_size), -(-height // tile_size)
     tiles_per_gauss, isect_ids, flatten_ids = isect_tiles(
-        means2d, radii, depths, tile_size, tile_width, tile_height,
-        segmented=segmented, packed=packed, n_images=I, image_ids=image_ids, gaussian_ids=gaussian_ids,
-    )
-    isect_offsets = isect_offset_encode(isect_ids, I, tile_width, tile_height)
-    isect_offsets = isect_offsets.reshape(batch_dims + (C, tile_height, tile_width))
+        means2d, radii, depths, tile_size, tile_w, tile_h, segmented=segmented, packed=packed, n_images=n_images,
+        image_ids=image_ids, gaussian_ids=gaussian_ids)
+    isect_offsets = isect_offset_encode(isect_ids, n_images, tile_w, tile_h).reshape(d.batch + (d.C, tile_h, tile_w))
+    meta.update(tile_width=tile_w, tile_height=tile_h, tiles_per_gauss=tiles_per_gauss, isect_ids=isect_ids,
+                flatten_ids=flatten_ids, isect_offsets=isect_offsets, width=width, height=height, tile_size=tile_size,
+                n_batches=d.B, n_cameras=d.C)
 
-    meta.update(
-        {
-            "tile_width": tile_width,
-            "tile_height": tile_height,
-            "tiles_per_gauss": tiles_per_gauss,
-            "isect_ids": isect_ids,
-            "flatten_ids": flatten_ids,
-            "isect_offsets": isect_offsets,
-            "width": width,
-            "height": height,
-            "tile_size": tile_size,
-            "n_batches": B,
-            "n_cameras": C,
-        }
-    )
+    # ---- 4. composite (channels beyond `channel_chunk` in slices; only the first slice's alpha is kept, 668-720) ----------
+    n_ch = shaded.shape[-1]
+    pieces, render_alphas = [], None
+    step = max(int(channel_chunk), 1)
+    for lo in range(0, n_ch, step):
+        hi = min(lo + step, n_ch)
+        whole = lo == 0 and hi == n_ch
+        part = shaded if whole else shaded[..., lo:hi]
+        part_bg = backgrounds if (backgrounds is None or whole) else backgrounds[..., lo:hi]
+        img, alpha = rasterize_to_pixels(means2d, conics, part, alpha_in, width, height, tile_size, isect_offsets,
+                                         flatten_ids, backgrounds=part_bg, packed=packed, absgrad=absgrad)
+        pieces.append(img)
+        if render_alphas is None:
+            render_alphas = alpha
+    render_colors = pieces[0] if len(pieces) == 1 else torch.cat(pieces, dim=-1)
 
-    if colors.shape[-1] > channel_chunk:
-        n_chunks = (colors.shape[-1] + channel_chunk - 1) // channel_chunk
-        render_colors, render_alphas = [], []
-        for i in range(n_chunks):
-            colors_chunk = colors[..., i * channel_chunk : (i + 1) * channel_chunk]
-            backgrounds_chunk = (
-                backgrounds[..., i * channel_chunk : (i + 1) * channel_chunk] if backgrounds is not None else None
-            )
-            render_colors_, render_alphas_ = rasterize_to_pixels(
-                means2d, conics, colors_chunk, opacities, width, height, tile_size, isect_offsets, flatten_ids,
-                backgrounds=backgrounds_chunk, packed=packed, absgrad=absgrad,
-            )
-            render_colors.append(render_colors_)
-            render_alphas.append(render_alphas_)
-        render_colors = torch.cat(render_colors, dim=-1)
-        render_alphas = render_alphas[0]  # discard the rest
-    else:
-        render_colors, render_alphas = rasterize_to_pixels(
-            means2d, conics, colors, opacities, width, height, tile_size, isect_offsets, flatten_ids,
-            backgrounds=backgrounds, packed=packed, absgrad=absgrad,
-        )
-    if render_mode in ["ED", "RGB+ED"]:
-        render_colors = torch.cat(
-            [render_colors[..., :-1], render_colors[..., -1:] / render_alphas.clamp(min=1e-10)], dim=-1
-        )
+    if render_mode in ("ED", "RGB+ED"):  # expected depth = accumulated depth / accumulated alpha (760-768)
+        expected = render_colors[..., -1:] / render_alphas.clamp(min=1e-10)
+        render_colors = torch.cat([render_colors[..., :-1], expected], dim=-1)
     return render_colors, render_alphas, meta
-
-
-def _transformed_means(means: Tensor, rigid) -> Tensor:
-    """Means after the rigid transform, in torch (only used for SH view directions)."""
-    from .torch_ref import apply_rigid_torch
-
-    return apply_rigid_torch(means, None, rigid)[0]

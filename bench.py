@@ -121,6 +121,11 @@ def domino_poses_np(n_bodies=N_BODIES, frames=None, centers=None):
     return q, t
 
 
+def frames_of_rank(rank, world, count, start=0):
+    """Animation frames rendered by `rank`: start + rank, start + rank + world, ... (`count` of them, modulo 240)."""
+    return [(start + rank + world * i) % N_FRAMES for i in range(count)]
+
+
 def make_domino_scene(n_gauss=N_GAUSS, n_bodies=N_BODIES, device="cuda:0", **kw):
     import torch
 
@@ -373,7 +378,7 @@ def ours_arm(args):
     q_all, t_all = torch.from_numpy(q_np).to(dev), torch.from_numpy(t_np).to(dev)  # [240,K,4], [240,K,3]
     fr = rs.FrameRenderer(sc["means"], sc["quats"], sc["scales"], sc["opacities"], sc["colors"], WIDTH, HEIGHT,
                           cluster_ids=sc["cluster_ids"], body_centers=sc["body_centers"], max_isects=args.max_isects)
-    frames = [(rank + world * i) % N_FRAMES for i in range(args.warmup + args.steps)]
+    frames = frames_of_rank(rank, world, args.warmup + args.steps)
 
     def barrier():
         if dist is not None:
