@@ -325,6 +325,7 @@ def _fill_raster(a, means2d, conics, colors, opacities, backgrounds, masks, imag
     a.backgrounds, a.masks = _ptr(backgrounds), _ptr(masks)
     a.tile_offsets, a.flatten_ids = _ptr(tile_offsets), _ptr(flatten_ids)
     a.attr_mod_colors, a.attr_mod_opacities = attr_mod_colors, attr_mod_opacities
+    a.n_rows = means2d.numel() // 2
     return I
 
 
@@ -355,6 +356,9 @@ def rasterize_to_pixels_3dgs_fwd(
         alphas = torch.empty(image_dims + (image_height, image_width, 1), dtype=torch.float32, device=dev)
         last_ids = torch.empty(image_dims + (image_height, image_width), dtype=torch.int32, device=dev)
         a.render_colors, a.render_alphas, a.last_ids = _ptr(renders), _ptr(alphas), _ptr(last_ids)
+        # staging records (32 B per projected splat), packed by rs_raster_fwd itself on this path
+        records = torch.empty((max(a.n_rows, 1), 8), dtype=torch.float32, device=dev)
+        a.records, a.records_ready = records.data_ptr(), 0
         _lib.check(lib.rs_raster_fwd(ctypes.byref(a), _stream()))
     return renders, alphas, last_ids
 

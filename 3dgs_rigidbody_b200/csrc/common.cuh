@@ -94,6 +94,36 @@ __device__ __forceinline__ int32_t rs_tile_count(int32_t radius_x, int32_t radiu
     return (int32_t)((r.y1 - r.y0) * (r.x1 - r.x0));
 }
 
+// Conservative half extents (in pixels) of {p : sigma(p) <= ln(255 * opacity)}, i.e. of the region where a splat can
+// reach alpha >= 1/255 (RasterizeToPixels3DGSFwd.cu:148-149 skips everything else).  3e38 = "cannot cull",
+// -3e38 = "can never contribute".  Used to build the per-splat compositing record.
+__device__ __forceinline__ void rs_cull_extents(float a, float b, float c, float op, float &ex, float &ey) {
+    ex = 3e38f;
+    ey = 3e38f;
+    const float det = a * c - b * b;
+    const float L = logf(op * 255.f);
+    if (op < RS_ALPHA_THRESHOLD * 0.999f) { // alpha <= op < 1/255 whenever sigma >= 0
+        ex = -3e38f;
+        ey = -3e38f;
+        return;
+    }
+    if (a > 0.f && c > 0.f && det > 0.f && a * c <= 256.f * det && L == L) {
+        const float Lm = L + 1e-3f * (1.f + fabsf(L));
+        if (Lm <= 0.f) {
+            ex = 0.25f;
+            ey = 0.25f;
+            return;
+        }
+        const float inv = 2.f * Lm / det;
+        const float hx = sqrtf(inv * c) * 1.0005f + 0.25f;
+        const float hy = sqrtf(inv * a) * 1.0005f + 0.25f;
+        if (hx < 4096.f && hy < 4096.f) {
+            ex = hx;
+            ey = hy;
+        }
+    }
+}
+
 // block-wide sum of one int per thread (blockDim.x == RS_ISECT_THREADS), result valid in thread 0
 __device__ __forceinline__ int rs_block_sum_256(int v, int *smem8) {
 #pragma unroll

@@ -12,7 +12,7 @@ int rs_isect_ids_from_offsets(const int32_t *offsets, const int32_t *flatten_ids
 
 namespace {
 struct FrameLayout {
-    size_t radii, means2d, depths, conics, tiles_per_gauss, block_sums, isect_ids, flatten_ids, bin_ws, bin_ws_bytes,
+    size_t radii, means2d, depths, conics, records, tiles_per_gauss, block_sums, isect_ids, flatten_ids, bin_ws, bin_ws_bytes,
         tile_offsets, last_ids, total;
 };
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -31,6 +31,7 @@ FrameLayout make_layout(int32_t C, int32_t N, int32_t W, int32_t H, int32_t tile
     L.means2d = take(E * 2 * 4);
     L.depths = take(E * 4);
     L.conics = take(E * 3 * 4);
+    L.records = take(E * 8 * 4);
     L.tiles_per_gauss = take(E * 4);
     L.block_sums = take(((size_t)rs_isect_num_blocks((int64_t)E) + 1) * 4);
     L.isect_ids = take((size_t)max_isects * 8); // only written by rs_frame_export_isect_ids
@@ -140,6 +141,7 @@ extern "C" int rs_render_frame(const rs_frame_args *a, rs_stream_t stream) {
     p.means2d = reinterpret_cast<float *>(w + L.means2d);
     p.depths = reinterpret_cast<float *>(w + L.depths);
     p.conics = reinterpret_cast<float *>(w + L.conics);
+    p.records = reinterpret_cast<float *>(w + L.records);
     p.tiles_per_gauss = reinterpret_cast<int32_t *>(w + L.tiles_per_gauss);
     p.block_sums = reinterpret_cast<int32_t *>(w + L.block_sums);
     if (int e = rs_project_fwd(&p, stream))
@@ -181,5 +183,8 @@ extern "C" int rs_render_frame(const rs_frame_args *a, rs_stream_t stream) {
     r.render_colors = a->render_colors;
     r.render_alphas = a->render_alphas;
     r.last_ids = reinterpret_cast<int32_t *>(w + L.last_ids);
+    r.records = p.records;
+    r.records_ready = 1;
+    r.n_rows = (int64_t)p.C * p.N;
     return rs_raster_fwd(&r, stream);
 }

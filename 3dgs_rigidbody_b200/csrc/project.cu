@@ -139,6 +139,13 @@ rs_project_fwd_kernel(const rs_project_fwd_args a) {
         a.conics[idx * 3 + 2] = o.cc;
         if (a.compensations != nullptr)
             a.compensations[idx] = o.comp;
+        if (a.records != nullptr && ok) { // compositing record (see raster_fwd.cu); culled rows are never referenced
+            float ex, ey;
+            rs_cull_extents(o.ca, o.cb, o.cc, opac, ex, ey);
+            float4 *rec = reinterpret_cast<float4 *>(a.records) + idx * 2;
+            rec[0] = make_float4(o.mx, o.my, opac, o.ca);
+            rec[1] = make_float4(o.cb, o.cc, ex, ey);
+        }
         if (a.tiles_per_gauss != nullptr) {
             int cnt = rs_tile_count(o.rx, o.ry, o.mx, o.my, (uint32_t)a.tile_size, (uint32_t)a.tile_width,
                                     (uint32_t)a.tile_height);

@@ -2,13 +2,17 @@
 // Replaces csrc/RasterizeToPixels3DGSFwd.cu:17-187 (host side csrc/Rasterization.cpp:20-115).
 //
 // One CTA (256 threads) per 16x16 tile, like the reference, but:
-//   * each warp owns an 8x4 pixel sub-block and, per batch of 256 staged splats, tests 32 splats at a time (one per
-//     lane) against its sub-block with a conservative ellipse bounding box derived from the conic and the opacity
-//     (alpha >= 1/255  <=>  sigma <= ln(255 * opacity)); a ballot gives the list of splats that can touch the
-//     sub-block and only those are evaluated.  A skipped (pixel, splat) pair is one the reference would have
-//     `continue`d on (alpha < 1/255), so results are unchanged while ~2/3 of the evaluations disappear.
-//   * colours are staged in shared memory with the geometry (the reference re-reads them from global per pixel).
-//   * a warp whose 32 pixels are saturated stops evaluating (the reference only stops per CTA).
+//   * splats are staged as 32-byte RECORDS {x, y, opacity, conic a | conic b, conic c, cull half-extents} that the
+//     projection kernel (frame path) or a small pack kernel (operator path) writes once per (camera, Gaussian); the
+//     compositing kernel copies them global -> shared with cp.async (LDGSTS, no register staging) through a ring of
+//     RAST_STAGES batches of 256 splats, so the gathers of batch b+2 are in flight while batch b is composited and
+//     there is ONE block barrier per batch (the reference: load, barrier, composite, barrier, nothing in flight);
+//   * each warp owns an 8x4 pixel sub-block and tests 32 staged splats at a time (one per lane) against it with the
+//     record's conservative bounding box of {alpha >= 1/255}; a ballot gives the splats that can touch the sub-block
+//     and only those are evaluated.  A skipped (pixel, splat) pair is one the reference would have `continue`d on
+//     (alpha < 1/255), so results are unchanged while most of the evaluations disappear;
+//   * colours are staged in shared memory with the geometry (the reference re-reads them from global per pixel);
+//   * a warp whose 32 pixels are saturated stops evaluating (the reference only stops per CTA);
 //   * any channel count is handled (template capacity >= channels, > 32 in chunks) -- no python-side padding.
 // The per-pixel arithmetic reproduces the reference's compiled instruction sequence (FMUL/FFMA association read from
 // its SASS: sigma = fma(dy, b*dx, 0.5 * fma(dx, a*dx, (c*dy)*dy)), alpha = min(.999, op * ex2(-sigma*log2e)), FTZ) so
@@ -18,44 +22,49 @@
 
 #define RAST_THREADS 256
 
-template <int CDIM> struct RastSmem {
-    float4 xyoa[RAST_THREADS]; // x, y, opacity, conic.a
-    float4 bcee[RAST_THREADS]; // conic.b, conic.c, half-extent x, half-extent y (cull box)
-    float color[CDIM][RAST_THREADS]; // channel-major: conflict-free staging, broadcast reads
-};
-
-// conservative half extents of {p : sigma(p) <= ln(255 op)}; 3e38 = "cannot cull", -3e38 = "can never contribute"
-__device__ __forceinline__ void rs_cull_extents(float a, float b, float c, float op, float &ex, float &ey) {
-    ex = 3e38f;
-    ey = 3e38f;
-    const float det = a * c - b * b;
-    const float L = logf(op * 255.f);
-    if (op < RS_ALPHA_THRESHOLD * 0.999f) { // alpha <= op < 1/255 whenever sigma >= 0
-        ex = -3e38f;
-        ey = -3e38f;
-        return;
-    }
-    if (a > 0.f && c > 0.f && det > 0.f && a * c <= 256.f * det && L == L) {
-        const float Lm = L + 1e-3f * (1.f + fabsf(L));
-        if (Lm <= 0.f) {
-            ex = 0.25f;
-            ey = 0.25f;
-            return;
-        }
-        const float inv = 2.f * Lm / det;
-        const float hx = sqrtf(inv * c) * 1.0005f + 0.25f;
-        const float hy = sqrtf(inv * a) * 1.0005f + 0.25f;
-        if (hx < 4096.f && hy < 4096.f) {
-            ex = hx;
-            ey = hy;
-        }
-    }
+__device__ __forceinline__ void rs_cp_async16(void *smem, const void *gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void rs_cp_async4(void *smem, const void *gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void rs_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void rs_cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-template <int CDIM>
+// records [n, 8] from the operator-level tensors (means2d, conics, opacities)
+__global__ void __launch_bounds__(256) rs_raster_pack_kernel(const rs_raster_fwd_args a, const int64_t n_rows) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_rows)
+        return;
+    const float2 xy = reinterpret_cast<const float2 *>(a.means2d)[g];
+    const float ca = a.conics[g * 3 + 0], cb = a.conics[g * 3 + 1], cc = a.conics[g * 3 + 2];
+    const float op = a.opacities[a.attr_mod_opacities > 0 ? g % a.attr_mod_opacities : g];
+    float ex, ey;
+    rs_cull_extents(ca, cb, cc, op, ex, ey);
+    float4 *rec = reinterpret_cast<float4 *>(a.records) + g * 2;
+    rec[0] = make_float4(xy.x, xy.y, op, ca);
+    rec[1] = make_float4(cb, cc, ex, ey);
+}
+
+// CP = colour row pitch in shared memory (floats): CDIM rounded up to a multiple of 4 so rows can be read as float4
+template <int CDIM> struct RastCfg {
+    static constexpr int CP = (CDIM + 3) & ~3;
+    static constexpr int STAGES = (CDIM <= 8) ? 3 : 2;
+    static constexpr int STAGE_FLOATS = RAST_THREADS * (8 + CP);
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_FLOATS * sizeof(float);
+};
+
+template <int CDIM, bool VEC_COLORS>
 __global__ void __launch_bounds__(RAST_THREADS)
 rs_raster_fwd_kernel(const rs_raster_fwd_args a, const int ch_off, const int ch_cnt) {
-    __shared__ RastSmem<CDIM> sm;
+    using Cfg = RastCfg<CDIM>;
+    constexpr int CP = Cfg::CP;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ __align__(16) float rast_smem[];
 
     const uint32_t tiles_per_image = (uint32_t)(a.tile_width * a.tile_height);
     const uint32_t image_id = blockIdx.x / tiles_per_image;
@@ -98,90 +107,139 @@ rs_raster_fwd_kernel(const rs_raster_fwd_args a, const int ch_off, const int ch_
     const float bx0 = (float)sub_x + 0.5f, bx1 = (float)sub_x + 7.5f;
     const float by0 = (float)sub_y + 0.5f, by1 = (float)sub_y + 3.5f;
 
+    const float4 *records = reinterpret_cast<const float4 *>(a.records);
+    // thread tr stages splat (batch_start + tr) of a batch: record (2 x 16 B) + colour row into stage `st`
+    auto issue = [&](int32_t g, int st) {
+        float *base = rast_smem + (size_t)st * Cfg::STAGE_FLOATS;
+        float4 *r0 = reinterpret_cast<float4 *>(base) + tr;
+        float4 *r1 = reinterpret_cast<float4 *>(base + RAST_THREADS * 4) + tr;
+        float *col = base + RAST_THREADS * 8 + tr * CP;
+        rs_cp_async16(r0, records + (size_t)g * 2);
+        rs_cp_async16(r1, records + (size_t)g * 2 + 1);
+        const int32_t gc = a.attr_mod_colors > 0 ? g % a.attr_mod_colors : g;
+        const float *cp = a.colors + (size_t)gc * a.channels + ch_off;
+        if (VEC_COLORS) { // rows are 16-byte aligned and ch_cnt == CP
+#pragma unroll
+            for (int k = 0; k < CP; k += 4)
+                rs_cp_async16(col + k, cp + k);
+        } else {
+#pragma unroll
+            for (int k = 0; k < CDIM; ++k)
+                if (k < ch_cnt)
+                    rs_cp_async4(col + k, cp + k);
+        }
+    };
+
+    // pad columns of the colour rows are never copied; zero them once so the unpredicated FMAs below add 0
+    // (only the pad columns: the async copies own the others)
+    if (!VEC_COLORS) {
+        for (int s = 0; s < STAGES; ++s) {
+            float *col = rast_smem + (size_t)s * Cfg::STAGE_FLOATS + RAST_THREADS * 8 + tr * CP;
+#pragma unroll
+            for (int k = 0; k < CP; ++k)
+                if (k >= ch_cnt)
+                    col[k] = 0.f;
+        }
+    }
+
+    // prologue: batches 0 .. STAGES-2 in flight, id of batch STAGES-1 prefetched
+    int32_t g_next = -1;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        const int32_t idx = range_start + RAST_THREADS * s + tr;
+        if (s < num_batches && idx < range_end)
+            issue(a.flatten_ids[idx], s);
+        rs_cp_async_commit();
+    }
+    {
+        const int32_t idx = range_start + RAST_THREADS * (STAGES - 1) + tr;
+        if (idx < range_end)
+            g_next = a.flatten_ids[idx];
+    }
+
     float T = 1.0f;
     uint32_t cur_idx = 0;
     bool done = !inside;
     bool warp_done = __all_sync(0xffffffffu, done);
-    float pix_out[CDIM];
+    float pix_out[CP];
 #pragma unroll
-    for (int k = 0; k < CDIM; ++k)
+    for (int k = 0; k < CP; ++k)
         pix_out[k] = 0.f;
 
     for (int b = 0; b < num_batches; ++b) {
-        // also the barrier that protects the staging buffers from the previous batch
+        rs_cp_async_wait<STAGES - 2>(); // this thread's copies of batch b have landed
+        // everyone's copies of batch b are visible, and everyone is finished with batch b-1 (whose stage is refilled next)
         if (__syncthreads_count(done) >= RAST_THREADS)
             break;
+        {
+            const int nb = b + STAGES - 1;
+            if (g_next >= 0)
+                issue(g_next, nb % STAGES);
+            rs_cp_async_commit();
+            const int32_t idx = range_start + RAST_THREADS * (nb + 1) + tr;
+            g_next = (idx < range_end) ? a.flatten_ids[idx] : -1;
+        }
+        if (warp_done)
+            continue;
 
         const int32_t batch_start = range_start + RAST_THREADS * b;
-        const int32_t idx = batch_start + tr;
-        if (idx < range_end) {
-            const int32_t g = a.flatten_ids[idx];
-            const float2 xy = reinterpret_cast<const float2 *>(a.means2d)[g];
-            const int32_t go = a.attr_mod_opacities > 0 ? g % a.attr_mod_opacities : g;
-            const int32_t gc = a.attr_mod_colors > 0 ? g % a.attr_mod_colors : g;
-            const float op = a.opacities[go];
-            const float ca = a.conics[(size_t)g * 3 + 0];
-            const float cb = a.conics[(size_t)g * 3 + 1];
-            const float cc = a.conics[(size_t)g * 3 + 2];
-            float ex, ey;
-            rs_cull_extents(ca, cb, cc, op, ex, ey);
-            sm.xyoa[tr] = make_float4(xy.x, xy.y, op, ca);
-            sm.bcee[tr] = make_float4(cb, cc, ex, ey);
-            const float *cp = a.colors + (size_t)gc * a.channels + ch_off;
-#pragma unroll
-            for (int k = 0; k < CDIM; ++k)
-                if (k < ch_cnt)
-                    sm.color[k][tr] = cp[k];
-        }
-        __syncthreads();
+        const int batch_size = min(RAST_THREADS, range_end - batch_start);
+        const float *base = rast_smem + (size_t)(b % STAGES) * Cfg::STAGE_FLOATS;
+        const float4 *s_r0 = reinterpret_cast<const float4 *>(base);
+        const float4 *s_r1 = reinterpret_cast<const float4 *>(base + RAST_THREADS * 4);
+        const float *s_col = base + RAST_THREADS * 8;
 
-        if (!warp_done) {
-            const int batch_size = min(RAST_THREADS, range_end - batch_start);
-            for (int chunk = 0; chunk < batch_size; chunk += 32) {
-                const int t = chunk + lane;
-                bool hit = false;
-                if (t < batch_size) {
-                    const float4 g0 = sm.xyoa[t];
-                    const float4 g1 = sm.bcee[t];
-                    hit = (g0.x + g1.z >= bx0) && (g0.x - g1.z <= bx1) && (g0.y + g1.w >= by0) &&
-                          (g0.y - g1.w <= by1);
-                }
-                unsigned m = __ballot_sync(0xffffffffu, hit);
-                while (m) {
-                    const int tt = chunk + __ffs(m) - 1;
-                    m &= m - 1;
-                    if (!done) {
-                        const float4 g0 = sm.xyoa[tt];
-                        const float4 g1 = sm.bcee[tt];
-                        const float dx = __fsub_rn(g0.x, px);
-                        const float dy = __fsub_rn(g0.y, py);
-                        const float tc = __fmul_rn(__fmul_rn(g1.y, dy), dy);
-                        const float s = __fmaf_rn(dx, __fmul_rn(g0.w, dx), tc);
-                        const float sigma = __fmaf_rn(dy, __fmul_rn(g1.x, dx), __fmul_rn(s, 0.5f));
-                        const float alpha = fminf(0.999f, __fmul_rn(g0.z, __expf(-sigma)));
-                        if (!(sigma < 0.f || alpha < RS_ALPHA_THRESHOLD)) {
-                            const float next_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
-                            if (next_T <= 1e-4f) {
-                                done = true;
-                            } else {
-                                const float vis = __fmul_rn(alpha, T);
+        for (int chunk = 0; chunk < batch_size; chunk += 32) {
+            const int t = chunk + lane;
+            bool hit = false;
+            if (t < batch_size) {
+                const float4 g0 = s_r0[t];
+                const float4 g1 = s_r1[t];
+                hit = (g0.x + g1.z >= bx0) && (g0.x - g1.z <= bx1) && (g0.y + g1.w >= by0) && (g0.y - g1.w <= by1);
+            }
+            // bit-reversed ballot: the next splat in list order is the highest set bit (one FLO per iteration)
+            unsigned m = __brev(__ballot_sync(0xffffffffu, hit));
+            while (m) {
+                const int lz = __clz(m);
+                m &= ~(0x80000000u >> lz);
+                const int tt = chunk + lz;
+                if (!done) {
+                    const float4 g0 = s_r0[tt];
+                    const float4 g1 = s_r1[tt];
+                    const float dx = __fsub_rn(g0.x, px);
+                    const float dy = __fsub_rn(g0.y, py);
+                    const float tc = __fmul_rn(__fmul_rn(g1.y, dy), dy);
+                    const float s = __fmaf_rn(dx, __fmul_rn(g0.w, dx), tc);
+                    const float sigma = __fmaf_rn(dy, __fmul_rn(g1.x, dx), __fmul_rn(s, 0.5f));
+                    const float alpha = fminf(0.999f, __fmul_rn(g0.z, __expf(-sigma)));
+                    if (!(sigma < 0.f || alpha < RS_ALPHA_THRESHOLD)) {
+                        const float next_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
+                        if (next_T <= 1e-4f) {
+                            done = true;
+                        } else {
+                            const float vis = __fmul_rn(alpha, T);
+                            const float4 *crow = reinterpret_cast<const float4 *>(s_col + tt * CP);
 #pragma unroll
-                                for (int k = 0; k < CDIM; ++k)
-                                    if (k < ch_cnt)
-                                        pix_out[k] = __fmaf_rn(sm.color[k][tt], vis, pix_out[k]);
-                                cur_idx = (uint32_t)(batch_start + tt);
-                                T = next_T;
+                            for (int k = 0; k < CP; k += 4) {
+                                const float4 c4 = crow[k >> 2];
+                                pix_out[k + 0] = __fmaf_rn(c4.x, vis, pix_out[k + 0]);
+                                pix_out[k + 1] = __fmaf_rn(c4.y, vis, pix_out[k + 1]);
+                                pix_out[k + 2] = __fmaf_rn(c4.z, vis, pix_out[k + 2]);
+                                pix_out[k + 3] = __fmaf_rn(c4.w, vis, pix_out[k + 3]);
                             }
+                            cur_idx = (uint32_t)(batch_start + tt);
+                            T = next_T;
                         }
                     }
                 }
-                if (__all_sync(0xffffffffu, done)) {
-                    warp_done = true;
-                    break;
-                }
+            }
+            if (__all_sync(0xffffffffu, done)) {
+                warp_done = true;
+                break;
             }
         }
     }
+    rs_cp_async_wait<0>(); // nothing may still be landing in shared memory when the CTA retires
 
     if (inside) {
         a.render_alphas[pix_id] = __fsub_rn(1.0f, T);
@@ -196,8 +254,27 @@ rs_raster_fwd_kernel(const rs_raster_fwd_args a, const int ch_off, const int ch_
 
 template <int CDIM>
 static int launch_raster_fwd(const rs_raster_fwd_args &a, int ch_off, int ch_cnt, cudaStream_t s) {
+    using Cfg = RastCfg<CDIM>;
     const int64_t grid = (int64_t)a.I * a.tile_width * a.tile_height;
-    rs_raster_fwd_kernel<CDIM><<<(unsigned)grid, RAST_THREADS, 0, s>>>(a, ch_off, ch_cnt);
+    // 16-byte colour copies need aligned rows that fill the shared-memory pitch exactly
+    const bool vec = (ch_cnt == Cfg::CP) && (a.channels % 4 == 0) && (ch_off % 4 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(a.colors) & 15) == 0);
+    static bool attr_done[2] = {false, false};
+    if (vec) {
+        if (!attr_done[1]) {
+            RS_CUDA(cudaFuncSetAttribute(rs_raster_fwd_kernel<CDIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::SMEM));
+            attr_done[1] = true;
+        }
+        rs_raster_fwd_kernel<CDIM, true><<<(unsigned)grid, RAST_THREADS, Cfg::SMEM, s>>>(a, ch_off, ch_cnt);
+    } else {
+        if (!attr_done[0]) {
+            RS_CUDA(cudaFuncSetAttribute(rs_raster_fwd_kernel<CDIM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)Cfg::SMEM));
+            attr_done[0] = true;
+        }
+        rs_raster_fwd_kernel<CDIM, false><<<(unsigned)grid, RAST_THREADS, Cfg::SMEM, s>>>(a, ch_off, ch_cnt);
+    }
     RS_LAUNCH_CHECK("rs_raster_fwd_kernel");
     return 0;
 }
@@ -211,14 +288,12 @@ int rs_raster_fwd_chunk(const rs_raster_fwd_args &a, int ch_off, int ch_cnt, cud
         return launch_raster_fwd<3>(a, ch_off, ch_cnt, s);
     if (ch_cnt <= 4)
         return launch_raster_fwd<4>(a, ch_off, ch_cnt, s);
-    if (ch_cnt <= 5)
-        return launch_raster_fwd<5>(a, ch_off, ch_cnt, s);
     if (ch_cnt <= 8)
         return launch_raster_fwd<8>(a, ch_off, ch_cnt, s);
     if (ch_cnt <= 16)
         return launch_raster_fwd<16>(a, ch_off, ch_cnt, s);
-    if (ch_cnt <= 17)
-        return launch_raster_fwd<17>(a, ch_off, ch_cnt, s);
+    if (ch_cnt <= 20)
+        return launch_raster_fwd<20>(a, ch_off, ch_cnt, s);
     return launch_raster_fwd<32>(a, ch_off, ch_cnt, s);
 }
 
@@ -241,10 +316,19 @@ extern "C" int rs_raster_fwd(const rs_raster_fwd_args *a, rs_stream_t stream) {
         return e;
     if (a->I == 0)
         return 0;
-    RS_CHECK(a->means2d && a->conics && a->colors && a->opacities && a->tile_offsets && a->render_colors &&
-                 a->render_alphas && a->last_ids,
+    RS_CHECK(a->colors && a->tile_offsets && a->render_colors && a->render_alphas && a->last_ids,
              "rs_raster_fwd: null pointer");
     RS_CHECK(a->n_isects == 0 || a->flatten_ids != nullptr, "rs_raster_fwd: null flatten_ids");
+    RS_CHECK(a->records != nullptr && (reinterpret_cast<uintptr_t>(a->records) & 15) == 0,
+             "rs_raster_fwd: records scratch ([rows, 8] float, 16-byte aligned) is required");
+    if (!a->records_ready) {
+        RS_CHECK(a->means2d && a->conics && a->opacities, "rs_raster_fwd: null pointer");
+        RS_CHECK(a->n_rows > 0 || a->n_isects == 0, "rs_raster_fwd: n_rows required to pack records");
+        if (a->n_rows > 0) {
+            rs_raster_pack_kernel<<<rs_cdiv(a->n_rows, 256), 256, 0, (cudaStream_t)stream>>>(*a, a->n_rows);
+            RS_LAUNCH_CHECK("rs_raster_pack_kernel");
+        }
+    }
     for (int off = 0; off < a->channels; off += 32) {
         const int cnt = a->channels - off < 32 ? a->channels - off : 32;
         if (int e = rs_raster_fwd_chunk(*a, off, cnt, (cudaStream_t)stream))

@@ -86,6 +86,10 @@ typedef struct {
     int32_t *block_sums;        /* [rs_isect_num_blocks(B*C*N)] out, optional */
     int32_t tile_size, tile_width, tile_height;
     int32_t _pad;
+    /* optional: compositing records [B*C*N, 8] float = {x, y, opacity, conic a | conic b, conic c, cull half-extent x, y},
+     * the staging format of rs_raster_fwd (pass them as rs_raster_fwd_args.records with records_ready = 1).  Needs
+     * opacities; written for visible rows only. */
+    float *records;
 } rs_project_fwd_args;
 int rs_project_fwd(const rs_project_fwd_args *a, rs_stream_t stream);
 
@@ -217,6 +221,13 @@ typedef struct {
     float *render_colors;        /* [I,H,W,channels] out */
     float *render_alphas;        /* [I,H,W,1] out */
     int32_t *last_ids;           /* [I,H,W] out */
+    /* Staging records [I*N or nnz, 8] float (caller-allocated scratch, 32 B per row, 16 B aligned).  With
+     * records_ready == 0 rs_raster_fwd first packs them from means2d / conics / opacities; with records_ready == 1 they
+     * were written by rs_project_fwd (frame path) and means2d / conics / opacities may be NULL. */
+    float *records;
+    int32_t records_ready;
+    int32_t _pad;
+    int64_t n_rows;              /* rows of means2d / conics (I*N, or nnz when packed); needed when records_ready == 0 */
 } rs_raster_fwd_args;
 int rs_raster_fwd(const rs_raster_fwd_args *a, rs_stream_t stream);
 
