@@ -318,19 +318,9 @@ extern "C" int rs_isect_offsets(const int64_t *isect_ids_sorted, int64_t n_isect
 // intersection per tile, and 3 is stable, so equal (image, tile, depth) keys stay in ascending flatten-index order --
 // exactly the order the reference's stable sort of its emission order gives.
 // =====================================================================================================================
-int rs_sort_pairs_u32_internal(int64_t n_bound, const int32_t *n_dev, int begin_bit, int end_bit, uint32_t *keys_a,
-                               uint32_t *keys_b, int32_t *vals_a, int32_t *vals_b, void *workspace,
-                               uint64_t workspace_bytes, int32_t *result_in_b, cudaStream_t s);
-
-__global__ void __launch_bounds__(256)
-rs_bin_init_kernel(int64_t n_elems, const float *__restrict__ depths, uint32_t *__restrict__ keys,
-                   int32_t *__restrict__ elems) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_elems) {
-        keys[i] = __float_as_uint(depths[i]);
-        elems[i] = (int32_t)i;
-    }
-}
+int rs_sort_pairs_u32_internal(int64_t n_bound, const int32_t *n_dev, int begin_bit, int end_bit, const uint32_t *keys_in,
+                               const int32_t *vals_in, uint32_t *kbuf0, int32_t *vbuf0, uint32_t *kbuf1, int32_t *vbuf1,
+                               void *workspace, uint64_t workspace_bytes, int *passes, cudaStream_t s);
 
 // block sums of the tile counts taken in depth order
 __global__ void __launch_bounds__(RS_ISECT_THREADS)
@@ -508,28 +498,28 @@ extern "C" int rs_isect_sorted(const rs_isect_sorted_args *b, rs_stream_t stream
     int32_t *block_sums = reinterpret_cast<int32_t *>(w + L.block_sums);
     const int nb = rs_isect_num_blocks(a->n_elems);
 
-    // the tile sort ping-pongs between (tkeys_a, caller's flatten_ids) and (tkeys_b, vals_b); start on the side that makes
-    // the last pass land in the caller's flatten_ids
+    // tile sort: pass p writes buffer p & 1, the last pass must land in the caller's flatten_ids, and the emission goes to
+    // "buffer 1" (which the sort allows to alias its input)
     const int tile_bits = (int)(tile_n_bits + image_n_bits);
     const int tile_passes = (tile_bits + 7) / 8;
     uint32_t *tk_final = reinterpret_cast<uint32_t *>(w + L.tkeys_a), *tk_other = reinterpret_cast<uint32_t *>(w + L.tkeys_b);
     int32_t *tv_final = a->flatten_ids, *tv_other = reinterpret_cast<int32_t *>(w + L.vals_b);
-    uint32_t *tk_start = (tile_passes & 1) ? tk_other : tk_final;
-    int32_t *tv_start = (tile_passes & 1) ? tv_other : tv_final;
+    const bool final_is_buf0 = (tile_passes & 1) != 0;
+    uint32_t *tk_buf0 = final_is_buf0 ? tk_final : tk_other, *tk_buf1 = final_is_buf0 ? tk_other : tk_final;
+    int32_t *tv_buf0 = final_is_buf0 ? tv_final : tv_other, *tv_buf1 = final_is_buf0 ? tv_other : tv_final;
     const uint32_t *tkeys = tk_final;
 
     const int32_t *elems = nullptr;
     if (a->n_elems > 0) {
-        // 1. depth order: stable LSD sort of (depth bits, flatten index)
+        // 1. depth order: stable LSD sort of (depth bits, flatten index); the keys are read straight from `depths`, the
+        //    values of the first pass are the indices themselves
         uint32_t *dk_a = reinterpret_cast<uint32_t *>(w + L.dkeys_a), *dk_b = reinterpret_cast<uint32_t *>(w + L.dkeys_b);
         int32_t *el_a = reinterpret_cast<int32_t *>(w + L.elems_a), *el_b = reinterpret_cast<int32_t *>(w + L.elems_b);
-        rs_bin_init_kernel<<<rs_cdiv(a->n_elems, 256), 256, 0, s>>>(a->n_elems, a->depths, dk_a, el_a);
-        RS_LAUNCH_CHECK("rs_bin_init_kernel");
-        int32_t in_b = 0;
-        if (int e = rs_sort_pairs_u32_internal(a->n_elems, nullptr, 0, 32, dk_a, dk_b, el_a, el_b, w + L.sort_ws,
-                                               L.sort_ws_bytes, &in_b, s))
+        int passes = 0;
+        if (int e = rs_sort_pairs_u32_internal(a->n_elems, nullptr, 0, 32, reinterpret_cast<const uint32_t *>(a->depths),
+                                               nullptr, dk_a, el_a, dk_b, el_b, w + L.sort_ws, L.sort_ws_bytes, &passes, s))
             return e;
-        elems = in_b ? el_b : el_a;
+        elems = ((passes - 1) & 1) ? el_b : el_a;
         // 2a. block sums of the tile counts in depth order
         rs_bin_count_kernel<<<nb, RS_ISECT_THREADS, 0, s>>>(a->n_elems, elems, a->tiles_per_gauss, block_sums);
         RS_LAUNCH_CHECK("rs_bin_count_kernel");
@@ -542,14 +532,12 @@ extern "C" int rs_isect_sorted(const rs_isect_sorted_args *b, rs_stream_t stream
         // 2c. emission in depth order
         rs_isect_args e = *a;
         e.block_sums = block_sums;
-        rs_bin_emit_kernel<<<nb, RS_ISECT_THREADS, 0, s>>>(e, elems, tile_n_bits, tk_start, tv_start);
+        rs_bin_emit_kernel<<<nb, RS_ISECT_THREADS, 0, s>>>(e, elems, tile_n_bits, tk_buf1, tv_buf1);
         RS_LAUNCH_CHECK("rs_bin_emit_kernel");
         // 3. stable sort on the (image | tile) bits only
-        int32_t in_b = 0;
-        if (int err = rs_sort_pairs_u32_internal(a->capacity, a->n_isects, 0, tile_bits, tk_start,
-                                                 (tile_passes & 1) ? tk_final : tk_other, tv_start,
-                                                 (tile_passes & 1) ? tv_final : tv_other, w + L.sort_ws, L.sort_ws_bytes,
-                                                 &in_b, s))
+        int passes = 0;
+        if (int err = rs_sort_pairs_u32_internal(a->capacity, a->n_isects, 0, tile_bits, tk_buf1, tv_buf1, tk_buf0, tv_buf0,
+                                                 tk_buf1, tv_buf1, w + L.sort_ws, L.sort_ws_bytes, &passes, s))
             return err;
     }
     // 4. offsets (+ 64-bit ids on request)

@@ -1,15 +1,21 @@
 // Hand-written stable LSD radix sort of (key, int32 value) pairs -- replaces the cub::DeviceRadixSort::SortPairs call
-// of csrc/IntersectTile.cu:296-339 (keys = image | tile | depth bits, values = flatten ids).
+// of csrc/IntersectTile.cu:296-339.  Used twice per frame by the depth-ordered binning of isect.cu (u32 depth keys,
+// u32 image|tile keys) and exported as rs_radix_sort_pairs (u64 keys, the reference's image|tile|depth format).
 //
-// 8-bit digits, three kernels per pass, no inter-CTA spinning (every kernel is a plain grid):
-//   hist       each CTA counts the digits of its 4096-pair tile            -> hist[digit][cta]
-//   scan_rows  one CTA per digit: exclusive scan over CTAs (in place)       -> hist[digit][cta], bin_tot[digit]
-//   scatter    each CTA re-reads its tile, ranks pairs stably (warp match + per-warp digit counters, warp-striped
-//              order), re-orders the tile in shared memory so that equal digits are contiguous, and writes runs to
-//              their global positions (coalesced within a run).
-// Stability: tile order = (warp, item, lane) = ascending index; ranks preserve it; CTAs are ordered by the row scan.
-// Algorithmic HBM bytes per pair per pass: 8 (hist read) + 12 (read) + 12 (write) for 64-bit keys.
-// A device-side pair count (`n_dev`) makes the whole sort launchable without knowing n on the host.
+// One-sweep organisation, 8-bit digits:
+//   sort_hist_kernel   ONE read of the keys builds the 256-bin digit histogram of EVERY pass (LSD passes only permute the
+//                      keys, so all global histograms are known up front); it also clears the look-back state.
+//   sort_pass_kernel   one launch per digit.  A persistent CTA takes tiles of 4096 pairs in ticket order, ranks them
+//                      stably in shared memory (warp match + per-warp digit counters, warp-striped order), obtains the
+//                      number of equal-digit pairs in all earlier tiles by DECOUPLED LOOK-BACK (each tile publishes
+//                      aggregate / inclusive counts per digit in one 32-bit word; a tile only ever waits on tiles with a
+//                      smaller ticket, which are already running), re-orders the tile in shared memory so that equal
+//                      digits are contiguous and writes the runs to their final positions.
+// Per pass every pair is read once and written once: algorithmic HBM bytes = n * 2 * (sizeof(key) + 4), plus one extra
+// key read for the histogram kernel per SORT (not per pass).
+// Stability: tile order = ticket order = ascending index; ranks preserve index order inside a tile.
+// A device-side pair count (`n_dev`) makes the whole sort launchable without knowing n on the host; grids are sized by
+// the SM count, never by the capacity.
 #include "common.cuh"
 
 #define SORT_THREADS 256
@@ -18,8 +24,19 @@
 #define SORT_WARPS (SORT_THREADS / 32)
 #define RADIX_BITS 8
 #define RADIX (1 << RADIX_BITS)
+#define SORT_MAX_PASSES 8
 
 static_assert(RADIX == SORT_THREADS, "one thread per digit in the block-level scans");
+
+#define LB_AGGREGATE 0x40000000u
+#define LB_INCLUSIVE 0x80000000u
+#define LB_VALUE 0x3fffffffu
+
+// workspace layout (uint32 words): [0, 8*256) digit histograms per pass | [2048, 2048+8) tile tickets per pass |
+// [2304, ...) look-back words: pass-major, [pass][tile][256]
+#define WS_HIST 0
+#define WS_TICKET (SORT_MAX_PASSES * RADIX)
+#define WS_LOOKBACK (WS_TICKET + 256)
 
 __device__ __forceinline__ int64_t sort_count(int64_t n_bound, const int32_t *n_dev) {
     return (n_dev != nullptr) ? min((int64_t)*n_dev, n_bound) : n_bound;
@@ -51,57 +68,53 @@ __device__ __forceinline__ int block_excl_scan_256(int v, int *wsum, int *total)
     return base + incl - v;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// histograms of all passes + look-back reset.  ws[WS_HIST..] and ws[WS_TICKET..] are zeroed by a memset before.
+// ---------------------------------------------------------------------------------------------------------------------
 template <typename KeyT>
 __global__ void __launch_bounds__(SORT_THREADS)
-sort_hist_kernel(const KeyT *__restrict__ keys, int64_t n_bound, const int32_t *__restrict__ n_dev, int shift,
-                 uint32_t mask, int32_t *__restrict__ hist, int nblocks) {
-    __shared__ int h[SORT_WARPS][RADIX];
+sort_hist_kernel(const KeyT *__restrict__ keys, int64_t n_bound, const int32_t *__restrict__ n_dev, int begin_bit,
+                 int end_bit, int passes, int nb_stride, uint32_t *__restrict__ ws) {
+    __shared__ unsigned int h[SORT_MAX_PASSES][RADIX];
     const int64_t n = sort_count(n_bound, n_dev);
-    if ((int64_t)blockIdx.x * SORT_TILE >= n)
-        return; // the grid is sized for n_bound; rows are only scanned up to ceil(n / SORT_TILE)
-    const int warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int w = 0; w < SORT_WARPS; ++w)
-        h[w][threadIdx.x] = 0;
+    for (int p = 0; p < passes; ++p)
+        h[p][threadIdx.x] = 0;
     __syncthreads();
-    const int64_t tile_start = (int64_t)blockIdx.x * SORT_TILE;
-    if (tile_start < n) {
-#pragma unroll
-        for (int k = 0; k < SORT_ITEMS; ++k) {
-            const int64_t idx = tile_start + k * SORT_THREADS + threadIdx.x;
-            if (idx < n) {
-                const uint32_t d = (uint32_t)(keys[idx] >> shift) & mask;
-                atomicAdd(&h[warp][d], 1);
+    const int lane = threadIdx.x & 31;
+    for (int64_t base = (int64_t)blockIdx.x * SORT_THREADS; base < n; base += (int64_t)gridDim.x * SORT_THREADS) {
+        const int64_t idx = base + threadIdx.x;
+        const bool valid = idx < n;
+        const KeyT key = valid ? keys[idx] : (KeyT)0;
+        for (int p = 0; p < passes; ++p) {
+            const int shift = begin_bit + p * RADIX_BITS;
+            const int bits = min(RADIX_BITS, end_bit - shift);
+            const uint32_t d = (uint32_t)(key >> shift) & ((1u << bits) - 1u);
+            // nearly sorted inputs (tile ids in emission order) put a whole warp on one digit: count it with one add
+            const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
+            const unsigned same = __ballot_sync(0xffffffffu, valid && d == d0);
+            const unsigned act = __ballot_sync(0xffffffffu, valid);
+            if (same == act) {
+                if (lane == 0 && act)
+                    atomicAdd(&h[p][d0], (unsigned)__popc(act));
+            } else if (valid) {
+                atomicAdd(&h[p][d], 1u);
             }
         }
     }
     __syncthreads();
-    int s = 0;
-#pragma unroll
-    for (int w = 0; w < SORT_WARPS; ++w)
-        s += h[w][threadIdx.x];
-    hist[(size_t)threadIdx.x * nblocks + blockIdx.x] = s;
-}
-
-// grid = RADIX CTAs; CTA d scans row d of hist (nblocks entries) in place (exclusive) and writes bin_tot[d].
-__global__ void __launch_bounds__(SORT_THREADS)
-sort_scan_rows_kernel(int32_t *__restrict__ hist, int nblocks, int64_t n_bound, const int32_t *__restrict__ n_dev,
-                      int32_t *__restrict__ bin_tot) {
-    __shared__ int wsum[SORT_WARPS];
-    int32_t *row = hist + (size_t)blockIdx.x * nblocks;
-    const int nb_eff = (int)((sort_count(n_bound, n_dev) + SORT_TILE - 1) / SORT_TILE);
-    int carry = 0;
-    for (int start = 0; start < nb_eff; start += SORT_THREADS) {
-        const int i = start + threadIdx.x;
-        const int v = (i < nb_eff) ? row[i] : 0;
-        int tot;
-        const int ex = block_excl_scan_256(v, wsum, &tot);
-        if (i < nb_eff)
-            row[i] = carry + ex;
-        carry += tot;
+    for (int p = 0; p < passes; ++p) {
+        const unsigned v = h[p][threadIdx.x];
+        if (v)
+            atomicAdd(&ws[WS_HIST + p * RADIX + threadIdx.x], v);
     }
-    if (threadIdx.x == 0)
-        bin_tot[blockIdx.x] = carry;
+    // reset the look-back words of the tiles this sort will use
+    const int64_t words = (n + SORT_TILE - 1) / SORT_TILE * RADIX;
+    for (int p = 0; p < passes; ++p) {
+        uint32_t *lb = ws + WS_LOOKBACK + (size_t)p * nb_stride * RADIX;
+        for (int64_t i = (int64_t)blockIdx.x * SORT_THREADS + threadIdx.x; i < words;
+             i += (int64_t)gridDim.x * SORT_THREADS)
+            lb[i] = 0u;
+    }
 }
 
 template <typename KeyT> struct SortSmem {
@@ -109,95 +122,141 @@ template <typename KeyT> struct SortSmem {
     int32_t vals[SORT_TILE];
     int wh[SORT_WARPS][RADIX]; // per-warp digit counters -> exclusive per-warp offsets
     int bin_start[RADIX];      // first slot of each digit inside the re-ordered tile
-    int gbase[RADIX];          // global index of that first slot
+    int64_t gbase[RADIX];      // global index of that first slot
+    int gstart[RADIX];         // exclusive scan of the global digit histogram
     int wsum[SORT_WARPS];
+    int tile;
 };
 
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 template <typename KeyT>
-__global__ void __launch_bounds__(SORT_THREADS)
-sort_scatter_kernel(const KeyT *__restrict__ keys_in, const int32_t *__restrict__ vals_in, KeyT *__restrict__ keys_out,
-                    int32_t *__restrict__ vals_out, int64_t n_bound, const int32_t *__restrict__ n_dev, int shift,
-                    uint32_t mask, const int32_t *__restrict__ hist, int nblocks,
-                    const int32_t *__restrict__ bin_tot) {
+__global__ void __launch_bounds__(SORT_THREADS, sizeof(KeyT) == 4 ? 3 : 2)
+sort_pass_kernel(const KeyT *__restrict__ keys_in, const int32_t *__restrict__ vals_in, KeyT *__restrict__ keys_out,
+                 int32_t *__restrict__ vals_out, int64_t n_bound, const int32_t *__restrict__ n_dev, int shift,
+                 uint32_t mask, int pass, int nb_stride, uint32_t *__restrict__ ws) {
     extern __shared__ __align__(16) unsigned char sort_smem_raw[];
     SortSmem<KeyT> &sm = *reinterpret_cast<SortSmem<KeyT> *>(sort_smem_raw);
     const int64_t n = sort_count(n_bound, n_dev);
-    const int64_t tile_start = (int64_t)blockIdx.x * SORT_TILE;
-    if (tile_start >= n)
-        return;
-    const int count = (int)min((int64_t)SORT_TILE, n - tile_start);
+    const int nb_eff = (int)((n + SORT_TILE - 1) / SORT_TILE);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = rs_lanemask_lt();
+    uint32_t *lookback = ws + WS_LOOKBACK + (size_t)pass * nb_stride * RADIX;
 
-#pragma unroll
-    for (int w = 0; w < SORT_WARPS; ++w)
-        sm.wh[w][threadIdx.x] = 0;
-
-    // warp-striped load: warp w owns [w*512, (w+1)*512), item k of lane l sits at k*32 + l
-    KeyT key[SORT_ITEMS];
-    int32_t val[SORT_ITEMS];
-    const int wbase = warp * (32 * SORT_ITEMS);
-#pragma unroll
-    for (int k = 0; k < SORT_ITEMS; ++k) {
-        const int local = wbase + k * 32 + lane;
-        if (local < count) {
-            key[k] = keys_in[tile_start + local];
-            val[k] = vals_in[tile_start + local];
-        } else {
-            key[k] = ~(KeyT)0; // sorts to the very end of the tile, never written out
-            val[k] = 0;
-        }
-    }
-    __syncthreads();
-
-    int rank[SORT_ITEMS];
-#pragma unroll
-    for (int k = 0; k < SORT_ITEMS; ++k) {
-        const uint32_t d = (uint32_t)(key[k] >> shift) & mask;
-        const unsigned peers = __match_any_sync(0xffffffffu, d);
-        const int leader = __ffs(peers) - 1;
-        int old = 0;
-        if (lane == leader) {
-            old = sm.wh[warp][d];
-            sm.wh[warp][d] = old + __popc(peers);
-        }
-        old = __shfl_sync(0xffffffffu, old, leader);
-        rank[k] = old + __popc(peers & lt);
-        __syncwarp();
-    }
-    __syncthreads();
-
-    // thread t handles digit t: per-warp exclusive offsets, tile-level digit start, global base
+    // exclusive scan of this pass's global histogram: where each digit's output range starts
     {
-        int sum = 0;
+        const int g = (int)ws[WS_HIST + pass * RADIX + threadIdx.x];
+        const int ex = block_excl_scan_256(g, sm.wsum, nullptr);
+        sm.gstart[threadIdx.x] = ex;
+    }
+
+    while (true) {
+        __syncthreads(); // previous tile fully written out; sm.tile free
+        if (threadIdx.x == 0)
+            sm.tile = (int)atomicAdd(&ws[WS_TICKET + pass], 1u);
 #pragma unroll
-        for (int w = 0; w < SORT_WARPS; ++w) {
-            const int c = sm.wh[w][threadIdx.x];
-            sm.wh[w][threadIdx.x] = sum;
-            sum += c;
+        for (int w = 0; w < SORT_WARPS; ++w)
+            sm.wh[w][threadIdx.x] = 0;
+        __syncthreads();
+        const int tile = sm.tile;
+        if (tile >= nb_eff)
+            break;
+        const int64_t tile_start = (int64_t)tile * SORT_TILE;
+        const int count = (int)min((int64_t)SORT_TILE, n - tile_start);
+
+        // warp-striped load: warp w owns [w*512, (w+1)*512), item k of lane l sits at k*32 + l
+        KeyT key[SORT_ITEMS];
+        int32_t val[SORT_ITEMS];
+        const int wbase = warp * (32 * SORT_ITEMS);
+#pragma unroll
+        for (int k = 0; k < SORT_ITEMS; ++k) {
+            const int local = wbase + k * 32 + lane;
+            if (local < count) {
+                key[k] = keys_in[tile_start + local];
+                val[k] = vals_in != nullptr ? vals_in[tile_start + local] : (int32_t)(tile_start + local);
+            } else {
+                key[k] = ~(KeyT)0; // sorts to the very end of the tile, never written out
+                val[k] = 0;
+            }
         }
-        const int start = block_excl_scan_256(sum, sm.wsum, nullptr);
-        const int gb = block_excl_scan_256(bin_tot[threadIdx.x], sm.wsum, nullptr);
-        sm.bin_start[threadIdx.x] = start;
-        sm.gbase[threadIdx.x] = gb + hist[(size_t)threadIdx.x * nblocks + blockIdx.x];
-    }
-    __syncthreads();
+
+        int rank[SORT_ITEMS];
+#pragma unroll
+        for (int k = 0; k < SORT_ITEMS; ++k) {
+            const uint32_t d = (uint32_t)(key[k] >> shift) & mask;
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            const int leader = __ffs(peers) - 1;
+            int old = 0;
+            if (lane == leader) {
+                old = sm.wh[warp][d];
+                sm.wh[warp][d] = old + __popc(peers);
+            }
+            old = __shfl_sync(0xffffffffu, old, leader);
+            rank[k] = old + __popc(peers & lt);
+            __syncwarp();
+        }
+        __syncthreads();
+
+        // thread t handles digit t: per-warp exclusive offsets, tile-level digit start, look-back for the global base
+        {
+            int sum = 0;
+#pragma unroll
+            for (int w = 0; w < SORT_WARPS; ++w) {
+                const int c = sm.wh[w][threadIdx.x];
+                sm.wh[w][threadIdx.x] = sum;
+                sum += c;
+            }
+            // padding keys (all ones) of a ragged last tile were counted in the top digit: take them out of the counts
+            // that are published (they are the last entries of that digit, so local ranks are unaffected)
+            int real = sum;
+            if (count < SORT_TILE && threadIdx.x == (int)(((uint32_t)((~(KeyT)0) >> shift)) & mask))
+                real = sum - (SORT_TILE - count);
+            uint32_t *mine = lookback + (size_t)tile * RADIX + threadIdx.x;
+            st_volatile_u32(mine, (tile == 0 ? LB_INCLUSIVE : LB_AGGREGATE) | (uint32_t)real);
+            const int start = block_excl_scan_256(sum, sm.wsum, nullptr);
+            int64_t excl = 0;
+            if (tile > 0) {
+                int t = tile - 1;
+                while (true) {
+                    uint32_t v;
+                    do {
+                        v = ld_volatile_u32(lookback + (size_t)t * RADIX + threadIdx.x);
+                    } while ((v & (LB_AGGREGATE | LB_INCLUSIVE)) == 0u);
+                    excl += (int64_t)(v & LB_VALUE);
+                    if (v & LB_INCLUSIVE)
+                        break;
+                    --t;
+                }
+                st_volatile_u32(mine, LB_INCLUSIVE | (uint32_t)(excl + real));
+            }
+            sm.bin_start[threadIdx.x] = start;
+            sm.gbase[threadIdx.x] = (int64_t)sm.gstart[threadIdx.x] + excl;
+        }
+        __syncthreads();
 
 #pragma unroll
-    for (int k = 0; k < SORT_ITEMS; ++k) {
-        const uint32_t d = (uint32_t)(key[k] >> shift) & mask;
-        const int pos = sm.bin_start[d] + sm.wh[warp][d] + rank[k];
-        sm.keys[pos] = key[k];
-        sm.vals[pos] = val[k];
-    }
-    __syncthreads();
+        for (int k = 0; k < SORT_ITEMS; ++k) {
+            const uint32_t d = (uint32_t)(key[k] >> shift) & mask;
+            const int pos = sm.bin_start[d] + sm.wh[warp][d] + rank[k];
+            sm.keys[pos] = key[k];
+            sm.vals[pos] = val[k];
+        }
+        __syncthreads();
 
-    for (int i = threadIdx.x; i < count; i += SORT_THREADS) {
-        const KeyT kk = sm.keys[i];
-        const uint32_t d = (uint32_t)(kk >> shift) & mask;
-        const int64_t out = (int64_t)sm.gbase[d] + (i - sm.bin_start[d]);
-        keys_out[out] = kk;
-        vals_out[out] = sm.vals[i];
+        for (int i = threadIdx.x; i < count; i += SORT_THREADS) {
+            const KeyT kk = sm.keys[i];
+            const uint32_t d = (uint32_t)(kk >> shift) & mask;
+            const int64_t out = sm.gbase[d] + (i - sm.bin_start[d]);
+            keys_out[out] = kk;
+            vals_out[out] = sm.vals[i];
+        }
     }
 }
 
@@ -205,78 +264,84 @@ static inline int sort_nblocks(int64_t n) { return (int)((n + SORT_TILE - 1) / S
 
 extern "C" uint64_t rs_radix_sort_workspace_bytes(int64_t n) {
     const uint64_t nb = (uint64_t)(sort_nblocks(n) > 0 ? sort_nblocks(n) : 1);
-    return (uint64_t)RADIX * nb * sizeof(int32_t) + RADIX * sizeof(int32_t) + 256;
+    return ((uint64_t)WS_LOOKBACK + (uint64_t)SORT_MAX_PASSES * nb * RADIX) * sizeof(uint32_t) + 256;
 }
 
+// keys_in/vals_in are only read (vals_in == nullptr: values are the indices 0..n-1); pass p writes buffer p & 1, so the
+// result ends in buffer (passes - 1) & 1.  buf 0 must not alias the input; buf 1 may.
 template <typename KeyT>
-static int radix_sort_impl(int64_t n_bound, const int32_t *n_dev, int begin_bit, int end_bit, KeyT *keys_a,
-                           KeyT *keys_b, int32_t *vals_a, int32_t *vals_b, void *workspace, uint64_t workspace_bytes,
-                           int32_t *result_in_b, cudaStream_t s) {
-    if (result_in_b)
-        *result_in_b = 0;
+static int radix_sort_impl(int64_t n_bound, const int32_t *n_dev, int begin_bit, int end_bit, const KeyT *keys_in,
+                           const int32_t *vals_in, KeyT *kbuf0, int32_t *vbuf0, KeyT *kbuf1, int32_t *vbuf1,
+                           void *workspace, uint64_t workspace_bytes, int *passes_out, cudaStream_t s) {
+    if (passes_out)
+        *passes_out = 0;
     if (n_bound <= 0 || end_bit <= begin_bit)
         return 0;
-    RS_CHECK(keys_a && keys_b && vals_a && vals_b && workspace, "rs_radix_sort_pairs: null pointer");
+    const int passes = (end_bit - begin_bit + RADIX_BITS - 1) / RADIX_BITS;
+    RS_CHECK(passes <= SORT_MAX_PASSES, "rs_radix_sort_pairs: too many key bits");
+    RS_CHECK(keys_in && kbuf0 && vbuf0 && workspace && (passes < 2 || (kbuf1 && vbuf1)),
+             "rs_radix_sort_pairs: null pointer");
     RS_CHECK(workspace_bytes >= rs_radix_sort_workspace_bytes(n_bound),
              "rs_radix_sort_pairs: workspace too small (%llu < %llu)", (unsigned long long)workspace_bytes,
              (unsigned long long)rs_radix_sort_workspace_bytes(n_bound));
-    RS_CHECK(n_bound < ((int64_t)1 << 31), "rs_radix_sort_pairs: n must fit in int32");
+    RS_CHECK(n_bound < (int64_t)LB_VALUE, "rs_radix_sort_pairs: n must be below 2^30");
     const int nb = sort_nblocks(n_bound);
-    int32_t *hist = reinterpret_cast<int32_t *>(workspace);
-    int32_t *bin_tot = hist + (size_t)RADIX * nb;
+    uint32_t *ws = reinterpret_cast<uint32_t *>(workspace);
     static bool attr_set[2] = {false, false};
     const int which = sizeof(KeyT) == 8 ? 1 : 0;
     const size_t smem = sizeof(SortSmem<KeyT>);
     if (!attr_set[which]) {
-        RS_CUDA(cudaFuncSetAttribute(sort_scatter_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)smem));
+        RS_CUDA(cudaFuncSetAttribute(sort_pass_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[which] = true;
     }
-    KeyT *kin = keys_a, *kout = keys_b;
-    int32_t *vin = vals_a, *vout = vals_b;
-    int passes = 0;
-    for (int shift = begin_bit; shift < end_bit; shift += RADIX_BITS) {
+    const int sms = rs_num_sms();
+    RS_CUDA(cudaMemsetAsync(ws, 0, (size_t)WS_LOOKBACK * sizeof(uint32_t), s));
+    const int hist_grid = (int)min((int64_t)sms * 8, (n_bound + SORT_THREADS - 1) / SORT_THREADS);
+    sort_hist_kernel<KeyT><<<hist_grid, SORT_THREADS, 0, s>>>(keys_in, n_bound, n_dev, begin_bit, end_bit, passes, nb,
+                                                              ws);
+    RS_LAUNCH_CHECK("sort_hist_kernel");
+    const int pass_grid = min(nb, sms * (sizeof(KeyT) == 4 ? 3 : 2));
+    const KeyT *kin = keys_in;
+    const int32_t *vin = vals_in;
+    for (int p = 0; p < passes; ++p) {
+        const int shift = begin_bit + p * RADIX_BITS;
         const int bits = min(RADIX_BITS, end_bit - shift);
         const uint32_t mask = (1u << bits) - 1u;
-        sort_hist_kernel<KeyT><<<nb, SORT_THREADS, 0, s>>>(kin, n_bound, n_dev, shift, mask, hist, nb);
-        RS_LAUNCH_CHECK("sort_hist_kernel");
-        sort_scan_rows_kernel<<<RADIX, SORT_THREADS, 0, s>>>(hist, nb, n_bound, n_dev, bin_tot);
-        RS_LAUNCH_CHECK("sort_scan_rows_kernel");
-        sort_scatter_kernel<KeyT><<<nb, SORT_THREADS, smem, s>>>(kin, vin, kout, vout, n_bound, n_dev, shift, mask,
-                                                                 hist, nb, bin_tot);
-        RS_LAUNCH_CHECK("sort_scatter_kernel");
-        KeyT *tk = kin;
+        KeyT *kout = (p & 1) ? kbuf1 : kbuf0;
+        int32_t *vout = (p & 1) ? vbuf1 : vbuf0;
+        sort_pass_kernel<KeyT><<<pass_grid, SORT_THREADS, smem, s>>>(kin, vin, kout, vout, n_bound, n_dev, shift, mask, p,
+                                                                     nb, ws);
+        RS_LAUNCH_CHECK("sort_pass_kernel");
         kin = kout;
-        kout = tk;
-        int32_t *tv = vin;
         vin = vout;
-        vout = tv;
-        ++passes;
     }
-    if (result_in_b)
-        *result_in_b = passes & 1;
+    if (passes_out)
+        *passes_out = passes;
     return 0;
 }
 
 extern "C" int rs_radix_sort_pairs(const rs_sort_args *a, rs_stream_t stream) {
     RS_CHECK(a != nullptr, "rs_radix_sort_pairs: null args");
     RS_CHECK(a->begin_bit >= 0 && a->end_bit <= 64 && a->begin_bit <= a->end_bit, "rs_radix_sort_pairs: bad bit range");
-    return radix_sort_impl<uint64_t>(a->n, a->n_dev, a->begin_bit, a->end_bit, reinterpret_cast<uint64_t *>(a->keys_a),
-                                     reinterpret_cast<uint64_t *>(a->keys_b), a->vals_a, a->vals_b, a->workspace,
-                                     a->workspace_bytes, a->result_in_b, (cudaStream_t)stream);
+    if (a->result_in_b)
+        *a->result_in_b = 0;
+    RS_CHECK(a->n <= 0 || a->end_bit == a->begin_bit || a->vals_a != nullptr, "rs_radix_sort_pairs: null pointer");
+    int passes = 0;
+    // double-buffer semantics of the reference's cub call: input in a, pass 0 writes b, pass 1 writes a, ...
+    const int e = radix_sort_impl<uint64_t>(a->n, a->n_dev, a->begin_bit, a->end_bit,
+                                            reinterpret_cast<const uint64_t *>(a->keys_a), a->vals_a,
+                                            reinterpret_cast<uint64_t *>(a->keys_b), a->vals_b,
+                                            reinterpret_cast<uint64_t *>(a->keys_a), a->vals_a, a->workspace,
+                                            a->workspace_bytes, &passes, (cudaStream_t)stream);
+    if (e == 0 && a->result_in_b)
+        *a->result_in_b = passes & 1;
+    return e;
 }
 
-int rs_sort_pairs_u32_internal(int64_t n_bound, const int32_t *n_dev, int begin_bit, int end_bit, uint32_t *keys_a,
-                               uint32_t *keys_b, int32_t *vals_a, int32_t *vals_b, void *workspace,
-                               uint64_t workspace_bytes, int32_t *result_in_b, cudaStream_t s) {
-    return radix_sort_impl<uint32_t>(n_bound, n_dev, begin_bit, end_bit, keys_a, keys_b, vals_a, vals_b, workspace,
-                                     workspace_bytes, result_in_b, s);
-}
-
-// internal entry for the fused frame path
-int rs_sort_pairs_u64_internal(int64_t n_bound, const int32_t *n_dev, int begin_bit, int end_bit, uint64_t *keys_a,
-                               uint64_t *keys_b, int32_t *vals_a, int32_t *vals_b, void *workspace,
-                               uint64_t workspace_bytes, int32_t *result_in_b, cudaStream_t s) {
-    return radix_sort_impl<uint64_t>(n_bound, n_dev, begin_bit, end_bit, keys_a, keys_b, vals_a, vals_b, workspace,
-                                     workspace_bytes, result_in_b, s);
+// internal entry for the binning path (isect.cu): u32 keys, read-only input, optional implicit index values
+int rs_sort_pairs_u32_internal(int64_t n_bound, const int32_t *n_dev, int begin_bit, int end_bit, const uint32_t *keys_in,
+                               const int32_t *vals_in, uint32_t *kbuf0, int32_t *vbuf0, uint32_t *kbuf1, int32_t *vbuf1,
+                               void *workspace, uint64_t workspace_bytes, int *passes, cudaStream_t s) {
+    return radix_sort_impl<uint32_t>(n_bound, n_dev, begin_bit, end_bit, keys_in, vals_in, kbuf0, vbuf0, kbuf1, vbuf1,
+                                     workspace, workspace_bytes, passes, s);
 }
