@@ -31,6 +31,7 @@ static_assert(RADIX == SORT_THREADS, "one thread per digit in the block-level sc
 #define LB_AGGREGATE 0x40000000u
 #define LB_INCLUSIVE 0x80000000u
 #define LB_VALUE 0x3fffffffu
+#define LB_WINDOW 8
 
 // workspace layout (uint32 words): [0, 8*256) digit histograms per pass | [2048, 2048+8) tile tickets per pass |
 // [2304, ...) look-back words: pass-major, [pass][tile][256]
@@ -223,16 +224,26 @@ sort_pass_kernel(const KeyT *__restrict__ keys_in, const int32_t *__restrict__ v
             const int start = block_excl_scan_256(sum, sm.wsum, nullptr);
             int64_t excl = 0;
             if (tile > 0) {
+                // Windowed look-back: when all tiles of a wave start together, walking one predecessor per L2 round trip
+                // serialises the wave; LB_WINDOW independent loads per round trip cut that chain by the window size.
                 int t = tile - 1;
-                while (true) {
-                    uint32_t v;
-                    do {
-                        v = ld_volatile_u32(lookback + (size_t)t * RADIX + threadIdx.x);
-                    } while ((v & (LB_AGGREGATE | LB_INCLUSIVE)) == 0u);
-                    excl += (int64_t)(v & LB_VALUE);
-                    if (v & LB_INCLUSIVE)
-                        break;
-                    --t;
+                bool found = false;
+                while (!found) {
+                    uint32_t v[LB_WINDOW];
+#pragma unroll
+                    for (int j = 0; j < LB_WINDOW; ++j)
+                        v[j] = (t - j >= 0) ? ld_volatile_u32(lookback + (size_t)(t - j) * RADIX + threadIdx.x)
+                                            : LB_INCLUSIVE; // before tile 0: inclusive prefix 0
+                    int used = 0;
+#pragma unroll
+                    for (int j = 0; j < LB_WINDOW; ++j) {
+                        if (!found && used == j && (v[j] & (LB_AGGREGATE | LB_INCLUSIVE)) != 0u) {
+                            excl += (int64_t)(v[j] & LB_VALUE);
+                            ++used;
+                            found = (v[j] & LB_INCLUSIVE) != 0u;
+                        }
+                    }
+                    t -= used;
                 }
                 st_volatile_u32(mine, LB_INCLUSIVE | (uint32_t)(excl + real));
             }
