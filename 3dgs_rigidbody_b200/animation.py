@@ -125,6 +125,17 @@ class FrameRenderer:
             _lib.check(self.lib.rs_render_frame(ctypes.byref(a), torch.cuda.current_stream().cuda_stream))
         return self.render_colors, self.render_alphas
 
+    def render_timed(self, viewmats: Tensor, Ks: Tensor, body_quats: Optional[Tensor] = None,
+                     body_trans: Optional[Tensor] = None):
+        """Measurement aid: one frame with CUDA events between the stages (synchronises).  Returns
+        (project_ms, binning_ms, composite_ms, frame_ms)."""
+        with torch.cuda.device(self.device):
+            a = self._fill(viewmats, Ks, body_quats, body_trans)
+            self._args = a
+            ms = (ctypes.c_float * 4)()
+            _lib.check(self.lib.rs_render_frame_timed(ctypes.byref(a), torch.cuda.current_stream().cuda_stream, ms))
+        return tuple(float(x) for x in ms)
+
     # ---- introspection (each of these synchronises) ---------------------------------------------------------------
     def n_isects(self) -> int:
         return int(self.status[0].item())

@@ -116,7 +116,29 @@ extern "C" int rs_frame_export_isect_ids(const rs_frame_args *a, rs_stream_t str
                                      reinterpret_cast<int64_t *>(w + L.isect_ids), stream);
 }
 
-extern "C" int rs_render_frame(const rs_frame_args *a, rs_stream_t stream) {
+static int render_frame_impl(const rs_frame_args *a, rs_stream_t stream, cudaEvent_t *ev);
+
+extern "C" int rs_render_frame(const rs_frame_args *a, rs_stream_t stream) { return render_frame_impl(a, stream, nullptr); }
+
+// Same frame with CUDA events between the stages; synchronises the stream and returns the stage times in milliseconds:
+// stage_ms[0] rigid + projection (+ tile count, records), [1] depth-ordered binning (both sorts, emission, offsets),
+// [2] compositing, [3] whole frame.  Measurement aid for bench.py; the product path is rs_render_frame.
+extern "C" int rs_render_frame_timed(const rs_frame_args *a, rs_stream_t stream, float *stage_ms) {
+    RS_CHECK(stage_ms != nullptr, "rs_render_frame_timed: null stage_ms");
+    static thread_local cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int i = 0; i < 4; ++i)
+        if (ev[i] == nullptr)
+            RS_CUDA(cudaEventCreate(&ev[i]));
+    if (int e = render_frame_impl(a, stream, ev))
+        return e;
+    RS_CUDA(cudaEventSynchronize(ev[3]));
+    for (int i = 0; i < 3; ++i)
+        RS_CUDA(cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]));
+    RS_CUDA(cudaEventElapsedTime(&stage_ms[3], ev[0], ev[3]));
+    return 0;
+}
+
+static int render_frame_impl(const rs_frame_args *a, rs_stream_t stream, cudaEvent_t *ev) {
     RS_CHECK(a != nullptr, "rs_render_frame: null args");
     rs_project_fwd_args p = a->proj;
     RS_CHECK(p.B == 1, "rs_render_frame: B must be 1");
@@ -144,8 +166,12 @@ extern "C" int rs_render_frame(const rs_frame_args *a, rs_stream_t stream) {
     p.records = reinterpret_cast<float *>(w + L.records);
     p.tiles_per_gauss = reinterpret_cast<int32_t *>(w + L.tiles_per_gauss);
     p.block_sums = reinterpret_cast<int32_t *>(w + L.block_sums);
+    if (ev)
+        RS_CUDA(cudaEventRecord(ev[0], s));
     if (int e = rs_project_fwd(&p, stream))
         return e;
+    if (ev)
+        RS_CUDA(cudaEventRecord(ev[1], s));
 
     rs_isect_sorted_args sa;
     memset(&sa, 0, sizeof(sa));
@@ -157,6 +183,8 @@ extern "C" int rs_render_frame(const rs_frame_args *a, rs_stream_t stream) {
     if (int e = rs_isect_sorted(&sa, stream))
         return e;
     const int32_t *vals_sorted = sa.isect.flatten_ids;
+    if (ev)
+        RS_CUDA(cudaEventRecord(ev[2], s));
 
     rs_raster_fwd_args r;
     memset(&r, 0, sizeof(r));
@@ -186,5 +214,9 @@ extern "C" int rs_render_frame(const rs_frame_args *a, rs_stream_t stream) {
     r.records = p.records;
     r.records_ready = 1;
     r.n_rows = (int64_t)p.C * p.N;
-    return rs_raster_fwd(&r, stream);
+    if (int e = rs_raster_fwd(&r, stream))
+        return e;
+    if (ev)
+        RS_CUDA(cudaEventRecord(ev[3], s));
+    return 0;
 }

@@ -198,22 +198,33 @@ rs_isect_offsets_kernel(const KeyT *__restrict__ isect_ids, int64_t n_bound, con
             offsets[i] = 0;
         return;
     }
-    // grid-stride: the grid is sized for the SM count, not for n_bound (which may be a loose capacity)
-    for (int64_t idx = first; idx < n_isects; idx += stride) {
-        const int64_t cur = (int64_t)(isect_ids[idx] >> HI);
-        const int64_t id_curr = (cur >> tile_n_bits) * n_tiles + (cur & ((1ll << tile_n_bits) - 1));
-        if (idx == 0) {
-            for (int64_t i = 0; i < id_curr + 1; ++i)
-                offsets[i] = 0;
+    // grid-stride: the grid is sized for the SM count, not for n_bound (which may be a loose capacity); 4 independent
+    // (current, previous) load pairs per thread and iteration
+    constexpr int UNROLL = 4;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x * UNROLL; base < n_isects; base += stride * UNROLL) {
+        int64_t cur[UNROLL], prev[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t idx = base + (int64_t)u * blockDim.x + threadIdx.x;
+            cur[u] = idx < n_isects ? (int64_t)(isect_ids[idx] >> HI) : 0;
+            prev[u] = (idx < n_isects && idx > 0) ? (int64_t)(isect_ids[idx - 1] >> HI) : 0;
         }
-        if (idx == n_isects - 1) {
-            for (int64_t i = id_curr + 1; i < (int64_t)I * n_tiles; ++i)
-                offsets[i] = (int32_t)n_isects;
-        }
-        if (idx > 0) {
-            const int64_t prev = (int64_t)(isect_ids[idx - 1] >> HI);
-            if (prev != cur) {
-                const int64_t id_prev = (prev >> tile_n_bits) * n_tiles + (prev & ((1ll << tile_n_bits) - 1));
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t idx = base + (int64_t)u * blockDim.x + threadIdx.x;
+            if (idx >= n_isects)
+                continue;
+            const int64_t id_curr = (cur[u] >> tile_n_bits) * n_tiles + (cur[u] & ((1ll << tile_n_bits) - 1));
+            if (idx == 0) {
+                for (int64_t i = 0; i < id_curr + 1; ++i)
+                    offsets[i] = 0;
+            }
+            if (idx == n_isects - 1) {
+                for (int64_t i = id_curr + 1; i < (int64_t)I * n_tiles; ++i)
+                    offsets[i] = (int32_t)n_isects;
+            }
+            if (idx > 0 && prev[u] != cur[u]) {
+                const int64_t id_prev = (prev[u] >> tile_n_bits) * n_tiles + (prev[u] & ((1ll << tile_n_bits) - 1));
                 for (int64_t i = id_prev + 1; i < id_curr + 1; ++i)
                     offsets[i] = (int32_t)idx;
             }

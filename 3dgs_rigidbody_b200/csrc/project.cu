@@ -13,7 +13,7 @@ struct ProjSmem {
 };
 
 template <bool HAS_RIGID>
-__global__ void __launch_bounds__(RS_ISECT_THREADS)
+__global__ void __launch_bounds__(RS_ISECT_THREADS, 3)
 rs_project_fwd_kernel(const rs_project_fwd_args a) {
     extern __shared__ __align__(16) float smem_dyn[]; // pose table (HAS_RIGID only)
     __shared__ ProjSmem sm;

@@ -76,7 +76,7 @@ __device__ __forceinline__ void rs_cp_async_mbar_arrive(uint64_t *bar) {
 #define RAST_THREADS (32 * (RAST_CONSUMERS + 1)) // + one producer warp
 template <int CDIM> struct RastCfg {
     static constexpr int CP = (CDIM + 3) & ~3;
-    static constexpr int STAGES = (CDIM <= 8) ? 3 : 2;
+    static constexpr int STAGES = (CDIM <= 4) ? 4 : (CDIM <= 16 ? 3 : 2);
     static constexpr int STAGE_FLOATS = RAST_BATCH * (8 + CP);
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_FLOATS * sizeof(float);
 };

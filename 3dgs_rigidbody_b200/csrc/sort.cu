@@ -82,23 +82,33 @@ sort_hist_kernel(const KeyT *__restrict__ keys, int64_t n_bound, const int32_t *
         h[p][threadIdx.x] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    for (int64_t base = (int64_t)blockIdx.x * SORT_THREADS; base < n; base += (int64_t)gridDim.x * SORT_THREADS) {
-        const int64_t idx = base + threadIdx.x;
-        const bool valid = idx < n;
-        const KeyT key = valid ? keys[idx] : (KeyT)0;
-        for (int p = 0; p < passes; ++p) {
-            const int shift = begin_bit + p * RADIX_BITS;
-            const int bits = min(RADIX_BITS, end_bit - shift);
-            const uint32_t d = (uint32_t)(key >> shift) & ((1u << bits) - 1u);
-            // nearly sorted inputs (tile ids in emission order) put a whole warp on one digit: count it with one add
-            const uint32_t d0 = __shfl_sync(0xffffffffu, d, 0);
-            const unsigned same = __ballot_sync(0xffffffffu, valid && d == d0);
-            const unsigned act = __ballot_sync(0xffffffffu, valid);
-            if (same == act) {
-                if (lane == 0 && act)
-                    atomicAdd(&h[p][d0], (unsigned)__popc(act));
-            } else if (valid) {
-                atomicAdd(&h[p][d], 1u);
+    constexpr int UNROLL = 4; // independent loads in flight per thread
+    for (int64_t base = (int64_t)blockIdx.x * (SORT_THREADS * UNROLL); base < n;
+         base += (int64_t)gridDim.x * (SORT_THREADS * UNROLL)) {
+        KeyT key[UNROLL];
+        bool valid[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const int64_t idx = base + u * SORT_THREADS + threadIdx.x;
+            valid[u] = idx < n;
+            key[u] = valid[u] ? keys[idx] : (KeyT)0;
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const unsigned act = __ballot_sync(0xffffffffu, valid[u]);
+            for (int p = 0; p < passes; ++p) {
+                const int shift = begin_bit + p * RADIX_BITS;
+                const int bits = min(RADIX_BITS, end_bit - shift);
+                const uint32_t d = (uint32_t)(key[u] >> shift) & ((1u << bits) - 1u);
+                // nearly sorted inputs (tile ids in emission order) put a whole warp on one digit: one add for all
+                const uint32_t d0 = __shfl_sync(0xffffffffu, d, __ffs(act | 0x80000000u) - 1);
+                const unsigned same = __ballot_sync(0xffffffffu, valid[u] && d == d0);
+                if (same == act) {
+                    if (lane == 0 && act)
+                        atomicAdd(&h[p][d0], (unsigned)__popc(act));
+                } else if (valid[u]) {
+                    atomicAdd(&h[p][d], 1u);
+                }
             }
         }
     }
@@ -307,7 +317,7 @@ static int radix_sort_impl(int64_t n_bound, const int32_t *n_dev, int begin_bit,
     }
     const int sms = rs_num_sms();
     RS_CUDA(cudaMemsetAsync(ws, 0, (size_t)WS_LOOKBACK * sizeof(uint32_t), s));
-    const int hist_grid = (int)min((int64_t)sms * 8, (n_bound + SORT_THREADS - 1) / SORT_THREADS);
+    const int hist_grid = (int)min((int64_t)sms * 2, (n_bound + SORT_THREADS * 4 - 1) / (SORT_THREADS * 4));
     sort_hist_kernel<KeyT><<<hist_grid, SORT_THREADS, 0, s>>>(keys_in, n_bound, n_dev, begin_bit, end_bit, passes, nb,
                                                               ws);
     RS_LAUNCH_CHECK("sort_hist_kernel");

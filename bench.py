@@ -248,99 +248,51 @@ def reference_arm(args):
 # ----------------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------------
-def stage_breakdown(rs, torch, sc, bq, bt, peak_gbs, reps=5):
-    """One frame through the separate C-ABI entry points (the `_C` operator shim) with CUDA events per stage."""
-    C = rs._C
-    dev = sc["means"].device
-    rp = rs.RigidPoses(sc["cluster_ids"], bq, bt, sc["body_centers"])
-    tw, th = (WIDTH + 15) // 16, (HEIGHT + 15) // 16
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-    acc = {}
-    M = V = 0
-    for rep in range(reps + 1):
-        marks = [("start", ev())]
-        marks[0][1].record()
-        radii, means2d, depths, conics, _ = C.projection_ewa_3dgs_fused_fwd(
-            sc["means"], None, sc["quats"], sc["scales"], sc["opacities"], sc["viewmats"], sc["Ks"], WIDTH, HEIGHT, 0.3,
-            0.01, 1e10, 0.0, False, C.PINHOLE, rp)
-        e = ev(); e.record(); marks.append(("rigid+project", e))
-        tpg, isect_ids, flatten_ids = C.intersect_tile(means2d, radii, depths, None, None, 1, 16, tw, th, True, False)
-        e = ev(); e.record(); marks.append(("isect count+scan+emit+sort (incl. host sync)", e))
-        offs = C.intersect_offset(isect_ids, 1, tw, th)
-        e = ev(); e.record(); marks.append(("offsets", e))
-        out = C.rasterize_to_pixels_3dgs_fwd(means2d[0], conics[0], sc["colors"], sc["opacities"], None, None, WIDTH,
-                                             HEIGHT, 16, offs, flatten_ids)
-        e = ev(); e.record(); marks.append(("composite fwd", e))
-        torch.cuda.synchronize()
-        M = int(isect_ids.numel())
-        V = int((radii > 0).all(-1).sum())
-        if rep == 0:
-            continue
-        for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
-            acc.setdefault(n1, []).append(e0.elapsed_time(e1))
-        del out
-    N = sc["means"].shape[0]
-    D = sc["colors"].shape[1]
-    P = WIDTH * HEIGHT
-    bits = 32 + (tw * th).bit_length() + 1
-    passes = (bits + 7) // 8
+def stage_breakdown(fr, sc, q_all, t_all, frames, peak_gbs, peak_src, n_tiles):
+    """Per-stage CUDA-event times of the SAME frames through the frame path itself (rs_render_frame_timed records events
+    between the stages of rs_render_frame).  Returns (stages, roofline): `stages` lists every stage with its algorithmic
+    bytes (SURVEY.md section 8d formulas, with this scene's measured M) and achieved GB/s; `roofline` is the dominant
+    kernel of the step (compositing: one launch of rs_raster_fwd_kernel per frame)."""
+    ms = np.array([fr.render_timed(sc["viewmats"], sc["Ks"], q_all[f], t_all[f]) for f in frames], np.float64)
+    mean = ms.mean(0)
+    N, D, C = fr.N, fr.D, fr.C
+    E, P = C * N, C * fr.W * fr.H
+    M = fr.n_isects()
+    key_bits = 32 + int(n_tiles).bit_length() + int(C).bit_length()
+    ref_passes = (key_bits + 7) // 8
+    tile_passes = (key_bits - 32 + 7) // 8
     alg = {
-        "rigid+project": N * (12 + 16 + 12 + 4 + 4) + N * 32,
-        "isect count+scan+emit+sort (incl. host sync)": N * 32 + N * 20 + M * 12 + M * 8 + passes * 2 * M * 12,
-        "offsets": M * 8 + tw * th * 4,
-        "composite fwd": M * (4 + 28 + 4 * D) + P * (D + 2) * 4,
+        "rigid+project": N * 48 + E * 32,
+        # what the reference's count + cumsum + emission + 64-bit cub sort + offsets move (SURVEY 8d)
+        "binning": E * 32 + (E * 20 + M * 12) + (M * 8 + ref_passes * 2 * M * 12) + (M * 8 + n_tiles * C * 4),
+        "composite": M * (4 + 28 + 4 * D) + P * (D + 2) * 4,
     }
+    # what the depth-ordered scheme actually has to move: depth sort (hist + 4 passes of 8-byte pairs), ordered count
+    # and emission, tile sort (hist + passes of 8-byte pairs), offsets
+    moved_binning = E * 4 + 4 * E * 16 + E * 8 + (E * 24 + M * 8) + M * 4 + tile_passes * M * 16 + M * 4
     stages = []
-    for name, ts in acc.items():
-        ms = float(np.median(ts))
-        gbs = alg[name] / (ms * 1e-3) / 1e9
-        stages.append({"stage": name, "ms": round(ms, 4), "algorithmic_MB": round(alg[name] / 1e6, 1),
-                       "GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak_gbs, 4)})
-    return stages, M, V
-
-
-def sort_roofline(rs, torch, M, end_bit, peak_gbs, peak_src, reps=10):
-    """The dominant HBM-bound kernel: one LSD radix-sort pass over the frame's M (u64 key, i32 value) pairs.  Timed live:
-    the full sort (all passes) between CUDA events, divided by the number of scatter launches; algorithmic bytes per
-    pass = M * (8 histogram read + 12 read + 12 write)."""
-    import ctypes
-
-    _lib = importlib.import_module("3dgs_rigidbody_b200._lib")
-    lib = _lib.load()
-    dev = "cuda:0" if not torch.cuda.current_device() else f"cuda:{torch.cuda.current_device()}"
-    g = torch.Generator(device=dev).manual_seed(1)
-    keys = torch.randint(0, 1 << end_bit, (M,), dtype=torch.int64, device=dev, generator=g)
-    vals = torch.arange(M, dtype=torch.int32, device=dev)
-    ka, kb = torch.empty_like(keys), torch.empty_like(keys)
-    va, vb = torch.empty_like(vals), torch.empty_like(vals)
-    ws_bytes = lib.rs_radix_sort_workspace_bytes(M)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    passes = (end_bit + 7) // 8
-    times = []
-    stream = torch.cuda.current_stream().cuda_stream
-    for rep in range(reps + 2):
-        ka.copy_(keys)
-        va.copy_(vals)
-        a = _lib.rs_sort_args()
-        a.n, a.n_dev, a.begin_bit, a.end_bit = M, None, 0, end_bit
-        a.keys_a, a.keys_b, a.vals_a, a.vals_b = ka.data_ptr(), kb.data_ptr(), va.data_ptr(), vb.data_ptr()
-        a.workspace, a.workspace_bytes = ws.data_ptr(), ws_bytes
-        res = ctypes.c_int32(0)
-        a.result_in_b = ctypes.addressof(res)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        _lib.check(lib.rs_radix_sort_pairs(ctypes.byref(a), stream))
-        e1.record()
-        torch.cuda.synchronize()
-        if rep >= 2:
-            times.append(e0.elapsed_time(e1))
-    ms_pass = float(np.median(times)) / passes
-    bytes_pass = M * (8 + 12 + 12)
-    achieved = bytes_pass / (ms_pass * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "radix sort pass (sort_hist + sort_scan_rows + sort_scatter), u64 key + i32 value",
-            "achieved": round(achieved, 1), "peak": peak_gbs, "unit": "GB/s", "frac": round(achieved / peak_gbs, 4),
-            "traffic": None, "peak_source": peak_src, "pairs": M, "passes": passes, "ms_per_pass": round(ms_pass, 4),
-            "algorithmic_bytes_per_launch": bytes_pass}
+    for k, name in enumerate(("rigid+project", "binning", "composite")):
+        t = float(mean[k]) * 1e-3
+        st = {"stage": name, "ms": round(float(mean[k]), 4), "algorithmic_MB": round(alg[name] / 1e6, 1),
+              "GBps": round(alg[name] / t / 1e9, 1), "frac_of_hbm_peak": round(alg[name] / t / 1e9 / peak_gbs, 4)}
+        if name == "binning":
+            st["bytes_actually_moved_MB"] = round(moved_binning / 1e6, 1)
+            st["GBps_actually_moved"] = round(moved_binning / t / 1e9, 1)
+            st["note"] = ("algorithmic bytes = the reference's 64-bit LSD sort accounting (SURVEY 8d); the depth-ordered "
+                          "scheme moves far fewer bytes, so the first fraction may exceed what the kernels stream")
+        stages.append(st)
+    t_c = float(mean[2]) * 1e-3
+    achieved = alg["composite"] / t_c / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": "rs_raster_fwd_kernel (compositing, 1 launch/frame: the largest share of the step)",
+        "achieved": round(achieved, 1), "peak": peak_gbs, "unit": "GB/s", "frac": round(achieved / peak_gbs, 4),
+        "traffic": 70.46e6, "traffic_source": "ncu --set full r01 (profiles/r01c_kernels_ncu_full.txt): dram read+write per launch",
+        "peak_source": peak_src, "algorithmic_bytes_per_launch": alg["composite"], "ms_per_launch": round(float(mean[2]), 4),
+        "frames_timed": int(len(frames)),
+        "note": "this kernel is bound by SM issue (FP32 FMA + MUFU.EX2 + LDS), not by HBM: see profiles/ for issue-slot "
+                "utilisation; HBM-bound stages are in `stages`",
+    }
+    return stages, roofline, float(mean[3]), M
 
 
 def ours_arm(args):
@@ -491,13 +443,12 @@ def ours_arm(args):
         "clocks": clocks,
     }
     if world == 1 and not args.no_extras:
-        tw, th = (WIDTH + 15) // 16, (HEIGHT + 15) // 16
-        end_bit = 32 + (tw * th).bit_length() + 1
-        f = frames[-1]
-        stages, M, V = stage_breakdown(rs, torch, sc, q_all[f], t_all[f], peak_gbs)
+        n_tiles = ((WIDTH + 15) // 16) * ((HEIGHT + 15) // 16)
+        stages, roofline, frame_ms, M = stage_breakdown(fr, sc, q_all, t_all, frames[args.warmup:], peak_gbs, peak_src,
+                                                        n_tiles)
         line["stages"] = stages
-        line["config"]["visible_gaussians"] = V
-        line["roofline"] = sort_roofline(rs, torch, M, end_bit, peak_gbs, peak_src)
+        line["roofline"] = roofline
+        line["config"]["frame_ms_with_stage_events"] = round(frame_ms, 4)
         torch.cuda.empty_cache()
         budget = args.cpu_budget
         cpu_frames = [(60 + 37 * i) % N_FRAMES for i in range(64)]  # stops at the CPU budget below

@@ -268,6 +268,9 @@ typedef struct {
 uint64_t rs_frame_workspace_bytes(int32_t C, int32_t N, int32_t image_width, int32_t image_height, int32_t tile_size,
                                   int32_t channels, int64_t max_isects);
 int rs_render_frame(const rs_frame_args *a, rs_stream_t stream);
+/* Measurement aid: the same frame with CUDA events between its stages; synchronises the stream.  stage_ms (host, [4]) =
+ * {rigid + projection, binning (sorts, emission, offsets), compositing, whole frame} in milliseconds. */
+int rs_render_frame_timed(const rs_frame_args *a, rs_stream_t stream, float *stage_ms);
 /* device pointers into a frame workspace, for tests and `meta`: which = 0 isect_ids(sorted), 1 flatten_ids(sorted),
  * 2 tile_offsets, 3 last_ids, 4 tiles_per_gauss.  Valid after rs_render_frame on the same workspace geometry. */
 void *rs_frame_workspace_ptr(const rs_frame_args *a, int which);
