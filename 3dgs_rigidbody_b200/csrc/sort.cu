@@ -131,14 +131,24 @@ sort_hist_kernel(const KeyT *__restrict__ keys, int64_t n_bound, const int32_t *
 template <typename KeyT> struct SortSmem {
     KeyT keys[SORT_TILE];
     int32_t vals[SORT_TILE];
+    int32_t vals_stage[SORT_TILE]; // the tile's values in input order, landed by cp.async while the keys are ranked
     int wh[SORT_WARPS][RADIX]; // per-warp digit counters -> exclusive per-warp offsets
     int bin_start[RADIX];      // first slot of each digit inside the re-ordered tile
-    int64_t gbase[RADIX];      // global index of that first slot
+    int delta[RADIX];          // global index of slot i of the re-ordered tile = delta[digit] + i
+    int real[RADIX];           // digit counts of this tile without padding
     int gstart[RADIX];         // exclusive scan of the global digit histogram
     int wsum[SORT_WARPS];
     int tile;
 };
 
+__device__ __forceinline__ void sort_cp_async16(void *smem, const void *gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem)
+                 : "memory");
+}
+__device__ __forceinline__ void sort_cp_async4(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem)
+                 : "memory");
+}
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
     uint32_t v;
     asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
@@ -184,38 +194,56 @@ sort_pass_kernel(const KeyT *__restrict__ keys_in, const int32_t *__restrict__ v
 
         // warp-striped load: warp w owns [w*512, (w+1)*512), item k of lane l sits at k*32 + l
         KeyT key[SORT_ITEMS];
-        int32_t val[SORT_ITEMS];
         const int wbase = warp * (32 * SORT_ITEMS);
 #pragma unroll
         for (int k = 0; k < SORT_ITEMS; ++k) {
             const int local = wbase + k * 32 + lane;
-            if (local < count) {
-                key[k] = keys_in[tile_start + local];
-                val[k] = vals_in != nullptr ? vals_in[tile_start + local] : (int32_t)(tile_start + local);
-            } else {
-                key[k] = ~(KeyT)0; // sorts to the very end of the tile, never written out
-                val[k] = 0;
-            }
+            key[k] = (local < count) ? keys_in[tile_start + local]
+                                     : ~(KeyT)0; // sorts to the very end of the tile, never written out
         }
 
+        // values: asynchronous copy into shared memory (no registers held across the ranking)
+        if (vals_in != nullptr) {
+            const int32_t *src = vals_in + tile_start;
+            if (count == SORT_TILE && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+#pragma unroll
+                for (int q = 0; q < SORT_TILE / (SORT_THREADS * 4); ++q) {
+                    const int e = (q * SORT_THREADS + threadIdx.x) * 4;
+                    sort_cp_async16(&sm.vals_stage[e], src + e);
+                }
+            } else {
+                for (int e = threadIdx.x; e < count; e += SORT_THREADS)
+                    sort_cp_async4(&sm.vals_stage[e], src + e);
+            }
+            asm volatile("cp.async.commit_group;\n" ::: "memory");
+        }
+
+        // Stable ranks.  All SORT_ITEMS match operations are independent (pipelined); the per-warp digit counters are
+        // bumped with shared-memory atomics by the leader lane of each peer group: atomics of one warp reach the LSU in
+        // program order, so round k is counted before round k+1 without any read-modify-write dependency chain.
+        unsigned peers[SORT_ITEMS];
+#pragma unroll
+        for (int k = 0; k < SORT_ITEMS; ++k)
+            peers[k] = __match_any_sync(0xffffffffu, (uint32_t)(key[k] >> shift) & mask);
         int rank[SORT_ITEMS];
 #pragma unroll
         for (int k = 0; k < SORT_ITEMS; ++k) {
             const uint32_t d = (uint32_t)(key[k] >> shift) & mask;
-            const unsigned peers = __match_any_sync(0xffffffffu, d);
-            const int leader = __ffs(peers) - 1;
+            const int leader = __ffs(peers[k]) - 1;
             int old = 0;
-            if (lane == leader) {
-                old = sm.wh[warp][d];
-                sm.wh[warp][d] = old + __popc(peers);
-            }
-            old = __shfl_sync(0xffffffffu, old, leader);
-            rank[k] = old + __popc(peers & lt);
+            if (lane == leader)
+                old = atomicAdd(&sm.wh[warp][d], __popc(peers[k]));
             __syncwarp();
+            rank[k] = old;
+        }
+#pragma unroll
+        for (int k = 0; k < SORT_ITEMS; ++k) {
+            const int leader = __ffs(peers[k]) - 1;
+            rank[k] = __shfl_sync(0xffffffffu, rank[k], leader) + __popc(peers[k] & lt);
         }
         __syncthreads();
 
-        // thread t handles digit t: per-warp exclusive offsets, tile-level digit start, look-back for the global base
+        // thread t handles digit t: per-warp exclusive offsets, tile-level digit start, published aggregate
         {
             int sum = 0;
 #pragma unroll
@@ -229,52 +257,61 @@ sort_pass_kernel(const KeyT *__restrict__ keys_in, const int32_t *__restrict__ v
             int real = sum;
             if (count < SORT_TILE && threadIdx.x == (int)(((uint32_t)((~(KeyT)0) >> shift)) & mask))
                 real = sum - (SORT_TILE - count);
-            uint32_t *mine = lookback + (size_t)tile * RADIX + threadIdx.x;
-            st_volatile_u32(mine, (tile == 0 ? LB_INCLUSIVE : LB_AGGREGATE) | (uint32_t)real);
-            const int start = block_excl_scan_256(sum, sm.wsum, nullptr);
-            int64_t excl = 0;
+            st_volatile_u32(lookback + (size_t)tile * RADIX + threadIdx.x,
+                            (tile == 0 ? LB_INCLUSIVE : LB_AGGREGATE) | (uint32_t)real);
+            sm.real[threadIdx.x] = real;
+            const int start = block_excl_scan_256(sum, sm.wsum, nullptr); // (contains the barrier that publishes sm.real)
+            sm.bin_start[threadIdx.x] = start;
+        }
+        // Decoupled look-back, one digit per thread.  Windowed: LB_WINDOW independent loads per L2 round trip -- when all
+        // tiles of a wave start together, the inclusive prefix can only advance one window per round trip, and that chain
+        // of round trips (not bandwidth, not instruction issue) is what bounds a pass.
+        {
+            const int d = threadIdx.x;
+            int excl = 0;
             if (tile > 0) {
-                // Windowed look-back: when all tiles of a wave start together, walking one predecessor per L2 round trip
-                // serialises the wave; LB_WINDOW independent loads per round trip cut that chain by the window size.
                 int t = tile - 1;
                 bool found = false;
                 while (!found) {
                     uint32_t v[LB_WINDOW];
 #pragma unroll
-                    for (int j = 0; j < LB_WINDOW; ++j)
-                        v[j] = (t - j >= 0) ? ld_volatile_u32(lookback + (size_t)(t - j) * RADIX + threadIdx.x)
-                                            : LB_INCLUSIVE; // before tile 0: inclusive prefix 0
+                    for (int jj = 0; jj < LB_WINDOW; ++jj)
+                        v[jj] = (t - jj >= 0) ? ld_volatile_u32(lookback + (size_t)(t - jj) * RADIX + d)
+                                              : LB_INCLUSIVE; // before tile 0: inclusive prefix 0
                     int used = 0;
 #pragma unroll
-                    for (int j = 0; j < LB_WINDOW; ++j) {
-                        if (!found && used == j && (v[j] & (LB_AGGREGATE | LB_INCLUSIVE)) != 0u) {
-                            excl += (int64_t)(v[j] & LB_VALUE);
+                    for (int jj = 0; jj < LB_WINDOW; ++jj) {
+                        if (!found && used == jj && (v[jj] & (LB_AGGREGATE | LB_INCLUSIVE)) != 0u) {
+                            excl += (int)(v[jj] & LB_VALUE);
                             ++used;
-                            found = (v[j] & LB_INCLUSIVE) != 0u;
+                            found = (v[jj] & LB_INCLUSIVE) != 0u;
                         }
                     }
                     t -= used;
                 }
-                st_volatile_u32(mine, LB_INCLUSIVE | (uint32_t)(excl + real));
+                st_volatile_u32(lookback + (size_t)tile * RADIX + d, LB_INCLUSIVE | (uint32_t)(excl + sm.real[d]));
             }
-            sm.bin_start[threadIdx.x] = start;
-            sm.gbase[threadIdx.x] = (int64_t)sm.gstart[threadIdx.x] + excl;
+            // global index of slot i of the re-ordered tile = delta[digit] + i
+            sm.delta[d] = sm.gstart[d] + excl - sm.bin_start[d];
         }
-        __syncthreads();
+        asm volatile("cp.async.wait_group 0;\n" ::: "memory"); // this thread's value copies have landed ...
+        __syncthreads();                                       // ... and so have everyone else's
 
 #pragma unroll
         for (int k = 0; k < SORT_ITEMS; ++k) {
             const uint32_t d = (uint32_t)(key[k] >> shift) & mask;
             const int pos = sm.bin_start[d] + sm.wh[warp][d] + rank[k];
+            const int local = wbase + k * 32 + lane;
             sm.keys[pos] = key[k];
-            sm.vals[pos] = val[k];
+            if (local < count)
+                sm.vals[pos] = vals_in != nullptr ? sm.vals_stage[local] : (int32_t)(tile_start + local);
         }
         __syncthreads();
 
         for (int i = threadIdx.x; i < count; i += SORT_THREADS) {
             const KeyT kk = sm.keys[i];
             const uint32_t d = (uint32_t)(kk >> shift) & mask;
-            const int64_t out = sm.gbase[d] + (i - sm.bin_start[d]);
+            const int64_t out = (int64_t)(sm.delta[d] + i);
             keys_out[out] = kk;
             vals_out[out] = sm.vals[i];
         }
