@@ -13,7 +13,7 @@ Public surface (mirrors the reference):
 """
 from . import _C  # noqa: F401
 from ._C import RigidPoses, RigidSplatError  # noqa: F401
-from .animation import FrameRenderer  # noqa: F401
+from .animation import FramePipeline, FrameRenderer  # noqa: F401
 from .rendering import rasterization  # noqa: F401
 from .rigid import body_centers, cluster_ids_from_groups, make_rigid  # noqa: F401
 from .sh import spherical_harmonics  # noqa: F401

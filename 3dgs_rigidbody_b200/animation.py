@@ -180,3 +180,49 @@ class FrameRenderer:
             "tile_width": self.tile_width,
             "tile_height": self.tile_height,
         }
+
+
+class FramePipeline:
+    """Several frames in flight on one GPU.
+
+    Animation frames are independent units (that is also how they shard across GPUs).  At 1 M
+    Gaussians most stages of a frame are short latency-bound kernels that leave most of the 148 SMs idle, while
+    compositing saturates the issue slots; giving every in-flight frame its own stream and workspace lets the binning of
+    frame f+1 run underneath the compositing of frame f.  `depth` FrameRenderers share the (read-only) Gaussian tensors.
+
+        pipe = FramePipeline(3, means, quats, scales, opacities, colors, W, H, cluster_ids=ids, body_centers=c)
+        for f in range(F):
+            img, alpha, done = pipe.submit(viewmats, Ks, body_quats[f], body_trans[f])   # enqueue only
+            ...                                                                           # consume after done.wait()
+        pipe.join()                                                                       # current stream waits for all
+    The returned buffers belong to the renderer that drew the frame and are overwritten `depth` submissions later.
+    """
+
+    def __init__(self, depth: int, *args, **kwargs):
+        assert depth >= 1
+        self.renderers = [FrameRenderer(*args, **kwargs) for _ in range(depth)]
+        dev = self.renderers[0].device
+        with torch.cuda.device(dev):
+            self.streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+        self.device = dev
+        self.count = 0
+
+    def submit(self, viewmats: Tensor, Ks: Tensor, body_quats: Optional[Tensor] = None,
+               body_trans: Optional[Tensor] = None):
+        k = self.count % len(self.renderers)
+        self.count += 1
+        stream = self.streams[k]
+        stream.wait_stream(torch.cuda.current_stream(self.device))  # the frame's inputs were produced there
+        with torch.cuda.stream(stream):
+            img, alpha = self.renderers[k].render(viewmats, Ks, body_quats, body_trans)
+            done = torch.cuda.Event()
+            done.record(stream)
+        return img, alpha, done
+
+    def join(self) -> None:
+        cur = torch.cuda.current_stream(self.device)
+        for s in self.streams:
+            cur.wait_stream(s)
+
+    def overflowed(self) -> bool:
+        return any(r.overflowed() for r in self.renderers)

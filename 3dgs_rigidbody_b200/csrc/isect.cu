@@ -351,12 +351,25 @@ rs_bin_count_kernel(int64_t n_elems, const int32_t *__restrict__ elems, const in
         block_sums[blockIdx.x] = s;
 }
 
+// Emission in depth order.  A CTA owns RS_ISECT_BLOCK depth-consecutive elements (4 per thread, blocked); after a CTA
+// scan of their tile counts, every thread walks the tiles of its own elements (row-major, no division in the loop) and
+// writes (image|tile key, flatten id) into a shared-memory window of EMIT_CHUNK output slots; the window is then copied
+// to global memory with fully coalesced stores.  Elements covering more than EMIT_BIG tiles (a splat filling the
+// screen) are filled by the whole CTA instead of one thread, so a single huge Gaussian cannot serialise the CTA.
+#define EMIT_CHUNK 4096
+#define EMIT_BIG 64
 struct BinEmitSmem {
     int32_t excl[RS_ISECT_BLOCK + 1];
-    uint32_t rect[RS_ISECT_BLOCK];  // x0 | y0 << 16
-    uint32_t width[RS_ISECT_BLOCK]; // x1 - x0
-    uint32_t hi[RS_ISECT_BLOCK];    // image id << tile_n_bits
-    int32_t elem[RS_ISECT_BLOCK];
+    uint32_t skey[EMIT_CHUNK];
+    int32_t sval[EMIT_CHUNK];
+    // elements with more than EMIT_BIG tiles
+    int32_t big_start[RS_ISECT_BLOCK / 4];
+    uint32_t big_rect[RS_ISECT_BLOCK / 4]; // x0 | y0 << 16
+    uint32_t big_wh[RS_ISECT_BLOCK / 4];   // width | count... (width in the low 16 bits)
+    int32_t big_cnt[RS_ISECT_BLOCK / 4];
+    uint32_t big_hi[RS_ISECT_BLOCK / 4];
+    int32_t big_elem[RS_ISECT_BLOCK / 4];
+    int32_t n_big;
     int32_t warp_tot[8];
 };
 
@@ -366,13 +379,18 @@ rs_bin_emit_kernel(const rs_isect_args a, const int32_t *__restrict__ elems, uin
     __shared__ BinEmitSmem sm;
     const int64_t base = (int64_t)blockIdx.x * RS_ISECT_BLOCK;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int cnt[4];
+    if (threadIdx.x == 0)
+        sm.n_big = 0;
+    int cnt[4], elem[4];
+    uint32_t x0[4], y0[4], w[4], hi[4];
     int tsum = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int slot = threadIdx.x * 4 + k;
-        const int64_t i = base + slot;
+        const int64_t i = base + threadIdx.x * 4 + k;
         int c = 0;
+        elem[k] = 0;
+        x0[k] = y0[k] = hi[k] = 0;
+        w[k] = 1;
         if (i < a.n_elems) {
             const int32_t e = elems[i];
             c = a.tiles_per_gauss[e];
@@ -381,11 +399,12 @@ rs_bin_emit_kernel(const rs_isect_args a, const int32_t *__restrict__ elems, uin
                 const float2 m = reinterpret_cast<const float2 *>(a.means2d)[e];
                 const RsTileRect tr = rs_tile_rect(m.x, m.y, (float)r.x, (float)r.y, (uint32_t)a.tile_size,
                                                    (uint32_t)a.tile_width, (uint32_t)a.tile_height);
-                sm.rect[slot] = tr.x0 | (tr.y0 << 16);
-                sm.width[slot] = tr.x1 - tr.x0;
+                x0[k] = tr.x0;
+                y0[k] = tr.y0;
+                w[k] = tr.x1 - tr.x0;
                 const uint32_t iid = (a.image_ids != nullptr) ? (uint32_t)a.image_ids[e] : (uint32_t)(e / a.N);
-                sm.hi[slot] = iid << tile_n_bits;
-                sm.elem[slot] = e;
+                hi[k] = iid << tile_n_bits;
+                elem[k] = e;
             }
         }
         cnt[k] = c;
@@ -401,42 +420,82 @@ rs_bin_emit_kernel(const rs_isect_args a, const int32_t *__restrict__ elems, uin
     if (lane == 31)
         sm.warp_tot[warp] = incl;
     __syncthreads();
-    int wbase = 0;
+    int wbase = 0, total = 0;
 #pragma unroll
-    for (int w = 0; w < 8; ++w)
-        wbase += (w < warp) ? sm.warp_tot[w] : 0;
-    int run = wbase + incl - tsum;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        sm.excl[threadIdx.x * 4 + k] = run;
-        run += cnt[k];
+    for (int q = 0; q < 8; ++q) {
+        const int t = sm.warp_tot[q];
+        wbase += (q < warp) ? t : 0;
+        total += t;
     }
-    if (threadIdx.x == RS_ISECT_THREADS - 1)
-        sm.excl[RS_ISECT_BLOCK] = run;
-    __syncthreads();
-
-    const int total = sm.excl[RS_ISECT_BLOCK];
-    const int64_t out_base = a.block_sums[blockIdx.x];
-    for (int j = threadIdx.x; j < total; j += RS_ISECT_THREADS) {
-        int lo = 0, hi = RS_ISECT_BLOCK;
+    int start[4];
+    {
+        int run = wbase + incl - tsum;
 #pragma unroll
-        for (int step = 0; step < 10; ++step) {
-            const int mid = (lo + hi) >> 1;
-            if (sm.excl[mid] <= j)
-                lo = mid;
-            else
-                hi = mid;
+        for (int k = 0; k < 4; ++k) {
+            start[k] = run;
+            run += cnt[k];
+            if (cnt[k] > EMIT_BIG) { // handed to the whole CTA
+                const int slot = atomicAdd(&sm.n_big, 1);
+                if (slot < RS_ISECT_BLOCK / 4) {
+                    sm.big_start[slot] = start[k];
+                    sm.big_rect[slot] = x0[k] | (y0[k] << 16);
+                    sm.big_wh[slot] = w[k];
+                    sm.big_cnt[slot] = cnt[k];
+                    sm.big_hi[slot] = hi[k];
+                    sm.big_elem[slot] = elem[k];
+                    cnt[k] = 0; // not filled by this thread
+                }
+            }
         }
-        const int slot = lo;
-        const uint32_t r = (uint32_t)(j - sm.excl[slot]);
-        const uint32_t w = sm.width[slot];
-        const uint32_t ty = (sm.rect[slot] >> 16) + r / w;
-        const uint32_t tx = (sm.rect[slot] & 0xffffu) + r % w;
-        const int64_t o = out_base + j;
-        if (o < a.capacity) {
-            tile_keys[o] = sm.hi[slot] | (ty * (uint32_t)a.tile_width + tx);
-            vals[o] = sm.elem[slot];
+    }
+    __syncthreads();
+    const int n_big = min(sm.n_big, RS_ISECT_BLOCK / 4);
+    const int64_t out_base = a.block_sums[blockIdx.x]; // exclusive offset of this block (after the scan kernel)
+    const uint32_t tile_w = (uint32_t)a.tile_width;
+
+    for (int B = 0; B < total; B += EMIT_CHUNK) {
+        const int Bend = B + EMIT_CHUNK;
+        // every thread: the tiles of its own (small) elements that fall into this window
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int s0 = start[k], s1 = start[k] + cnt[k];
+            const int lo = max(s0, B), up = min(s1, Bend);
+            if (lo < up) {
+                const uint32_t r = (uint32_t)(lo - s0);
+                uint32_t ty = y0[k] + r / w[k];
+                uint32_t tx = x0[k] + r % w[k];
+                const uint32_t xe = x0[k] + w[k];
+                for (int sl = lo; sl < up; ++sl) {
+                    sm.skey[sl - B] = hi[k] | (ty * tile_w + tx);
+                    sm.sval[sl - B] = elem[k];
+                    if (++tx == xe) {
+                        tx = x0[k];
+                        ++ty;
+                    }
+                }
+            }
         }
+        // the whole CTA: big elements
+        for (int q = 0; q < n_big; ++q) {
+            const int s0 = sm.big_start[q], s1 = s0 + sm.big_cnt[q];
+            const int lo = max(s0, B), up = min(s1, Bend);
+            const uint32_t bw = sm.big_wh[q], bx0 = sm.big_rect[q] & 0xffffu, by0 = sm.big_rect[q] >> 16;
+            for (int sl = lo + threadIdx.x; sl < up; sl += RS_ISECT_THREADS) {
+                const uint32_t r = (uint32_t)(sl - s0);
+                sm.skey[sl - B] = sm.big_hi[q] | ((by0 + r / bw) * tile_w + bx0 + r % bw);
+                sm.sval[sl - B] = sm.big_elem[q];
+            }
+        }
+        __syncthreads();
+        const int n_out = min(EMIT_CHUNK, total - B);
+        for (int jj = threadIdx.x; jj < n_out; jj += RS_ISECT_THREADS) {
+            const int64_t o = out_base + B + jj;
+            if (o < a.capacity) {
+                tile_keys[o] = sm.skey[jj];
+                vals[o] = sm.sval[jj];
+            }
+        }
+        __syncthreads();
     }
 }
 

@@ -11,10 +11,13 @@ tile-intersect + radix sort -> front-to-back compositing (the commented-out loop
 apply_transform() per body + rasterization()).
 
   value     frames/s over all ranks, everything resident in HBM (poses [240,K,.] pre-generated on the device),
-            K frames enqueued back to back, CUDA events on the launching stream, max over ranks.
+            K frames enqueued back to back through FramePipeline (`--in-flight` frames per GPU, one stream + workspace
+            each, so the latency-bound binning of one frame overlaps the compositing of another), CUDA events on the
+            launching stream, max over ranks.
   e2e       frames/s through the public per-frame API (FrameRenderer.render -> C ABI rs_render_frame) with HOST inputs
             and HOST results: per step the frame's poses + camera are copied from pinned host memory and the rendered
-            image [H,W,3] + alpha [H,W,1] are copied back to pinned host memory; copies are inside the timed region.
+            float32 image [H,W,3] is copied back to pinned host memory (what the reference's loop keeps,
+            main.py:387-400); copies are inside the timed region.  At ~25 MB per frame this leg is PCIe-bound.
   roofline  the dominant HBM-bound kernel of the step (radix-sort scatter pass), timed live with CUDA events.
   stages    per-stage CUDA-event times of one frame through the separate C-ABI entry points, with achieved GB/s against
             the algorithmic bytes of SURVEY.md section 8(d) -- explains `value`.
@@ -338,10 +341,15 @@ def ours_arm(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ------------------------------------------------------------------------------
+    pipe = rs.FramePipeline(args.in_flight, sc["means"], sc["quats"], sc["scales"], sc["opacities"], sc["colors"], WIDTH,
+                            HEIGHT, cluster_ids=sc["cluster_ids"], body_centers=sc["body_centers"],
+                            max_isects=args.max_isects)
     for f in frames[:args.warmup]:
         fr.render(sc["viewmats"], sc["Ks"], q_all[f], t_all[f])
+        pipe.submit(sc["viewmats"], sc["Ks"], q_all[f], t_all[f])
+    pipe.join()
     torch.cuda.synchronize()
-    assert not fr.overflowed(), "max_isects too small for the benchmark scene"
+    assert not fr.overflowed() and not pipe.overflowed(), "max_isects too small for the benchmark scene"
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -352,66 +360,59 @@ def ours_arm(args):
     t_wall0 = time.time()
     e0.record()
     for f in frames[args.warmup:]:
-        fr.render(sc["viewmats"], sc["Ks"], q_all[f], t_all[f])
+        pipe.submit(sc["viewmats"], sc["Ks"], q_all[f], t_all[f])
+    pipe.join()
     e1.record()
     barrier()
     t_wall1 = time.time()
     ms = e0.elapsed_time(e1)
     launches = (lib.rs_launch_count() - n0) if n0 is not None else None
-    assert not fr.overflowed()
-    n_isects_last = fr.n_isects()
+    assert not pipe.overflowed()
+    n_isects_last = pipe.renderers[(pipe.count - 1) % args.in_flight].n_isects()
 
-    # ---- end to end: host inputs -> C ABI -> host results, double-buffered ------------------------------------------
+    # ---- end to end: host inputs -> C ABI -> host results, `in_flight` frames pipelined ---------------------------------
     K = N_BODIES
-    h_pose = [torch.empty(K * 7 + 16 + 9, dtype=torch.float32).pin_memory() for _ in range(2)]
-    d_pose = [torch.empty(K * 7 + 16 + 9, dtype=torch.float32, device=dev) for _ in range(2)]
-    h_img = [torch.empty(HEIGHT, WIDTH, 3, dtype=torch.float32).pin_memory() for _ in range(2)]
-    h_alpha = [torch.empty(HEIGHT, WIDTH, 1, dtype=torch.float32).pin_memory() for _ in range(2)]
-    d_img = [torch.empty(1, HEIGHT, WIDTH, 3, dtype=torch.float32, device=dev) for _ in range(2)]
-    d_alpha = [torch.empty(1, HEIGHT, WIDTH, 1, dtype=torch.float32, device=dev) for _ in range(2)]
-    copy_stream = torch.cuda.Stream(device=dev)
+    depth = args.in_flight
+    h_pose = [torch.empty(K * 7 + 16 + 9, dtype=torch.float32).pin_memory() for _ in range(depth)]
+    d_pose = [torch.empty(K * 7 + 16 + 9, dtype=torch.float32, device=dev) for _ in range(depth)]
+    h_img = [torch.empty(HEIGHT, WIDTH, 3, dtype=torch.float32).pin_memory() for _ in range(depth)]
     vm_np, Ks_np = sc_np["viewmats"].reshape(-1), sc_np["Ks"].reshape(-1)
-    rendered = [torch.cuda.Event() for _ in range(2)]
-    copied = [torch.cuda.Event() for _ in range(2)]
+    slot_done = [None] * depth
     h2d_bytes = (K * 7 + 25) * 4
-    d2h_bytes = HEIGHT * WIDTH * 4 * 4
-    main = torch.cuda.current_stream()
+    d2h_bytes = HEIGHT * WIDTH * 3 * 4  # the rendered image; the reference's loop discards the alphas (main.py:387-400)
 
     def e2e_frame(i, f):
-        b = i & 1
+        k = i % depth
+        if slot_done[k] is not None:
+            slot_done[k].synchronize()  # the host buffers of this slot hold a finished frame: "consume" it, then reuse
         # host side of the step: this frame's poses + camera, packed into one pinned buffer
-        hp = h_pose[b].numpy()
+        hp = h_pose[k].numpy()
         hp[:K * 4] = q_np[f].reshape(-1)
         hp[K * 4:K * 7] = t_np[f].reshape(-1)
         hp[K * 7:K * 7 + 16] = vm_np
         hp[K * 7 + 16:] = Ks_np
-        d_pose[b].copy_(h_pose[b], non_blocking=True)
-        bq = d_pose[b][:K * 4].view(K, 4)
-        bt = d_pose[b][K * 4:K * 7].view(K, 3)
-        vm = d_pose[b][K * 7:K * 7 + 16].view(1, 4, 4)
-        Ks = d_pose[b][K * 7 + 16:].view(1, 3, 3)
-        main.wait_event(copied[b])  # the staging image of two frames ago has left the device
-        img, alpha = fr.render(vm, Ks, bq, bt)
-        d_img[b].copy_(img, non_blocking=True)
-        d_alpha[b].copy_(alpha, non_blocking=True)
-        rendered[b].record(main)
-        copy_stream.wait_event(rendered[b])
-        with torch.cuda.stream(copy_stream):
-            h_img[b].copy_(d_img[b][0], non_blocking=True)
-            h_alpha[b].copy_(d_alpha[b][0], non_blocking=True)
-            copied[b].record(copy_stream)
+        with torch.cuda.stream(pipe.streams[k]):
+            d_pose[k].copy_(h_pose[k], non_blocking=True)
+            bq = d_pose[k][:K * 4].view(K, 4)
+            bt = d_pose[k][K * 4:K * 7].view(K, 3)
+            vm = d_pose[k][K * 7:K * 7 + 16].view(1, 4, 4)
+            Ks = d_pose[k][K * 7 + 16:].view(1, 3, 3)
+            img, alpha = pipe.renderers[k].render(vm, Ks, bq, bt)
+            h_img[k].copy_(img[0], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(pipe.streams[k])
+            slot_done[k] = ev
 
     for i, f in enumerate(frames[:args.warmup]):
         e2e_frame(i, f)
+    torch.cuda.synchronize()
     barrier()
-    copy_stream.synchronize()
     t0 = time.perf_counter()
     for i, f in enumerate(frames[args.warmup:]):
         e2e_frame(i, f)
-    copy_stream.synchronize()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    e2e_checksum = float(h_img[(args.steps - 1) & 1].sum())
+    e2e_checksum = float(h_img[(args.steps - 1) % depth].sum())
 
     t_ms = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -432,13 +433,13 @@ def ours_arm(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_max / args.steps, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "gaussians": N_GAUSS, "bodies": N_BODIES, "width": WIDTH, "height": HEIGHT,
-                   "channels": 3, "n_isects_last_frame": n_isects_last, "sharding": f"frames round-robin over {world} rank(s), no collective",
+                   "channels": 3, "n_isects_last_frame": n_isects_last, "frames_in_flight_per_gpu": args.in_flight, "sharding": f"frames round-robin over {world} rank(s), no collective",
                    "l2": "per-frame working set (Gaussians 60 MB + projected 36 MB + 2x(keys+values) >= 200 MB + images 41 MB) "
                          "exceeds the 126 MB L2 and every frame has new poses; no explicit flush"},
         "e2e": {"value": round(total_frames / (e2e_ms_max * 1e-3), 2), "unit": "frames/s",
                 "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                "api": "FrameRenderer.render -> rs_render_frame (C ABI); pinned host poses+camera in, pinned host image+alpha out, "
-                       "D2H of frame i overlaps the render of frame i+1", "checksum_last_image": e2e_checksum},
+                "api": "FrameRenderer.render -> rs_render_frame (C ABI); pinned host poses+camera in, pinned host float32 image out, "
+                       "one stream per in-flight frame (H2D, render, D2H in stream order)", "checksum_last_image": e2e_checksum},
         "gpu_launches": launches,
         "clocks": clocks,
     }
@@ -472,6 +473,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--max-isects", type=int, default=24_000_000)
+    ap.add_argument("--in-flight", type=int, default=4, help="frames in flight per GPU (streams + workspaces)")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-extras", action="store_true", help="skip stages / roofline / cpu_baseline (profiling runs)")
     args = ap.parse_args()

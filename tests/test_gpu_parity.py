@@ -480,3 +480,37 @@ def test_full_size_properties_1m_1080p(rs):
     assert float(alpha.mean()) > 0.01
     img2, _ = fr.render(sc["viewmats"], sc["Ks"], bq, bt)
     assert torch.equal(img2, img)  # idempotence / determinism
+
+
+def test_frame_pipeline_matches_sequential(rs):
+    """Several frames in flight (one stream + workspace each) give exactly the frames a single renderer gives."""
+    W, H = 320, 192
+    s = synthetic_scene(9, 30_000, K=4)
+    vm, Ks = pinhole_cameras(1, W, H)
+    t = {k: T(v) for k, v in s.items()}
+    common = dict(cluster_ids=t["cluster_ids"], body_centers=t["body_centers"], max_isects=1 << 21)
+    args = (t["means"], t["quats"], t["scales"], t["opacities"], t["colors"], W, H)
+    fr = rs.FrameRenderer(*args, **common)
+    pipe = rs.FramePipeline(3, *args, **common)
+    rng = np.random.default_rng(0)
+    poses = [(T(rng.normal(size=(4, 4)).astype(np.float32)), T((rng.normal(size=(4, 3)) * 0.3).astype(np.float32)))
+             for _ in range(7)]
+    want = []
+    for q, tr in poses:
+        img, alpha = fr.render(T(vm), T(Ks), q, tr)
+        want.append((img.clone(), alpha.clone()))
+    got = []
+    for q, tr in poses:
+        img, alpha, done = pipe.submit(T(vm), T(Ks), q, tr)
+        done.synchronize()  # consume before the slot is reused
+        got.append((img.clone(), alpha.clone()))
+    pipe.join()
+    # and without consuming in between: only the last `depth` frames remain in the slots
+    outs = [pipe.submit(T(vm), T(Ks), q, tr) for q, tr in poses]
+    pipe.join()
+    torch.cuda.synchronize()
+    for (wi, wa), (gi, ga) in zip(want, got):
+        assert torch.equal(wi, gi) and torch.equal(wa, ga)
+    for k in range(len(poses) - 3, len(poses)):
+        assert torch.equal(outs[k][0], want[k][0])
+    assert not pipe.overflowed()
