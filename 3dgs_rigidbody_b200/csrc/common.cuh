@@ -124,6 +124,19 @@ __device__ __forceinline__ void rs_cull_extents(float a, float b, float c, float
     }
 }
 
+// Cull limit of a splat for the exact ellipse-vs-rectangle test of raster_fwd.cu: a pixel can only reach alpha >= 1/255
+// if sigma(pixel) <= ln(255 * opacity) (RasterizeToPixels3DGSFwd.cu:148-149); the limit carries a 1e-3 margin for the
+// float error of both evaluations.  +3e38 = "cannot cull" (degenerate conic), -3e38 = "can never contribute".
+__device__ __forceinline__ float rs_cull_limit(float a, float b, float c, float op) {
+    if (op < RS_ALPHA_THRESHOLD * 0.999f) // alpha <= op < 1/255 whenever sigma >= 0
+        return -3e38f;
+    const float det = a * c - b * b;
+    const float L = logf(op * 255.f);
+    if (a > 0.f && c > 0.f && det > 0.f && a * c <= 256.f * det && L == L)
+        return L + 1e-3f * (1.f + fabsf(L));
+    return 3e38f;
+}
+
 // block-wide sum of one int per thread (blockDim.x == RS_ISECT_THREADS), result valid in thread 0
 __device__ __forceinline__ int rs_block_sum_256(int v, int *smem8) {
 #pragma unroll

@@ -49,9 +49,20 @@ rs_project_fwd_kernel(const rs_project_fwd_args a) {
         const uint64_t idx = block_base + (uint64_t)it * RS_ISECT_THREADS + threadIdx.x;
         if (idx >= total)
             break;
-        const uint32_t img = (uint32_t)(idx / N); // bid * C + cid
-        const uint32_t gid = (uint32_t)(idx - (uint64_t)img * N);
-        const uint32_t bid = img / C;
+        // (image, gaussian) of this element; the common single-image case needs no division at all and totals below
+        // 2^32 avoid the 64-bit divide
+        uint32_t img, gid;
+        if (total <= N) {
+            img = 0;
+            gid = (uint32_t)idx;
+        } else if (total <= 0xffffffffull) {
+            img = (uint32_t)idx / N;
+            gid = (uint32_t)idx - img * N;
+        } else {
+            img = (uint32_t)(idx / N); // bid * C + cid
+            gid = (uint32_t)(idx - (uint64_t)img * N);
+        }
+        const uint32_t bid = (C == 1) ? img : img / C;
         const size_t gsrc = (size_t)bid * N + gid; // row in the per-batch Gaussian arrays
 
         RsCam cam;
@@ -140,11 +151,9 @@ rs_project_fwd_kernel(const rs_project_fwd_args a) {
         if (a.compensations != nullptr)
             a.compensations[idx] = o.comp;
         if (a.records != nullptr && ok) { // compositing record (see raster_fwd.cu); culled rows are never referenced
-            float ex, ey;
-            rs_cull_extents(o.ca, o.cb, o.cc, opac, ex, ey);
             float4 *rec = reinterpret_cast<float4 *>(a.records) + idx * 2;
             rec[0] = make_float4(o.mx, o.my, opac, o.ca);
-            rec[1] = make_float4(o.cb, o.cc, ex, ey);
+            rec[1] = make_float4(o.cb, o.cc, rs_cull_limit(o.ca, o.cb, o.cc, opac), 0.f);
         }
         if (a.tiles_per_gauss != nullptr) {
             int cnt = rs_tile_count(o.rx, o.ry, o.mx, o.my, (uint32_t)a.tile_size, (uint32_t)a.tile_width,

@@ -2,13 +2,13 @@
 // Replaces csrc/RasterizeToPixels3DGSFwd.cu:17-187 (host side csrc/Rasterization.cpp:20-115).
 //
 // One CTA (256 threads) per 16x16 tile, like the reference, but:
-//   * splats are staged as 32-byte RECORDS {x, y, opacity, conic a | conic b, conic c, cull half-extents} that the
+//   * splats are staged as 32-byte RECORDS {x, y, opacity, conic a | conic b, conic c, cull limit, 0} that the
 //     projection kernel (frame path) or a small pack kernel (operator path) writes once per (camera, Gaussian); the
 //     compositing kernel copies them global -> shared with cp.async (LDGSTS, no register staging) through a ring of
 //     RAST_STAGES batches of 256 splats, so the gathers of batch b+2 are in flight while batch b is composited and
 //     there is ONE block barrier per batch (the reference: load, barrier, composite, barrier, nothing in flight);
 //   * each warp owns an 8x4 pixel sub-block and tests 32 staged splats at a time (one per lane) against it with the
-//     record's conservative bounding box of {alpha >= 1/255}; a ballot gives the splats that can touch the sub-block
+//     record's region {alpha >= 1/255} (exact ellipse-vs-rectangle test); a ballot gives the splats that can touch the sub-block
 //     and only those are evaluated.  A skipped (pixel, splat) pair is one the reference would have `continue`d on
 //     (alpha < 1/255), so results are unchanged while most of the evaluations disappear;
 //   * colours are staged in shared memory with the geometry (the reference re-reads them from global per pixel);
@@ -42,11 +42,9 @@ __global__ void __launch_bounds__(256) rs_raster_pack_kernel(const rs_raster_fwd
     const float2 xy = reinterpret_cast<const float2 *>(a.means2d)[g];
     const float ca = a.conics[g * 3 + 0], cb = a.conics[g * 3 + 1], cc = a.conics[g * 3 + 2];
     const float op = a.opacities[a.attr_mod_opacities > 0 ? g % a.attr_mod_opacities : g];
-    float ex, ey;
-    rs_cull_extents(ca, cb, cc, op, ex, ey);
     float4 *rec = reinterpret_cast<float4 *>(a.records) + g * 2;
     rec[0] = make_float4(xy.x, xy.y, op, ca);
-    rec[1] = make_float4(cb, cc, ex, ey);
+    rec[1] = make_float4(cb, cc, rs_cull_limit(ca, cb, cc, op), 0.f);
 }
 
 // ---- mbarrier helpers (shared::cta) --------------------------------------------------------------------------------
@@ -70,6 +68,14 @@ __device__ __forceinline__ void rs_cp_async_mbar_arrive(uint64_t *bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];\n" ::"r"(rs_smem_addr(bar)) : "memory");
 }
 
+#ifdef RS_RASTER_STATS
+__device__ unsigned long long rs_stats[8];
+extern "C" void rs_raster_stats(unsigned long long *out) { // {iterations, with >= 1 passing lane, passing, active, chunks}
+    cudaMemcpyFromSymbol(out, rs_stats, sizeof(unsigned long long) * 8);
+    unsigned long long z[8] = {0};
+    cudaMemcpyToSymbol(rs_stats, z, sizeof(z));
+}
+#endif
 // CP = colour row pitch in shared memory (floats): CDIM rounded up to a multiple of 4 so rows can be read as float4
 #define RAST_BATCH 256                   // splats per ring stage
 #define RAST_CONSUMERS 8                 // compositing warps (one 8x4 pixel sub-block each)
@@ -256,12 +262,36 @@ rs_raster_fwd_kernel(const rs_raster_fwd_args a, const int ch_off, const int ch_
             const float *s_col = base + RAST_BATCH * 8;
 
             for (int chunk = 0; chunk < batch_size; chunk += 32) {
+#ifdef RS_RASTER_STATS
+                if (lane == 0)
+                    atomicAdd(&rs_stats[4], 1ull);
+#endif
                 const int t = chunk + lane;
                 bool hit = false;
                 if (t < batch_size) {
                     const float4 g0 = s_r0[t];
                     const float4 g1 = s_r1[t];
-                    hit = (g0.x + g1.z >= bx0) && (g0.x - g1.z <= bx1) && (g0.y + g1.w >= by0) && (g0.y - g1.w <= by1);
+                    // exact test: minimum of sigma over the sub-block rectangle [bx0,bx1] x [by0,by1] (which spans the
+                    // pixel centres) against the splat's cull limit.  sigma is a convex quadratic centred on the splat,
+                    // so the minimum is 0 if the centre is inside, else it lies on the edge(s) facing the centre: at
+                    // most one vertical and one horizontal edge, each a clamped 1-D minimisation.
+                    const float cx = g0.x, cy = g0.y, qa = g0.w, qb = g1.x, qc = g1.y;
+                    const float dx = cx - fminf(fmaxf(cx, bx0), bx1); // 0 when the centre is within the x range
+                    const float dy = cy - fminf(fmaxf(cy, by0), by1);
+                    // vertical edge (fixed dx): optimum dy* = -b dx / c, clamped to the edge
+                    const float pyv = fminf(fmaxf(cy + __fdividef(qb * dx, qc), by0), by1);
+                    const float d2 = cy - pyv;
+                    const float qv = 0.5f * (qa * dx * dx + qc * d2 * d2) + qb * dx * d2;
+                    // horizontal edge (fixed dy): optimum dx* = -b dy / a
+                    const float pxh = fminf(fmaxf(cx + __fdividef(qb * dy, qa), bx0), bx1);
+                    const float d1 = cx - pxh;
+                    const float qh = 0.5f * (qa * d1 * d1 + qc * dy * dy) + qb * d1 * dy;
+                    float qmin = 0.f;
+                    if (dx != 0.f)
+                        qmin = qv;
+                    if (dy != 0.f)
+                        qmin = (dx != 0.f) ? fminf(qv, qh) : qh;
+                    hit = !(qmin > g1.z); // NaN -> evaluate
                 }
                 // bit-reversed ballot: the next splat in list order is the highest set bit (one FLO per iteration)
                 unsigned m = __brev(__ballot_sync(0xffffffffu, hit));
@@ -269,6 +299,24 @@ rs_raster_fwd_kernel(const rs_raster_fwd_args a, const int ch_off, const int ch_
                     const int lz = __clz(m);
                     m &= ~(0x80000000u >> lz);
                     const int tt = chunk + lz;
+#ifdef RS_RASTER_STATS // instrumentation build only (tools/raster_stats.py): how selective is the cull test?
+                    {
+                        const float4 q0 = s_r0[tt];
+                        const float4 q1 = s_r1[tt];
+                        const float ddx = q0.x - px, ddy = q0.y - py;
+                        const float sg = 0.5f * (q0.w * ddx * ddx + q1.y * ddy * ddy) + q1.x * ddx * ddy;
+                        const float al = fminf(0.999f, q0.z * __expf(-sg));
+                        const bool pass = !done && !(sg < 0.f || al < RS_ALPHA_THRESHOLD);
+                        const unsigned pm = __ballot_sync(0xffffffffu, pass);
+                        const unsigned am = __ballot_sync(0xffffffffu, !done);
+                        if (lane == 0) {
+                            atomicAdd(&rs_stats[0], 1ull);
+                            atomicAdd(&rs_stats[1], pm ? 1ull : 0ull);
+                            atomicAdd(&rs_stats[2], (unsigned long long)__popc(pm));
+                            atomicAdd(&rs_stats[3], (unsigned long long)__popc(am));
+                        }
+                    }
+#endif
                     if (!done) {
                         const float4 g0 = s_r0[tt];
                         const float4 g1 = s_r1[tt];

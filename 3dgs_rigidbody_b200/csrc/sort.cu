@@ -288,6 +288,8 @@ sort_pass_kernel(const KeyT *__restrict__ keys_in, const int32_t *__restrict__ v
                         }
                     }
                     t -= used;
+                    if (used == 0)
+                        __nanosleep(200); // predecessor not published yet: leave the issue slots to other warps / frames
                 }
                 st_volatile_u32(lookback + (size_t)tile * RADIX + d, LB_INCLUSIVE | (uint32_t)(excl + sm.real[d]));
             }

@@ -86,7 +86,7 @@ typedef struct {
     int32_t *block_sums;        /* [rs_isect_num_blocks(B*C*N)] out, optional */
     int32_t tile_size, tile_width, tile_height;
     int32_t _pad;
-    /* optional: compositing records [B*C*N, 8] float = {x, y, opacity, conic a | conic b, conic c, cull half-extent x, y},
+    /* optional: compositing records [B*C*N, 8] float = {x, y, opacity, conic a | conic b, conic c, cull limit, 0},
      * the staging format of rs_raster_fwd (pass them as rs_raster_fwd_args.records with records_ready = 1).  Needs
      * opacities; written for visible rows only. */
     float *records;
