@@ -82,7 +82,7 @@ extern "C" void rs_raster_stats(unsigned long long *out) { // {iterations, with 
 #define RAST_THREADS (32 * (RAST_CONSUMERS + 1)) // + one producer warp
 template <int CDIM> struct RastCfg {
     static constexpr int CP = (CDIM + 3) & ~3;
-    static constexpr int STAGES = (CDIM <= 4) ? 4 : (CDIM <= 16 ? 3 : 2);
+    static constexpr int STAGES = (CDIM <= 8) ? 3 : 2;
     static constexpr int STAGE_FLOATS = RAST_BATCH * (8 + CP);
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_FLOATS * sizeof(float);
 };
@@ -168,11 +168,14 @@ rs_raster_fwd_kernel(const rs_raster_fwd_args a, const int ch_off, const int ch_
         // ---------------------------------------------------------------------------------------------------------------
         const float4 *records = reinterpret_cast<const float4 *>(a.records);
         constexpr int PER_LANE = RAST_BATCH / 32;
-        int32_t gid[PER_LANE];
+        // flatten ids are fetched TWO batches ahead of the copies that need them (gid = batch b, gnx = batch b+1), so the
+        // id round trip is off the producer's critical path
+        int32_t gid[PER_LANE], gnx[PER_LANE];
 #pragma unroll
         for (int k = 0; k < PER_LANE; ++k) {
             const int32_t idx = range_start + k * 32 + lane;
-            gid[k] = (num_batches > 0 && idx < range_end) ? a.flatten_ids[idx] : -1;
+            gid[k] = (idx < range_end) ? a.flatten_ids[idx] : -1;
+            gnx[k] = (idx + RAST_BATCH < range_end) ? a.flatten_ids[idx + RAST_BATCH] : -1;
         }
         for (int b = 0; b < num_batches; ++b) {
             const int st = b % STAGES;
@@ -212,11 +215,11 @@ rs_raster_fwd_kernel(const rs_raster_fwd_args a, const int ch_off, const int ch_
                 }
             }
             rs_cp_async_mbar_arrive(&full_bar[st]);
-            // ids of the next batch: their latency overlaps the copies just issued
 #pragma unroll
             for (int k = 0; k < PER_LANE; ++k) {
-                const int32_t idx = range_start + RAST_BATCH * (b + 1) + k * 32 + lane;
-                gid[k] = (idx < range_end) ? a.flatten_ids[idx] : -1;
+                gid[k] = gnx[k];
+                const int32_t idx = range_start + RAST_BATCH * (b + 2) + k * 32 + lane;
+                gnx[k] = (idx < range_end) ? a.flatten_ids[idx] : -1;
             }
         }
         rs_cp_async_wait<0>(); // nothing may still be landing in shared memory when the CTA retires
