@@ -56,6 +56,7 @@ WORKLOAD = "c2: synthetic domino scene, 1M Gaussians, 20 rigid bodies, 240-frame
 # ----------------------------------------------------------------------------------------------------------------------
 HALF_EXTENTS = np.array([0.05, 0.25, 0.5], np.float32)  # thin along x, standing along z (z up)
 SPACING = 0.35
+GRID_COLS, GRID_ROW_SPACING = 20, 0.9
 
 
 def _quat_about_y(theta):
@@ -79,13 +80,16 @@ def look_at(eye, target, up=(0.0, 0.0, 1.0)):
 
 
 def make_domino_scene_np(n_gauss=N_GAUSS, n_bodies=N_BODIES, width=WIDTH, height=HEIGHT, seed=42, s_max=0.02,
-                         permute=True, channels=3):
+                         permute=True, channels=3, n_cameras=1):
     rng = np.random.default_rng(seed)
     per = n_gauss // n_bodies
     ids = np.minimum(np.arange(n_gauss) // per, n_bodies - 1).astype(np.int32)
     u = rng.random((n_gauss, 3), dtype=np.float32) * 2 - 1
     means = u * HALF_EXTENTS
-    means[:, 0] += SPACING * ids
+    # bodies along a line (c2) or, beyond 40 bodies, on a 20-wide grid (c4: 20 x 25)
+    means[:, 0] += SPACING * (ids % GRID_COLS if n_bodies > 40 else ids)
+    if n_bodies > 40:
+        means[:, 1] += GRID_ROW_SPACING * (ids // GRID_COLS)
     means[:, 2] += HALF_EXTENTS[2]  # bottom face on z = 0
     quats = rng.standard_normal((n_gauss, 4), dtype=np.float32)
     quats /= np.linalg.norm(quats, axis=1, keepdims=True)
@@ -98,10 +102,17 @@ def make_domino_scene_np(n_gauss=N_GAUSS, n_bodies=N_BODIES, width=WIDTH, height
     centers = np.zeros((n_bodies, 3), np.float32)
     for k in range(n_bodies):
         centers[k] = means[ids == k].mean(0)
-    row_mid = 0.5 * SPACING * (n_bodies - 1)
-    viewmats = look_at((-2.0, -3.0, 1.5), (row_mid * 0.6, 0.0, 0.4))[None]
+    row_mid = 0.5 * SPACING * (min(n_bodies, GRID_COLS) - 1)
+    if n_cameras == 1:
+        viewmats = look_at((-2.0, -3.0, 1.5), (row_mid * 0.6, 0.0, 0.4))[None]
+    else:  # ring of cameras around the scene centre (c4)
+        cy = 0.5 * GRID_ROW_SPACING * ((n_bodies - 1) // GRID_COLS) if n_bodies > 40 else 0.0
+        rad = 1.2 * max(row_mid, cy) + 4.0
+        viewmats = np.stack([look_at((row_mid + rad * math.cos(2 * math.pi * c / n_cameras),
+                                      cy + rad * math.sin(2 * math.pi * c / n_cameras), 2.5), (row_mid, cy, 0.4))
+                             for c in range(n_cameras)])
     f = 0.5 * width / math.tan(math.radians(30.0))
-    Ks = np.array([[[f, 0, width / 2], [0, f, height / 2], [0, 0, 1]]], np.float32)
+    Ks = np.tile(np.array([[[f, 0, width / 2], [0, f, height / 2], [0, 0, 1]]], np.float32), (n_cameras, 1, 1))
     return dict(means=means, quats=quats, scales=scales, opacities=opacities, colors=colors, cluster_ids=ids,
                 body_centers=centers, viewmats=viewmats, Ks=Ks)
 
@@ -112,11 +123,13 @@ def domino_poses_np(n_bodies=N_BODIES, frames=None, centers=None):
     apply_transform pivot, main.py:210): t = R (c - e) + e - c."""
     frames = np.arange(N_FRAMES) if frames is None else np.atleast_1d(np.asarray(frames))
     k = np.arange(n_bodies)
-    theta = np.clip((frames[:, None] - 8.0 * k[None, :]) / 24.0, 0.0, 1.0) * math.radians(80.0)
+    theta = np.clip((frames[:, None] - 8.0 * (k % 40)[None, :]) / 24.0, 0.0, 1.0) * math.radians(80.0)
     q = _quat_about_y(theta).astype(np.float32)  # [F,K,4]
+    col = k % GRID_COLS if n_bodies > 40 else k
+    row_y = GRID_ROW_SPACING * (k // GRID_COLS) if n_bodies > 40 else np.zeros(n_bodies)
     if centers is None:
-        centers = np.stack([SPACING * k, np.zeros(n_bodies), np.full(n_bodies, HALF_EXTENTS[2])], -1)
-    e = np.stack([SPACING * k + HALF_EXTENTS[0], np.zeros(n_bodies), np.zeros(n_bodies)], -1)  # pivot edge
+        centers = np.stack([SPACING * col, row_y, np.full(n_bodies, HALF_EXTENTS[2])], -1)
+    e = np.stack([SPACING * col + HALF_EXTENTS[0], row_y, np.zeros(n_bodies)], -1)  # pivot edge
     c, s = np.cos(theta), np.sin(theta)
     d = (centers - e)[None]  # [1,K,3]
     Rd = np.stack([c * d[..., 0] + s * d[..., 2], np.broadcast_to(d[..., 1], c.shape), -s * d[..., 0] + c * d[..., 2]], -1)

@@ -289,3 +289,37 @@ def test_cpu_oracle_pinned_to_reference_cuda(rs, ref, orc):
     ok = o["margin"] > 1e-4
     assert np.abs(o["render_colors"] - rc_t.cpu().numpy())[ok].max() <= 1e-4
     assert np.abs(o["render_alphas"] - ra_t.cpu().numpy())[ok].max() <= 1e-4
+
+
+def test_c4_scale_6m_gaussians_4k_two_cameras(rs, ref):
+    """c4 scale on one GPU (6 M Gaussians, 500 bodies, 2 of the 8 ring cameras at 3840x2160 -> 15 tile bits + 2 image bits):
+    the depth-ordered binning against the reference's 64-bit cub sort, bit-exact, plus image parity on identical lists."""
+    import bench
+
+    W, H, C, N, K = 3840, 2160, 2, 6_000_000, 500
+    sc = bench.make_domino_scene(N, K, device=DEV, width=W, height=H, n_cameras=C)
+    bq, bt = bench.domino_poses(K, frame=150, device=DEV, centers=sc["body_centers"])
+    fr = rs.FrameRenderer(sc["means"], sc["quats"], sc["scales"], sc["opacities"], sc["colors"], W, H,
+                          cluster_ids=sc["cluster_ids"], body_centers=sc["body_centers"], n_cameras=C,
+                          max_isects=120_000_000)
+    img, alpha = fr.render(sc["viewmats"], sc["Ks"], bq, bt)
+    torch.cuda.synchronize()
+    assert not fr.overflowed()
+    m = fr.meta()
+    n = m["n_isects"]
+    assert n > 5_000_000
+    tpg_t, ids_t, flat_t = ref.intersect_tile(m["means2d"], m["radii"], m["depths"], None, None, C, 16, m["tile_width"],
+                                              m["tile_height"], True, False)
+    assert ids_t.numel() == n
+    assert torch.equal(m["tiles_per_gauss"], tpg_t)
+    assert torch.equal(m["isect_ids"], ids_t)
+    assert torch.equal(m["flatten_ids"], flat_t)
+    off_t = ref.intersect_offset(ids_t, C, m["tile_width"], m["tile_height"])
+    assert torch.equal(m["isect_offsets"], off_t)
+    del tpg_t, ids_t
+    rc_t, ra_t, li_t = ref.rasterize_to_pixels_3dgs_fwd(
+        m["means2d"], m["conics"], sc["colors"][None].expand(C, N, 3).contiguous(),
+        sc["opacities"][None].expand(C, N).contiguous(), None, None, W, H, 16, off_t, flat_t)
+    assert torch.equal(li_t, m["last_ids"])
+    assert torch.equal(rc_t, img) and torch.equal(ra_t, alpha)
+    assert float(alpha.mean()) > 0.005
