@@ -165,7 +165,7 @@ static int render_frame_impl(const rs_frame_args *a, rs_stream_t stream, cudaEve
     p.conics = reinterpret_cast<float *>(w + L.conics);
     p.records = reinterpret_cast<float *>(w + L.records);
     p.tiles_per_gauss = reinterpret_cast<int32_t *>(w + L.tiles_per_gauss);
-    p.block_sums = reinterpret_cast<int32_t *>(w + L.block_sums);
+    p.block_sums = nullptr; // the depth-ordered binning computes its own block sums
     if (ev)
         RS_CUDA(cudaEventRecord(ev[0], s));
     if (int e = rs_project_fwd(&p, stream))

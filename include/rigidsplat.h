@@ -81,7 +81,8 @@ typedef struct {
     float *depths;              /* [B,C,N]   out */
     float *conics;              /* [B,C,N,3] out */
     float *compensations;       /* [B,C,N]   out, optional (non-NULL <=> calc_compensations) */
-    /* optional fused tile counting (all three or none): */
+    /* optional fused tile counting: tiles_per_gauss (+ tile geometry); block_sums additionally feeds rs_isect_scan /
+     * rs_isect_emit (the unsorted path) and may be NULL when only rs_isect_sorted consumes the counts: */
     int32_t *tiles_per_gauss;   /* [B*C*N] out, optional */
     int32_t *block_sums;        /* [rs_isect_num_blocks(B*C*N)] out, optional */
     int32_t tile_size, tile_width, tile_height;
