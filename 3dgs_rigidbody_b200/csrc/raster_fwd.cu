@@ -76,6 +76,13 @@ extern "C" void rs_raster_stats(unsigned long long *out) { // {iterations, with 
     cudaMemcpyToSymbol(rs_stats, z, sizeof(z));
 }
 #endif
+// explicit shared-space loads from 32-bit shared addresses (keeps the generic->shared conversion out of the inner loop)
+__device__ __forceinline__ float4 rs_lds128(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
 // CP = colour row pitch in shared memory (floats): CDIM rounded up to a multiple of 4 so rows can be read as float4
 #define RAST_BATCH 256                   // splats per ring stage
 #define RAST_CONSUMERS 8                 // compositing warps (one 8x4 pixel sub-block each)
@@ -233,10 +240,11 @@ rs_raster_fwd_kernel(const rs_raster_fwd_args a, const int ch_off, const int ch_
     const float bx0 = (float)sub_x + 0.5f, bx1 = (float)sub_x + 7.5f;
     const float by0 = (float)sub_y + 0.5f, by1 = (float)sub_y + 3.5f;
 
+    const unsigned smem_base = rs_smem_addr(rast_smem);
     float T = 1.0f;
     uint32_t cur_idx = 0;
-    bool done = !inside;
-    bool warp_done = __all_sync(0xffffffffu, done);
+    int done = inside ? 0 : 1; // int, not bool: the compiler keeps bools byte-packed (PRMT traffic in the loop)
+    bool warp_done = __all_sync(0xffffffffu, done != 0);
     if (warp_done && lane == 0)
         atomicAdd(&done_warps, 1);
     float pix_out[CP];
@@ -259,10 +267,10 @@ rs_raster_fwd_kernel(const rs_raster_fwd_args a, const int ch_off, const int ch_
         if (!warp_done) {
             const int32_t batch_start = range_start + RAST_BATCH * b;
             const int batch_size = min(RAST_BATCH, range_end - batch_start);
-            const float *base = rast_smem + (size_t)st * Cfg::STAGE_FLOATS;
-            const float4 *s_r0 = reinterpret_cast<const float4 *>(base);
-            const float4 *s_r1 = reinterpret_cast<const float4 *>(base + RAST_BATCH * 4);
-            const float *s_col = base + RAST_BATCH * 8;
+            unsigned a_r0 = smem_base + (unsigned)(st * Cfg::STAGE_FLOATS * 4); // shared addresses of this stage
+            asm volatile("mov.u32 %0, %0;\n" : "+r"(a_r0)); // opaque: keep it in a register, do not rematerialise per use
+            const unsigned a_r1 = a_r0 + RAST_BATCH * 16;
+            const unsigned a_col = a_r0 + RAST_BATCH * 32;
 
             for (int chunk = 0; chunk < batch_size; chunk += 32) {
 #ifdef RS_RASTER_STATS
@@ -272,8 +280,8 @@ rs_raster_fwd_kernel(const rs_raster_fwd_args a, const int ch_off, const int ch_
                 const int t = chunk + lane;
                 bool hit = false;
                 if (t < batch_size) {
-                    const float4 g0 = s_r0[t];
-                    const float4 g1 = s_r1[t];
+                    const float4 g0 = rs_lds128(a_r0 + t * 16);
+                    const float4 g1 = rs_lds128(a_r1 + t * 16);
                     // exact test: minimum of sigma over the sub-block rectangle [bx0,bx1] x [by0,by1] (which spans the
                     // pixel centres) against the splat's cull limit.  sigma is a convex quadratic centred on the splat,
                     // so the minimum is 0 if the centre is inside, else it lies on the edge(s) facing the centre: at
@@ -304,8 +312,8 @@ rs_raster_fwd_kernel(const rs_raster_fwd_args a, const int ch_off, const int ch_
                     const int tt = chunk + lz;
 #ifdef RS_RASTER_STATS // instrumentation build only (tools/raster_stats.py): how selective is the cull test?
                     {
-                        const float4 q0 = s_r0[tt];
-                        const float4 q1 = s_r1[tt];
+                        const float4 q0 = rs_lds128(a_r0 + tt * 16);
+                        const float4 q1 = rs_lds128(a_r1 + tt * 16);
                         const float ddx = q0.x - px, ddy = q0.y - py;
                         const float sg = 0.5f * (q0.w * ddx * ddx + q1.y * ddy * ddy) + q1.x * ddx * ddy;
                         const float al = fminf(0.999f, q0.z * __expf(-sg));
@@ -321,8 +329,8 @@ rs_raster_fwd_kernel(const rs_raster_fwd_args a, const int ch_off, const int ch_
                     }
 #endif
                     if (!done) {
-                        const float4 g0 = s_r0[tt];
-                        const float4 g1 = s_r1[tt];
+                        const float4 g0 = rs_lds128(a_r0 + tt * 16);
+                        const float4 g1 = rs_lds128(a_r1 + tt * 16);
                         const float dx = __fsub_rn(g0.x, px);
                         const float dy = __fsub_rn(g0.y, py);
                         const float tc = __fmul_rn(__fmul_rn(g1.y, dy), dy);
@@ -332,13 +340,13 @@ rs_raster_fwd_kernel(const rs_raster_fwd_args a, const int ch_off, const int ch_
                         if (!(sigma < 0.f || alpha < RS_ALPHA_THRESHOLD)) {
                             const float next_T = __fmul_rn(T, __fsub_rn(1.0f, alpha));
                             if (next_T <= 1e-4f) {
-                                done = true;
+                                done = 1;
                             } else {
                                 const float vis = __fmul_rn(alpha, T);
-                                const float4 *crow = reinterpret_cast<const float4 *>(s_col + tt * CP);
+                                const unsigned crow = a_col + tt * (CP * 4);
 #pragma unroll
                                 for (int k = 0; k < CP; k += 4) {
-                                    const float4 c4 = crow[k >> 2];
+                                    const float4 c4 = rs_lds128(crow + k * 4);
                                     pix_out[k + 0] = __fmaf_rn(c4.x, vis, pix_out[k + 0]);
                                     pix_out[k + 1] = __fmaf_rn(c4.y, vis, pix_out[k + 1]);
                                     pix_out[k + 2] = __fmaf_rn(c4.z, vis, pix_out[k + 2]);
@@ -350,7 +358,7 @@ rs_raster_fwd_kernel(const rs_raster_fwd_args a, const int ch_off, const int ch_
                         }
                     }
                 }
-                if (__all_sync(0xffffffffu, done)) {
+                if (__all_sync(0xffffffffu, done != 0)) {
                     warp_done = true;
                     if (lane == 0)
                         atomicAdd(&done_warps, 1);
