@@ -10,6 +10,7 @@
 //            Gaussian that covers thousands of tiles is spread over the whole CTA.
 // All of it is HBM-bound integer work: 20 B read per element + 12 B written per intersection.
 #include "common.cuh"
+#include "sort_ws.cuh"
 
 extern "C" int32_t rs_isect_num_blocks(int64_t n_elems) { return (int32_t)((n_elems + RS_ISECT_BLOCK - 1) / RS_ISECT_BLOCK); }
 
@@ -331,7 +332,8 @@ extern "C" int rs_isect_offsets(const int64_t *isect_ids_sorted, int64_t n_isect
 // =====================================================================================================================
 int rs_sort_pairs_u32_internal(int64_t n_bound, const int32_t *n_dev, int begin_bit, int end_bit, const uint32_t *keys_in,
                                const int32_t *vals_in, uint32_t *kbuf0, int32_t *vbuf0, uint32_t *kbuf1, int32_t *vbuf1,
-                               void *workspace, uint64_t workspace_bytes, int *passes, cudaStream_t s);
+                               void *workspace, uint64_t workspace_bytes, int *passes, cudaStream_t s, bool hist_ready);
+int rs_sort_ws_prepare(void *workspace, cudaStream_t s);
 
 // block sums of the tile counts taken in depth order
 __global__ void __launch_bounds__(RS_ISECT_THREADS)
@@ -371,12 +373,19 @@ struct BinEmitSmem {
     int32_t big_elem[RS_ISECT_BLOCK / 4];
     int32_t n_big;
     int32_t warp_tot[8];
+    unsigned int hist[4 * 256]; // up to 4 passes of 8-bit digits over the (image | tile) bits
 };
 
 __global__ void __launch_bounds__(RS_ISECT_THREADS)
 rs_bin_emit_kernel(const rs_isect_args a, const int32_t *__restrict__ elems, uint32_t tile_n_bits,
-                   uint32_t *__restrict__ tile_keys, int32_t *__restrict__ vals) {
+                   uint32_t *__restrict__ tile_keys, int32_t *__restrict__ vals, uint32_t *__restrict__ sort_ws,
+                   int sort_bits, int sort_nb_stride) {
     __shared__ BinEmitSmem sm;
+    // digit histograms of the keys this CTA emits, for every pass of the tile sort that follows (saves that sort its own
+    // read of all M keys)
+    const int sort_passes = (sort_bits + RADIX_BITS - 1) / RADIX_BITS;
+    for (int i = threadIdx.x; i < sort_passes * RADIX; i += RS_ISECT_THREADS)
+        sm.hist[i] = 0;
     const int64_t base = (int64_t)blockIdx.x * RS_ISECT_BLOCK;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0)
@@ -488,14 +497,48 @@ rs_bin_emit_kernel(const rs_isect_args a, const int32_t *__restrict__ elems, uin
         }
         __syncthreads();
         const int n_out = min(EMIT_CHUNK, total - B);
-        for (int jj = threadIdx.x; jj < n_out; jj += RS_ISECT_THREADS) {
+        for (int j0 = 0; j0 < n_out; j0 += RS_ISECT_THREADS) { // warp-uniform trip count (ballots below)
+            const int jj = j0 + threadIdx.x;
             const int64_t o = out_base + B + jj;
-            if (o < a.capacity) {
-                tile_keys[o] = sm.skey[jj];
+            const bool live = jj < n_out && o < a.capacity;
+            const uint32_t key = live ? sm.skey[jj] : 0u;
+            if (live) {
+                tile_keys[o] = key;
                 vals[o] = sm.sval[jj];
+            }
+            const unsigned act = __ballot_sync(0xffffffffu, live);
+            if (act != 0u) {
+                for (int p = 0; p < sort_passes; ++p) {
+                    const int bits = min(RADIX_BITS, sort_bits - p * RADIX_BITS);
+                    const uint32_t d = (key >> (p * RADIX_BITS)) & ((1u << bits) - 1u);
+                    const uint32_t d0 = __shfl_sync(0xffffffffu, d, __ffs(act) - 1);
+                    const unsigned same = __ballot_sync(0xffffffffu, live && d == d0);
+                    if (same == act) { // a whole warp on one digit (the high tile bits): one add
+                        if (lane == __ffs(act) - 1)
+                            atomicAdd(&sm.hist[p * RADIX + d0], (unsigned)__popc(act));
+                    } else if (live) {
+                        atomicAdd(&sm.hist[p * RADIX + d], 1u);
+                    }
+                }
             }
         }
         __syncthreads();
+    }
+    for (int i = threadIdx.x; i < sort_passes * RADIX; i += RS_ISECT_THREADS) {
+        const unsigned v = sm.hist[i];
+        if (v)
+            atomicAdd(&sort_ws[WS_HIST + i], v);
+    }
+    // clear the look-back words the tile sort will use (the device-side count is known since the scan kernel)
+    {
+        const int64_t n = min((int64_t)*a.n_isects, a.capacity);
+        const int64_t words = (n + SORT_TILE - 1) / SORT_TILE * RADIX;
+        for (int p = 0; p < sort_passes; ++p) {
+            uint32_t *lb = sort_ws + WS_LOOKBACK + (size_t)p * sort_nb_stride * RADIX;
+            for (int64_t i = (int64_t)blockIdx.x * RS_ISECT_THREADS + threadIdx.x; i < words;
+                 i += (int64_t)gridDim.x * RS_ISECT_THREADS)
+                lb[i] = 0u;
+        }
     }
 }
 
@@ -587,7 +630,8 @@ extern "C" int rs_isect_sorted(const rs_isect_sorted_args *b, rs_stream_t stream
         int32_t *el_a = reinterpret_cast<int32_t *>(w + L.elems_a), *el_b = reinterpret_cast<int32_t *>(w + L.elems_b);
         int passes = 0;
         if (int e = rs_sort_pairs_u32_internal(a->n_elems, nullptr, 0, 32, reinterpret_cast<const uint32_t *>(a->depths),
-                                               nullptr, dk_a, el_a, dk_b, el_b, w + L.sort_ws, L.sort_ws_bytes, &passes, s))
+                                               nullptr, dk_a, el_a, dk_b, el_b, w + L.sort_ws, L.sort_ws_bytes, &passes, s,
+                                               false))
             return e;
         elems = ((passes - 1) & 1) ? el_b : el_a;
         // 2a. block sums of the tile counts in depth order
@@ -602,12 +646,18 @@ extern "C" int rs_isect_sorted(const rs_isect_sorted_args *b, rs_stream_t stream
         // 2c. emission in depth order
         rs_isect_args e = *a;
         e.block_sums = block_sums;
-        rs_bin_emit_kernel<<<nb, RS_ISECT_THREADS, 0, s>>>(e, elems, tile_n_bits, tk_buf1, tv_buf1);
+        RS_CHECK(tile_passes <= 4, "rs_isect_sorted: image + tile bits exceed 32");
+        if (int err = rs_sort_ws_prepare(w + L.sort_ws, s)) // the emission kernel accumulates the sort's histograms
+            return err;
+        const int sort_nb_stride = (int)((a->capacity + SORT_TILE - 1) / SORT_TILE);
+        rs_bin_emit_kernel<<<nb, RS_ISECT_THREADS, 0, s>>>(e, elems, tile_n_bits, tk_buf1, tv_buf1,
+                                                           reinterpret_cast<uint32_t *>(w + L.sort_ws), tile_bits,
+                                                           sort_nb_stride);
         RS_LAUNCH_CHECK("rs_bin_emit_kernel");
         // 3. stable sort on the (image | tile) bits only
         int passes = 0;
         if (int err = rs_sort_pairs_u32_internal(a->capacity, a->n_isects, 0, tile_bits, tk_buf1, tv_buf1, tk_buf0, tv_buf0,
-                                                 tk_buf1, tv_buf1, w + L.sort_ws, L.sort_ws_bytes, &passes, s))
+                                                 tk_buf1, tv_buf1, w + L.sort_ws, L.sort_ws_bytes, &passes, s, true))
             return err;
     }
     // 4. offsets (+ 64-bit ids on request)

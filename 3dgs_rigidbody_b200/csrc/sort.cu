@@ -18,13 +18,7 @@
 // the SM count, never by the capacity.
 #include "common.cuh"
 
-#define SORT_THREADS 256
-#define SORT_ITEMS 16
-#define SORT_TILE (SORT_THREADS * SORT_ITEMS)
-#define SORT_WARPS (SORT_THREADS / 32)
-#define RADIX_BITS 8
-#define RADIX (1 << RADIX_BITS)
-#define SORT_MAX_PASSES 8
+#include "sort_ws.cuh"
 
 static_assert(RADIX == SORT_THREADS, "one thread per digit in the block-level scans");
 
@@ -32,12 +26,6 @@ static_assert(RADIX == SORT_THREADS, "one thread per digit in the block-level sc
 #define LB_INCLUSIVE 0x80000000u
 #define LB_VALUE 0x3fffffffu
 #define LB_WINDOW 8
-
-// workspace layout (uint32 words): [0, 8*256) digit histograms per pass | [2048, 2048+8) tile tickets per pass |
-// [2304, ...) look-back words: pass-major, [pass][tile][256]
-#define WS_HIST 0
-#define WS_TICKET (SORT_MAX_PASSES * RADIX)
-#define WS_LOOKBACK (WS_TICKET + 256)
 
 __device__ __forceinline__ int64_t sort_count(int64_t n_bound, const int32_t *n_dev) {
     return (n_dev != nullptr) ? min((int64_t)*n_dev, n_bound) : n_bound;
@@ -332,7 +320,8 @@ extern "C" uint64_t rs_radix_sort_workspace_bytes(int64_t n) {
 template <typename KeyT>
 static int radix_sort_impl(int64_t n_bound, const int32_t *n_dev, int begin_bit, int end_bit, const KeyT *keys_in,
                            const int32_t *vals_in, KeyT *kbuf0, int32_t *vbuf0, KeyT *kbuf1, int32_t *vbuf1,
-                           void *workspace, uint64_t workspace_bytes, int *passes_out, cudaStream_t s) {
+                           void *workspace, uint64_t workspace_bytes, int *passes_out, cudaStream_t s,
+                           bool hist_ready = false) {
     if (passes_out)
         *passes_out = 0;
     if (n_bound <= 0 || end_bit <= begin_bit)
@@ -355,11 +344,13 @@ static int radix_sort_impl(int64_t n_bound, const int32_t *n_dev, int begin_bit,
         attr_set[which] = true;
     }
     const int sms = rs_num_sms();
-    RS_CUDA(cudaMemsetAsync(ws, 0, (size_t)WS_LOOKBACK * sizeof(uint32_t), s));
-    const int hist_grid = (int)min((int64_t)sms * 2, (n_bound + SORT_THREADS * 4 - 1) / (SORT_THREADS * 4));
-    sort_hist_kernel<KeyT><<<hist_grid, SORT_THREADS, 0, s>>>(keys_in, n_bound, n_dev, begin_bit, end_bit, passes, nb,
-                                                              ws);
-    RS_LAUNCH_CHECK("sort_hist_kernel");
+    if (!hist_ready) { // else: the producer of the keys already filled ws (rs_sort_ws_prepare + its own histogramming)
+        RS_CUDA(cudaMemsetAsync(ws, 0, (size_t)WS_LOOKBACK * sizeof(uint32_t), s));
+        const int hist_grid = (int)min((int64_t)sms * 2, (n_bound + SORT_THREADS * 4 - 1) / (SORT_THREADS * 4));
+        sort_hist_kernel<KeyT><<<hist_grid, SORT_THREADS, 0, s>>>(keys_in, n_bound, n_dev, begin_bit, end_bit, passes, nb,
+                                                                  ws);
+        RS_LAUNCH_CHECK("sort_hist_kernel");
+    }
     const int pass_grid = min(nb, sms * (sizeof(KeyT) == 4 ? 3 : 2));
     const KeyT *kin = keys_in;
     const int32_t *vin = vals_in;
@@ -401,7 +392,14 @@ extern "C" int rs_radix_sort_pairs(const rs_sort_args *a, rs_stream_t stream) {
 // internal entry for the binning path (isect.cu): u32 keys, read-only input, optional implicit index values
 int rs_sort_pairs_u32_internal(int64_t n_bound, const int32_t *n_dev, int begin_bit, int end_bit, const uint32_t *keys_in,
                                const int32_t *vals_in, uint32_t *kbuf0, int32_t *vbuf0, uint32_t *kbuf1, int32_t *vbuf1,
-                               void *workspace, uint64_t workspace_bytes, int *passes, cudaStream_t s) {
+                               void *workspace, uint64_t workspace_bytes, int *passes, cudaStream_t s, bool hist_ready) {
     return radix_sort_impl<uint32_t>(n_bound, n_dev, begin_bit, end_bit, keys_in, vals_in, kbuf0, vbuf0, kbuf1, vbuf1,
-                                     workspace, workspace_bytes, passes, s);
+                                     workspace, workspace_bytes, passes, s, hist_ready);
+}
+
+// zero the histogram / ticket header of a sort workspace: to be enqueued before a kernel that accumulates the digit
+// histograms itself (hist_ready = true above); that kernel must also clear the look-back words it will need.
+int rs_sort_ws_prepare(void *workspace, cudaStream_t s) {
+    RS_CUDA(cudaMemsetAsync(workspace, 0, (size_t)WS_LOOKBACK * sizeof(uint32_t), s));
+    return 0;
 }
