@@ -404,3 +404,42 @@ def rasterize_to_pixels_3dgs_bwd(
         a.v_colors, a.v_opacities = _ptr(v_colors), _ptr(v_opacities)
         _lib.check(lib.rs_raster_bwd(ctypes.byref(a), _stream()))
     return v_means2d_abs, v_means2d, v_conics, v_colors, v_opacities
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# spherical harmonics (Ops.h:154-168; csrc/SphericalHarmonics.cpp)
+# ---------------------------------------------------------------------------------------------------------------------
+def _fill_sh(a, degree: int, dirs: Tensor, coeffs: Tensor, masks: Optional[Tensor]) -> None:
+    _check(dirs, "dirs", torch.float32)
+    _check(coeffs, "coeffs", torch.float32)
+    if masks is not None:
+        _check(masks, "masks", torch.bool)
+    a.n = dirs.numel() // 3
+    a.degree, a.K = int(degree), coeffs.shape[-2]
+    a.dirs, a.coeffs, a.masks = _ptr(dirs), _ptr(coeffs), _ptr(masks)
+
+
+def spherical_harmonics_fwd(degrees_to_use: int, dirs: Tensor, coeffs: Tensor, masks: Optional[Tensor]) -> Tensor:
+    lib = _lib.load()
+    with torch.cuda.device(dirs.device):
+        a = _lib.rs_sh_args()
+        _fill_sh(a, degrees_to_use, dirs, coeffs, masks)
+        colors = torch.empty_like(dirs)
+        a.colors = _ptr(colors)
+        _lib.check(lib.rs_sh_fwd(ctypes.byref(a), _stream()))
+    return colors
+
+
+def spherical_harmonics_bwd(K: int, degrees_to_use: int, dirs: Tensor, coeffs: Tensor, masks: Optional[Tensor],
+                            v_colors: Tensor, compute_v_dirs: bool) -> Tuple[Tensor, Optional[Tensor]]:
+    lib = _lib.load()
+    _check(v_colors, "v_colors", torch.float32)
+    assert coeffs.shape[-2] == K, (coeffs.shape, K)
+    with torch.cuda.device(dirs.device):
+        a = _lib.rs_sh_args()
+        _fill_sh(a, degrees_to_use, dirs, coeffs, masks)
+        v_coeffs = torch.empty_like(coeffs)
+        v_dirs = torch.empty_like(dirs) if compute_v_dirs else None
+        a.v_colors, a.v_coeffs, a.v_dirs = _ptr(v_colors), _ptr(v_coeffs), _ptr(v_dirs)
+        _lib.check(lib.rs_sh_bwd(ctypes.byref(a), _stream()))
+    return v_coeffs, v_dirs

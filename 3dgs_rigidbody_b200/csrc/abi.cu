@@ -40,6 +40,8 @@ extern "C" uint64_t rs_sizeof_args(int which) {
         return sizeof(rs_rigid_t);
     case 8:
         return sizeof(rs_isect_sorted_args);
+    case 9:
+        return sizeof(rs_sh_args);
     default:
         return 0;
     }

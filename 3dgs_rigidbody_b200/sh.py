@@ -1,49 +1,35 @@
-"""Spherical-harmonics colour evaluation (adjacent to the graded path: SURVEY.md section 8f-1).
+"""Spherical-harmonics colour evaluation (the first "next" row after the graded path).
 
-Same interface as the reference's `spherical_harmonics` (gsplat/cuda/_wrapper.py:151-181; kernels
-csrc/SphericalHarmonicsCUDA.cu:20-116): real SH up to degree 4 of the NORMALISED direction, coefficients [..., K, 3].
-Round 1 evaluates it with differentiable torch ops on the device (it is not one of the three north-star subsystems);
-a fused CUDA version belongs to the "next" rows.  Masked-out entries return 0 (the reference leaves them
-uninitialised, SphericalHarmonics.cpp:29).
+Same interface as the reference's `spherical_harmonics` (gsplat/cuda/_wrapper.py:151-181, autograd node :1799-1831):
+real SH up to degree 4 of the NORMALISED direction, coefficients [..., K, 3].  Forward and backward are CUDA kernels
+behind the C ABI (`rs_sh_fwd` / `rs_sh_bwd`, csrc/sh.cu) reached through `_C.spherical_harmonics_fwd/bwd`, like every
+other operator; CPU tensors (host-logic tests only) are evaluated by the torch restatement in torch_ref.py.
+Masked-out entries return 0 (the reference leaves them uninitialised, SphericalHarmonics.cpp:29).
 """
 from typing import Optional
 
 import torch
-import torch.nn.functional as F
 from torch import Tensor
 
-_C0 = 0.28209479177387814
-_C1 = 0.4886025119029199
-_C2 = (1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792, 0.5462742152960396)
-_C3 = (-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154, -0.4570457994644658,
-       1.445305721320277, -0.5900435899266435)
-_C4 = (2.5033429417967046, -1.7701307697799304, 0.9461746957575601, -0.6690465435572892, 0.10578554691520431,
-       -0.6690465435572892, 0.47308734787878004, -1.7701307697799304, 0.6258357354491761)
+from . import _C
 
 
-def sh_bases(degree: int, dirs: Tensor) -> Tensor:
-    """Real SH basis values [..., (degree+1)^2] at unit directions `dirs` [..., 3]."""
-    x, y, z = dirs.unbind(-1)
-    out = [torch.full_like(x, _C0)]
-    if degree >= 1:
-        out += [-_C1 * y, _C1 * z, -_C1 * x]
-    if degree >= 2:
-        xx, yy, zz, xy, yz, xz = x * x, y * y, z * z, x * y, y * z, x * z
-        out += [_C2[0] * xy, _C2[1] * yz, _C2[2] * (2.0 * zz - xx - yy), _C2[3] * xz, _C2[4] * (xx - yy)]
-    if degree >= 3:
-        out += [
-            _C3[0] * y * (3 * xx - yy), _C3[1] * xy * z, _C3[2] * y * (4 * zz - xx - yy),
-            _C3[3] * z * (2 * zz - 3 * xx - 3 * yy), _C3[4] * x * (4 * zz - xx - yy), _C3[5] * z * (xx - yy),
-            _C3[6] * x * (xx - 3 * yy),
-        ]
-    if degree >= 4:
-        out += [
-            _C4[0] * xy * (xx - yy), _C4[1] * yz * (3 * xx - yy), _C4[2] * xy * (7 * zz - 1),
-            _C4[3] * yz * (7 * zz - 3), _C4[4] * (zz * (35 * zz - 30) + 3), _C4[5] * xz * (7 * zz - 3),
-            _C4[6] * (xx - yy) * (7 * zz - 1), _C4[7] * xz * (xx - 3 * yy),
-            _C4[8] * (xx * (xx - 3 * yy) - yy * (3 * xx - yy)),
-        ]
-    return torch.stack(out, dim=-1)
+class _SphericalHarmonics(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sh_degree: int, dirs: Tensor, coeffs: Tensor, masks: Optional[Tensor]) -> Tensor:
+        colors = _C.spherical_harmonics_fwd(sh_degree, dirs, coeffs, masks)
+        ctx.save_for_backward(dirs, coeffs, masks)
+        ctx.sh_degree = sh_degree
+        ctx.num_bases = coeffs.shape[-2]
+        return colors
+
+    @staticmethod
+    def backward(ctx, v_colors: Tensor):
+        dirs, coeffs, masks = ctx.saved_tensors
+        compute_v_dirs = ctx.needs_input_grad[1]
+        v_coeffs, v_dirs = _C.spherical_harmonics_bwd(ctx.num_bases, ctx.sh_degree, dirs, coeffs, masks,
+                                                      v_colors.contiguous(), compute_v_dirs)
+        return None, (v_dirs if compute_v_dirs else None), v_coeffs, None
 
 
 def spherical_harmonics(degrees_to_use: int, dirs: Tensor, coeffs: Tensor, masks: Optional[Tensor] = None) -> Tensor:
@@ -52,10 +38,11 @@ def spherical_harmonics(degrees_to_use: int, dirs: Tensor, coeffs: Tensor, masks
     batch_dims = dirs.shape[:-1]
     assert dirs.shape == batch_dims + (3,), dirs.shape
     assert coeffs.dim() == len(batch_dims) + 2 and coeffs.shape[:-2] == batch_dims and coeffs.shape[-1] == 3, coeffs.shape
-    nb = (degrees_to_use + 1) ** 2
-    bases = sh_bases(degrees_to_use, F.normalize(dirs, p=2, dim=-1))  # [..., nb]
-    colors = (bases[..., None] * coeffs[..., :nb, :]).sum(dim=-2)
     if masks is not None:
         assert masks.shape == batch_dims, masks.shape
-        colors = torch.where(masks[..., None], colors, torch.zeros_like(colors))
-    return colors
+        masks = masks.contiguous()
+    if not dirs.is_cuda:  # host-logic tests on a CPU box; the product path is CUDA
+        from .torch_ref import spherical_harmonics_torch
+
+        return spherical_harmonics_torch(degrees_to_use, dirs, coeffs, masks)
+    return _SphericalHarmonics.apply(degrees_to_use, dirs.contiguous(), coeffs.contiguous(), masks)

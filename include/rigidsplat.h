@@ -34,7 +34,7 @@ typedef void *rs_stream_t; /* cudaStream_t */
 int rs_abi_version(void);
 const char *rs_last_error(void);
 /* sizeof() of every args struct, for binding self-checks: which = 0 project_fwd, 1 project_bwd, 2 isect,
- * 3 sort, 4 raster_fwd, 5 raster_bwd, 6 frame, 7 rigid, 8 isect_sorted.  Returns 0 for an unknown id. */
+ * 3 sort, 4 raster_fwd, 5 raster_bwd, 6 frame, 7 rigid, 8 isect_sorted, 9 sh.  Returns 0 for an unknown id. */
 uint64_t rs_sizeof_args(int which);
 /* number of kernels this library has launched in this process (all threads); bench.py reports its delta over the
  * timed region as `gpu_launches`. */
@@ -243,6 +243,27 @@ typedef struct {
     float *v_opacities;          /* [I*N] zero-initialised */
 } rs_raster_bwd_args;
 int rs_raster_bwd(const rs_raster_bwd_args *a, rs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Spherical harmonics.  rs_sh_fwd replaces `spherical_harmonics_fwd` (Ops.h:154-160, csrc/SphericalHarmonicsCUDA.cu:20-116,
+ * :374-400), rs_sh_bwd `spherical_harmonics_bwd` (Ops.h:161-168, :118-372, :403-540): real SH up to degree 4 of the
+ * normalised direction, coefficients [n, K, 3].  Rows with masks[i] == 0 produce zeros (the reference leaves them
+ * uninitialised).  v_coeffs is fully written by rs_sh_bwd (rows beyond the used degree are zero).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int64_t n;
+    int32_t degree;              /* degrees_to_use, 0..4 */
+    int32_t K;                   /* coefficient rows per element, >= (degree+1)^2 */
+    const float *dirs;           /* [n,3], need not be unit */
+    const float *coeffs;         /* [n,K,3] */
+    const uint8_t *masks;        /* [n] bool, optional */
+    float *colors;               /* [n,3] out (forward) */
+    const float *v_colors;       /* [n,3] (backward) */
+    float *v_coeffs;             /* [n,K,3] out (backward) */
+    float *v_dirs;               /* [n,3] out (backward), optional */
+} rs_sh_args;
+int rs_sh_fwd(const rs_sh_args *a, rs_stream_t stream);
+int rs_sh_bwd(const rs_sh_args *a, rs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * rs_render_frame: the whole per-frame hot path in one call with NO host synchronisation -- what the commented-out

@@ -323,3 +323,40 @@ def test_c4_scale_6m_gaussians_4k_two_cameras(rs, ref):
     assert torch.equal(li_t, m["last_ids"])
     assert torch.equal(rc_t, img) and torch.equal(ra_t, alpha)
     assert float(alpha.mean()) > 0.005
+
+
+@pytest.mark.parametrize("deg,K", [(0, 1), (1, 4), (2, 16), (3, 16), (4, 25)])
+def test_spherical_harmonics_fwd_bwd_vs_reference_cuda(rs, ref, deg, K):
+    """rs_sh_fwd / rs_sh_bwd against the reference's spherical_harmonics_fwd / _bwd and against float64 torch autograd."""
+    import importlib
+
+    tr = importlib.import_module("3dgs_rigidbody_b200.torch_ref")
+    n = 20_000
+    g = torch.Generator(device=DEV).manual_seed(deg)
+    dirs = torch.randn(n, 3, device=DEV, generator=g) * 3.0
+    coeffs = torch.randn(n, K, 3, device=DEV, generator=g)
+    masks = torch.rand(n, device=DEV, generator=g) > 0.2
+    v_colors = torch.randn(n, 3, device=DEV, generator=g)
+    got = rs._C.spherical_harmonics_fwd(deg, dirs, coeffs, masks)
+    want = ref.spherical_harmonics_fwd(deg, dirs, coeffs, masks)
+    assert float((got - want)[masks].abs().max()) <= 2e-5
+    assert not got[~masks].any()
+    vco, vd = rs._C.spherical_harmonics_bwd(K, deg, dirs, coeffs, masks, v_colors, True)
+    vco_t, vd_t = ref.spherical_harmonics_bwd(K, deg, dirs, coeffs, masks, v_colors, True)
+    assert float((vco - vco_t)[masks].abs().max()) <= 2e-5 * max(1.0, float(vco_t[masks].abs().max()))
+    assert float((vd - vd_t)[masks].abs().max()) <= 1e-4 * max(1.0, float(vd_t[masks].abs().max()))
+    assert not vco[~masks].any() and not vd[~masks].any()
+    # float64 autograd of the torch restatement
+    d64 = dirs.double().requires_grad_(True)
+    c64 = coeffs.double().requires_grad_(True)
+    out = tr.spherical_harmonics_torch(deg, d64, c64, masks)
+    assert float((out.detach() - got.double()).abs().max()) <= 2e-5
+    out.backward(v_colors.double())
+    assert float((c64.grad - vco.double()).abs().max()) <= 2e-5 * max(1.0, float(c64.grad.abs().max()))
+    d_grad = d64.grad if d64.grad is not None else torch.zeros_like(d64)  # degree 0 does not depend on the direction
+    assert float((d_grad - vd.double()).abs().max()) <= 1e-4 * max(1.0, float(d_grad.abs().max()))
+    # the public autograd wrapper
+    d32 = dirs.clone().requires_grad_(True)
+    c32 = coeffs.clone().requires_grad_(True)
+    rs.spherical_harmonics(deg, d32, c32, masks=masks).backward(v_colors)
+    assert torch.equal(c32.grad, vco) and torch.equal(d32.grad, vd)
