@@ -5,7 +5,8 @@ pose for every rigid body, then one render.  The reference does `apply_transform
 tensors, main.py:200) followed by `rasterization()` with its `.item()` sync (csrc/Intersect.cpp:80); here one C-ABI call
 (`rs_render_frame`, include/rigidsplat.h) enqueues the whole pipeline on the current stream into a pre-sized workspace.
 
-Colours are post-activation per-Gaussian values [N, D] (sh_degree=None in the reference's terms).
+Colours are post-activation per-Gaussian values [N, D] (sh_degree=None in the reference's terms), or, with `sh_degree`,
+SH coefficients [N, K, 3] evaluated inside the projection kernel for the moved means (what main.py:328-339 renders with).
 """
 from __future__ import annotations
 
@@ -39,16 +40,20 @@ class FrameRenderer:
         eps2d: float = 0.3,
         backgrounds: Optional[Tensor] = None,  # [C,D]
         camera_model: int = PINHOLE,
+        sh_degree: Optional[int] = None,  # with it, `colors` holds SH coefficients [N,K,3] (main.py renders with degree 3)
     ):
         self.lib = _lib.load()
         dev = means.device
         N = means.shape[0]
         D = colors.shape[-1]
+        self.sh_degree = sh_degree
+        if sh_degree is not None:
+            assert colors.dim() == 3 and D == 3 and (sh_degree + 1) ** 2 <= colors.shape[1], colors.shape
         _check(means, "means", torch.float32, (N, 3))
         _check(quats, "quats", torch.float32, (N, 4), dev)
         _check(scales, "scales", torch.float32, (N, 3), dev)
         _check(opacities, "opacities", torch.float32, (N,), dev)
-        _check(colors, "colors", torch.float32, (N, D), dev)
+        _check(colors, "colors", torch.float32, (N, D) if sh_degree is None else (N, colors.shape[1], 3), dev)
         if cluster_ids is not None:
             _check(cluster_ids, "cluster_ids", torch.int32, (N,), dev)
         if backgrounds is not None:
@@ -94,7 +99,11 @@ class FrameRenderer:
         if self.cluster_ids is not None and body_quats is not None:
             RigidPoses(self.cluster_ids, body_quats, body_trans, self.body_centers).fill(p.rigid)
         p.tile_size, p.tile_width, p.tile_height = self.tile_size, self.tile_width, self.tile_height
-        a.colors = self.colors.data_ptr()
+        if self.sh_degree is None:
+            a.colors = self.colors.data_ptr()
+        else:  # colours are evaluated inside the projection kernel from the SH coefficients
+            a.colors = None
+            p.sh_coeffs, p.sh_degree, p.sh_K = self.colors.data_ptr(), int(self.sh_degree), self.colors.shape[1]
         a.channels = self.D
         a.colors_per_camera = 0
         a.backgrounds = self.backgrounds.data_ptr() if self.backgrounds is not None else None

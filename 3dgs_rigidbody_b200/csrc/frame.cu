@@ -12,7 +12,7 @@ int rs_isect_ids_from_offsets(const int32_t *offsets, const int32_t *flatten_ids
 
 namespace {
 struct FrameLayout {
-    size_t radii, means2d, depths, conics, records, tiles_per_gauss, block_sums, isect_ids, flatten_ids, bin_ws, bin_ws_bytes,
+    size_t radii, means2d, depths, conics, records, sh_colors, tiles_per_gauss, block_sums, isect_ids, flatten_ids, bin_ws, bin_ws_bytes,
         tile_offsets, last_ids, total;
 };
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -32,6 +32,7 @@ FrameLayout make_layout(int32_t C, int32_t N, int32_t W, int32_t H, int32_t tile
     L.depths = take(E * 4);
     L.conics = take(E * 3 * 4);
     L.records = take(E * 8 * 4);
+    L.sh_colors = take(E * 3 * 4); // only used when colours come from SH coefficients
     L.tiles_per_gauss = take(E * 4);
     L.block_sums = take(((size_t)rs_isect_num_blocks((int64_t)E) + 1) * 4);
     L.isect_ids = take((size_t)max_isects * 8); // only written by rs_frame_export_isect_ids
@@ -146,8 +147,9 @@ static int render_frame_impl(const rs_frame_args *a, rs_stream_t stream, cudaEve
     RS_CHECK(p.tile_size == RS_TILE, "rs_render_frame: tile_size must be 16");
     RS_CHECK(a->channels >= 1 && a->channels <= RS_MAX_CHANNELS, "rs_render_frame: Unsupported number of color channels: %d",
              a->channels);
-    RS_CHECK(a->colors && a->render_colors && a->render_alphas && a->status && a->workspace,
+    RS_CHECK((a->colors || p.sh_coeffs) && a->render_colors && a->render_alphas && a->status && a->workspace,
              "rs_render_frame: null pointer");
+    RS_CHECK(p.sh_coeffs == nullptr || a->channels == 3, "rs_render_frame: SH colours have 3 channels");
     RS_CHECK(p.opacities != nullptr, "rs_render_frame: opacities required");
     RS_CHECK(p.compensations == nullptr, "rs_render_frame: antialiased mode is not available on the fused path");
     RS_CHECK(a->max_isects > 0 && a->max_isects < ((int64_t)1 << 31), "rs_render_frame: bad max_isects");
@@ -164,6 +166,8 @@ static int render_frame_impl(const rs_frame_args *a, rs_stream_t stream, cudaEve
     p.depths = reinterpret_cast<float *>(w + L.depths);
     p.conics = reinterpret_cast<float *>(w + L.conics);
     p.records = reinterpret_cast<float *>(w + L.records);
+    if (p.sh_coeffs != nullptr)
+        p.sh_colors = reinterpret_cast<float *>(w + L.sh_colors);
     p.tiles_per_gauss = reinterpret_cast<int32_t *>(w + L.tiles_per_gauss);
     p.block_sums = nullptr; // the depth-ordered binning computes its own block sums
     if (ev)
@@ -200,9 +204,9 @@ static int render_frame_impl(const rs_frame_args *a, rs_stream_t stream, cudaEve
     r.n_isects_dev = a->status;
     r.means2d = p.means2d;
     r.conics = p.conics;
-    r.colors = a->colors;
+    r.colors = p.sh_coeffs != nullptr ? p.sh_colors : a->colors;
     r.opacities = p.opacities;
-    r.attr_mod_colors = a->colors_per_camera ? 0 : p.N;
+    r.attr_mod_colors = (a->colors_per_camera || p.sh_coeffs != nullptr) ? 0 : p.N;
     r.attr_mod_opacities = p.N;
     r.backgrounds = a->backgrounds;
     r.masks = nullptr;

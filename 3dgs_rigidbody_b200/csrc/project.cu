@@ -6,6 +6,23 @@
 // and every thread has 4 independent load chains in flight.  Algorithmic bytes per element: 48 read (mean 12,
 // quat 16, scale 12, opacity 4, cluster id 4) + 32 written (radii 8, mean2d 8, depth 4, conic 12) + 4 (tile count).
 #include "project_math.cuh"
+#include "sh_math.cuh"
+
+// colour of one visible Gaussian from its SH coefficients, view direction = moved mean - camera origin (-R^T t)
+__device__ __forceinline__ void rs_project_sh_color(const rs_project_fwd_args &a, const RsCam &cam, const float mean[3],
+                                                    size_t gsrc, size_t idx) {
+    const float ox = -(cam.R[0] * cam.t[0] + cam.R[3] * cam.t[1] + cam.R[6] * cam.t[2]);
+    const float oy = -(cam.R[1] * cam.t[0] + cam.R[4] * cam.t[1] + cam.R[7] * cam.t[2]);
+    const float oz = -(cam.R[2] * cam.t[0] + cam.R[5] * cam.t[1] + cam.R[8] * cam.t[2]);
+    const float dx = mean[0] - ox, dy = mean[1] - oy, dz = mean[2] - oz;
+    const float inorm = rsqrtf(dx * dx + dy * dy + dz * dz);
+    float B[25], c[3];
+    rs_sh_basis(a.sh_degree, dx * inorm, dy * inorm, dz * inorm, B);
+    rs_sh_dot(B, (a.sh_degree + 1) * (a.sh_degree + 1), a.sh_coeffs + gsrc * (size_t)a.sh_K * 3, c);
+    a.sh_colors[idx * 3 + 0] = fmaxf(c[0] + 0.5f, 0.f);
+    a.sh_colors[idx * 3 + 1] = fmaxf(c[1] + 0.5f, 0.f);
+    a.sh_colors[idx * 3 + 2] = fmaxf(c[2] + 0.5f, 0.f);
+}
 
 struct ProjSmem {
     float cam[2][16];
@@ -155,6 +172,8 @@ rs_project_fwd_kernel(const rs_project_fwd_args a) {
             rec[0] = make_float4(o.mx, o.my, opac, o.ca);
             rec[1] = make_float4(o.cb, o.cc, rs_cull_limit(o.ca, o.cb, o.cc, opac), 0.f);
         }
+        if (a.sh_coeffs != nullptr && ok)
+            rs_project_sh_color(a, cam, mean, gsrc, (size_t)idx);
         if (a.tiles_per_gauss != nullptr) {
             int cnt = rs_tile_count(o.rx, o.ry, o.mx, o.my, (uint32_t)a.tile_size, (uint32_t)a.tile_width,
                                     (uint32_t)a.tile_height);
@@ -320,6 +339,8 @@ rs_project_fwd_staged_kernel(const rs_project_fwd_args a) {
             rec[0] = make_float4(o.mx, o.my, opac, o.ca);
             rec[1] = make_float4(o.cb, o.cc, rs_cull_limit(o.ca, o.cb, o.cc, opac), 0.f);
         }
+        if (a.sh_coeffs != nullptr && ok)
+            rs_project_sh_color(a, cam, mean, src0 + t, idx);
         if (a.tiles_per_gauss != nullptr) {
             my_tiles = rs_tile_count(o.rx, o.ry, o.mx, o.my, (uint32_t)a.tile_size, (uint32_t)a.tile_width,
                                      (uint32_t)a.tile_height);
@@ -348,6 +369,10 @@ extern "C" int rs_project_fwd(const rs_project_fwd_args *a, rs_stream_t stream) 
     if (a->tiles_per_gauss != nullptr)
         RS_CHECK(a->tile_size > 0 && a->tile_width > 0 && a->tile_height > 0,
                  "rs_project_fwd: tile geometry required for fused tile counting");
+    if (a->sh_coeffs != nullptr)
+        RS_CHECK(a->sh_colors != nullptr && a->sh_degree >= 0 && a->sh_degree <= 4 &&
+                     (a->sh_degree + 1) * (a->sh_degree + 1) <= a->sh_K,
+                 "rs_project_fwd: bad SH arguments (degree %d, K %d)", a->sh_degree, a->sh_K);
     const bool rigid = a->rigid.cluster_ids != nullptr;
     if (rigid)
         RS_CHECK(a->rigid.body_quats && a->rigid.body_trans && a->rigid.K > 0,

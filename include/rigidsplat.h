@@ -91,6 +91,12 @@ typedef struct {
      * the staging format of rs_raster_fwd (pass them as rs_raster_fwd_args.records with records_ready = 1).  Needs
      * opacities; written for visible rows only. */
     float *records;
+    /* optional: view-dependent colours evaluated in place (rendering.py:491-525 without the dirs / colours round trip):
+     * sh_colors[b,c,g,:] = max(SH(sh_degree, mean' - camera origin, sh_coeffs[b,g]) + 0.5, 0) for visible rows, where
+     * mean' is the rigidly moved mean (the coefficients are NOT rotated with the body, as in main.py:200-226). */
+    const float *sh_coeffs;     /* [B,N,sh_K,3] optional */
+    float *sh_colors;           /* [B,C,N,3] out, required with sh_coeffs */
+    int32_t sh_degree, sh_K;
 } rs_project_fwd_args;
 int rs_project_fwd(const rs_project_fwd_args *a, rs_stream_t stream);
 
@@ -274,7 +280,9 @@ int rs_sh_bwd(const rs_sh_args *a, rs_stream_t stream);
  * ------------------------------------------------------------------------------------------------------------ */
 typedef struct {
     rs_project_fwd_args proj;    /* B must be 1; tiles_per_gauss/block_sums are taken from the workspace when NULL */
-    const float *colors;         /* [N,channels] (shared by all cameras) or [C,N,channels] if colors_per_camera */
+    const float *colors;         /* [N,channels] (shared by all cameras) or [C,N,channels] if colors_per_camera;
+                                  * ignored when proj.sh_coeffs is set (colours then come from the SH evaluation fused
+                                  * into the projection, channels must be 3, proj.sh_colors is taken from the workspace) */
     int32_t channels;
     int32_t colors_per_camera;
     const float *backgrounds;    /* [C,channels] optional */

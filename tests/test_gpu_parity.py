@@ -514,3 +514,31 @@ def test_frame_pipeline_matches_sequential(rs):
     for k in range(len(poses) - 3, len(poses)):
         assert torch.equal(outs[k][0], want[k][0])
     assert not pipe.overflowed()
+
+
+def test_frame_renderer_sh_matches_rasterization(rs):
+    """SH colours evaluated inside the projection kernel (frame path) vs rasterization(sh_degree=3) (operator path:
+    rs_sh_fwd on explicit view directions), rigid poses on."""
+    W, H, N, K = 288, 160, 20_000, 3
+    s = synthetic_scene(13, N, K=K)
+    vm, Ks = pinhole_cameras(2, W, H)
+    t = {k: T(v) for k, v in s.items()}
+    g = torch.Generator(device=DEV).manual_seed(4)
+    coeffs = torch.randn(N, 16, 3, device=DEV, generator=g) * 0.3
+    rigid = dict(cluster_ids=t["cluster_ids"], body_quats=t["body_quats"], body_trans=t["body_trans"],
+                 body_centers=t["body_centers"])
+    want, want_a, _ = rs.rasterization(t["means"], t["quats"], t["scales"], t["opacities"], coeffs, T(vm), T(Ks), W, H,
+                                       sh_degree=3, packed=False, **rigid)
+    fr = rs.FrameRenderer(t["means"], t["quats"], t["scales"], t["opacities"], coeffs, W, H, cluster_ids=t["cluster_ids"],
+                          body_centers=t["body_centers"], n_cameras=2, max_isects=1 << 21, sh_degree=3)
+    img, alpha = fr.render(T(vm), T(Ks), t["body_quats"], t["body_trans"])
+    assert float(want.abs().max()) > 0.1
+    assert float((img - want).abs().max()) <= 1e-4
+    assert float((alpha - want_a).abs().max()) <= 1e-4
+    # lower degree uses only the first rows
+    fr1 = rs.FrameRenderer(t["means"], t["quats"], t["scales"], t["opacities"], coeffs, W, H, cluster_ids=t["cluster_ids"],
+                           body_centers=t["body_centers"], n_cameras=2, max_isects=1 << 21, sh_degree=1)
+    img1, _ = fr1.render(T(vm), T(Ks), t["body_quats"], t["body_trans"])
+    want1, _, _ = rs.rasterization(t["means"], t["quats"], t["scales"], t["opacities"], coeffs, T(vm), T(Ks), W, H,
+                                   sh_degree=1, packed=False, **rigid)
+    assert float((img1 - want1).abs().max()) <= 1e-4
