@@ -137,6 +137,30 @@ __device__ __forceinline__ float rs_cull_limit(float a, float b, float c, float 
     return 3e38f;
 }
 
+// Exact test "can the splat reach alpha >= 1/255 somewhere in the rectangle [x0,x1] x [y0,y1] (pixel-centre coordinates)":
+// minimum of sigma over the rectangle against the cull limit.  sigma is a convex quadratic centred on the splat, so the
+// minimum is 0 if the centre is inside, else it lies on the edge(s) facing the centre: at most one vertical and one
+// horizontal edge, each a clamped 1-D minimisation.  NaN -> true (evaluate).
+__device__ __forceinline__ bool rs_splat_touches_rect(float cx, float cy, float qa, float qb, float qc, float limit,
+                                                      float x0, float x1, float y0, float y1) {
+    const float dx = cx - fminf(fmaxf(cx, x0), x1); // 0 when the centre is within the x range
+    const float dy = cy - fminf(fmaxf(cy, y0), y1);
+    // vertical edge (fixed dx): optimum dy* = -b dx / c, clamped to the edge
+    const float pyv = fminf(fmaxf(cy + __fdividef(qb * dx, qc), y0), y1);
+    const float d2 = cy - pyv;
+    const float qv = 0.5f * (qa * dx * dx + qc * d2 * d2) + qb * dx * d2;
+    // horizontal edge (fixed dy): optimum dx* = -b dy / a
+    const float pxh = fminf(fmaxf(cx + __fdividef(qb * dy, qa), x0), x1);
+    const float d1 = cx - pxh;
+    const float qh = 0.5f * (qa * d1 * d1 + qc * dy * dy) + qb * d1 * dy;
+    float qmin = 0.f;
+    if (dx != 0.f)
+        qmin = qv;
+    if (dy != 0.f)
+        qmin = (dx != 0.f) ? fminf(qv, qh) : qh;
+    return !(qmin > limit);
+}
+
 // block-wide sum of one int per thread (blockDim.x == RS_ISECT_THREADS), result valid in thread 0
 __device__ __forceinline__ int rs_block_sum_256(int v, int *smem8) {
 #pragma unroll

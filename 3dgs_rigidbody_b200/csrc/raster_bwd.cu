@@ -2,7 +2,7 @@
 // Replaces csrc/RasterizeToPixels3DGSBwd.cu:15-276 (host side csrc/Rasterization.cpp:117-228).
 //
 // Same tile / sub-block decomposition as the forward kernel (one CTA per 16x16 tile, a warp per 8x4 pixels, per-warp
-// culling of splats that cannot reach the sub-block), plus two B200-oriented changes to the reduction that dominates
+// exact culling of splats that cannot reach the sub-block), plus two B200-oriented changes to the reduction that dominates
 // the reference kernel:
 //   * the reference reduces each of the (CDIM + 8) gradient components with its own 5-step cg::reduce and lets lane 0
 //     issue (CDIM + 8) serial atomics.  Here the components are reduced together with a folding butterfly: at each of
@@ -16,36 +16,9 @@
 
 int rs_check_raster_args(const rs_raster_fwd_args *a, const char *who);
 
-__device__ __forceinline__ void rs_cull_extents_b(float a, float b, float c, float op, float &ex, float &ey) {
-    ex = 3e38f;
-    ey = 3e38f;
-    const float det = a * c - b * b;
-    const float L = logf(op * 255.f);
-    if (op < RS_ALPHA_THRESHOLD * 0.999f) {
-        ex = -3e38f;
-        ey = -3e38f;
-        return;
-    }
-    if (a > 0.f && c > 0.f && det > 0.f && a * c <= 256.f * det && L == L) {
-        const float Lm = L + 1e-3f * (1.f + fabsf(L));
-        if (Lm <= 0.f) {
-            ex = 0.25f;
-            ey = 0.25f;
-            return;
-        }
-        const float inv = 2.f * Lm / det;
-        const float hx = sqrtf(inv * c) * 1.0005f + 0.25f;
-        const float hy = sqrtf(inv * a) * 1.0005f + 0.25f;
-        if (hx < 4096.f && hy < 4096.f) {
-            ex = hx;
-            ey = hy;
-        }
-    }
-}
-
 template <int CDIM> struct RastBwdSmem {
     float4 xyoa[RAST_THREADS];
-    float4 bcee[RAST_THREADS];
+    float4 bcee[RAST_THREADS]; // conic b, conic c, cull limit (common.cuh: rs_cull_limit), unused
     int32_t id[RAST_THREADS];
     float color[CDIM][RAST_THREADS];
 };
@@ -215,10 +188,8 @@ rs_raster_bwd_kernel(const rs_raster_bwd_args b, const int ch_off, const int ch_
             const float ca = a.conics[(size_t)g * 3 + 0];
             const float cb = a.conics[(size_t)g * 3 + 1];
             const float cc = a.conics[(size_t)g * 3 + 2];
-            float ex, ey;
-            rs_cull_extents_b(ca, cb, cc, op, ex, ey);
             sm.xyoa[tr] = make_float4(xy.x, xy.y, op, ca);
-            sm.bcee[tr] = make_float4(cb, cc, ex, ey);
+            sm.bcee[tr] = make_float4(cb, cc, rs_cull_limit(ca, cb, cc, op), 0.f);
             sm.id[tr] = g;
             const float *cp = a.colors + (size_t)gc * a.channels + ch_off;
 #pragma unroll
@@ -235,7 +206,7 @@ rs_raster_bwd_kernel(const rs_raster_bwd_args b, const int ch_off, const int ch_
             if (t >= t_begin && t < batch_size) {
                 const float4 g0 = sm.xyoa[t];
                 const float4 g1 = sm.bcee[t];
-                hit = (g0.x + g1.z >= bx0) && (g0.x - g1.z <= bx1) && (g0.y + g1.w >= by0) && (g0.y - g1.w <= by1);
+                hit = rs_splat_touches_rect(g0.x, g0.y, g0.w, g1.x, g1.y, g1.z, bx0, bx1, by0, by1);
             }
             unsigned m = __ballot_sync(0xffffffffu, hit);
             while (m) {

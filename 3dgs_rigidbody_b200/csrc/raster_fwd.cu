@@ -282,27 +282,7 @@ rs_raster_fwd_kernel(const rs_raster_fwd_args a, const int ch_off, const int ch_
                 if (t < batch_size) {
                     const float4 g0 = rs_lds128(a_r0 + t * 16);
                     const float4 g1 = rs_lds128(a_r1 + t * 16);
-                    // exact test: minimum of sigma over the sub-block rectangle [bx0,bx1] x [by0,by1] (which spans the
-                    // pixel centres) against the splat's cull limit.  sigma is a convex quadratic centred on the splat,
-                    // so the minimum is 0 if the centre is inside, else it lies on the edge(s) facing the centre: at
-                    // most one vertical and one horizontal edge, each a clamped 1-D minimisation.
-                    const float cx = g0.x, cy = g0.y, qa = g0.w, qb = g1.x, qc = g1.y;
-                    const float dx = cx - fminf(fmaxf(cx, bx0), bx1); // 0 when the centre is within the x range
-                    const float dy = cy - fminf(fmaxf(cy, by0), by1);
-                    // vertical edge (fixed dx): optimum dy* = -b dx / c, clamped to the edge
-                    const float pyv = fminf(fmaxf(cy + __fdividef(qb * dx, qc), by0), by1);
-                    const float d2 = cy - pyv;
-                    const float qv = 0.5f * (qa * dx * dx + qc * d2 * d2) + qb * dx * d2;
-                    // horizontal edge (fixed dy): optimum dx* = -b dy / a
-                    const float pxh = fminf(fmaxf(cx + __fdividef(qb * dy, qa), bx0), bx1);
-                    const float d1 = cx - pxh;
-                    const float qh = 0.5f * (qa * d1 * d1 + qc * dy * dy) + qb * d1 * dy;
-                    float qmin = 0.f;
-                    if (dx != 0.f)
-                        qmin = qv;
-                    if (dy != 0.f)
-                        qmin = (dx != 0.f) ? fminf(qv, qh) : qh;
-                    hit = !(qmin > g1.z); // NaN -> evaluate
+                    hit = rs_splat_touches_rect(g0.x, g0.y, g0.w, g1.x, g1.y, g1.z, bx0, bx1, by0, by1);
                 }
                 // bit-reversed ballot: the next splat in list order is the highest set bit (one FLO per iteration)
                 unsigned m = __brev(__ballot_sync(0xffffffffu, hit));
