@@ -126,6 +126,7 @@ rs_raster_bwd_kernel(const rs_raster_bwd_args b, const int ch_off, const int ch_
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
         warp_bin_final = max(warp_bin_final, __shfl_xor_sync(0xffffffffu, warp_bin_final, o));
+    const bool inside_any = __any_sync(0xffffffffu, inside);
 
     float bg_dot = 0.f; // sum_k bg_k * v_render_c_k  (Bwd.cu:210-217)
     if (a.backgrounds != nullptr) {
@@ -173,7 +174,18 @@ rs_raster_bwd_kernel(const rs_raster_bwd_args b, const int ch_off, const int ch_
         }
     }
 
-    for (int bb = 0; bb < num_batches; ++bb) {
+    // Splats behind the furthest-back contributor of the whole TILE were never blended by any of its pixels (occluded):
+    // their batches are not even loaded.  In dense scenes that is most of the list (the forward pass reads 14-18 % of it).
+    __shared__ int tile_bin_final;
+    if (tr == 0)
+        tile_bin_final = range_start - 1;
+    __syncthreads();
+    if (lane == 0 && inside_any)
+        atomicMax(&tile_bin_final, warp_bin_final);
+    __syncthreads();
+    const int first_batch = max(0, (range_end - 1 - tile_bin_final) / RAST_THREADS);
+
+    for (int bb = first_batch; bb < num_batches; ++bb) {
         __syncthreads();
         // slot 0 of a batch is its furthest-back splat (Bwd.cu:132-150)
         const int32_t batch_end = range_end - 1 - RAST_THREADS * bb;
