@@ -71,7 +71,7 @@ template <int NV> __device__ __forceinline__ int fold_owner(const int lane, int 
 // component layout of the reduced vector: [0,CDIM) v_colors, CDIM..+2 v_conics, +3..+4 v_means2d, +5 v_opacity,
 // +6..+7 v_means2d_abs (ABS only)
 template <int CDIM, bool ABS>
-__global__ void __launch_bounds__(RAST_THREADS)
+__global__ void __launch_bounds__(RAST_THREADS, (CDIM <= 16) ? 3 : 2)
 rs_raster_bwd_kernel(const rs_raster_bwd_args b, const int ch_off, const int ch_cnt, const bool first_chunk) {
     constexpr int NV = CDIM + 6 + (ABS ? 2 : 0);
     __shared__ RastBwdSmem<CDIM> sm;

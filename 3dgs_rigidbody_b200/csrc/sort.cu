@@ -20,6 +20,10 @@
 
 #include "sort_ws.cuh"
 
+#ifndef SORT_LB_MODE
+#define SORT_LB_MODE 0
+#endif
+
 static_assert(RADIX == SORT_THREADS, "one thread per digit in the block-level scans");
 
 #define LB_AGGREGATE 0x40000000u
@@ -257,7 +261,37 @@ sort_pass_kernel(const KeyT *__restrict__ keys_in, const int32_t *__restrict__ v
         {
             const int d = threadIdx.x;
             int excl = 0;
+#if SORT_LB_MODE == 1 // timing experiment only: no waiting at all (results are wrong)
+            if (false) {
+#elif SORT_LB_MODE == 2 // every predecessor's aggregate is summed directly: no chain of inclusive prefixes to wait for
             if (tile > 0) {
+                for (int t0 = tile - 1; t0 >= 0; t0 -= 16) {
+                    uint32_t v[16];
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj)
+                        v[jj] = (t0 - jj >= 0) ? ld_volatile_u32(lookback + (size_t)(t0 - jj) * RADIX + d) : LB_AGGREGATE;
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) {
+                        while ((v[jj] & (LB_AGGREGATE | LB_INCLUSIVE)) == 0u)
+                            v[jj] = ld_volatile_u32(lookback + (size_t)(t0 - jj) * RADIX + d);
+                    }
+                    bool stop = false;
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) {
+                        if (!stop) {
+                            excl += (int)(v[jj] & LB_VALUE);
+                            stop = (v[jj] & LB_INCLUSIVE) != 0u;
+                        }
+                    }
+                    if (stop)
+                        break;
+                }
+                st_volatile_u32(lookback + (size_t)tile * RADIX + d, LB_INCLUSIVE | (uint32_t)(excl + sm.real[d]));
+            }
+            if (false) {
+#else
+            if (tile > 0) {
+#endif
                 int t = tile - 1;
                 bool found = false;
                 while (!found) {
@@ -383,6 +417,24 @@ extern "C" int rs_radix_sort_pairs(const rs_sort_args *a, rs_stream_t stream) {
                                             reinterpret_cast<const uint64_t *>(a->keys_a), a->vals_a,
                                             reinterpret_cast<uint64_t *>(a->keys_b), a->vals_b,
                                             reinterpret_cast<uint64_t *>(a->keys_a), a->vals_a, a->workspace,
+                                            a->workspace_bytes, &passes, (cudaStream_t)stream);
+    if (e == 0 && a->result_in_b)
+        *a->result_in_b = passes & 1;
+    return e;
+}
+
+// same as rs_radix_sort_pairs for 32-bit keys (keys_a / keys_b point to uint32 arrays): the sort the binning path runs
+extern "C" int rs_radix_sort_pairs32(const rs_sort_args *a, rs_stream_t stream) {
+    RS_CHECK(a != nullptr, "rs_radix_sort_pairs32: null args");
+    RS_CHECK(a->begin_bit >= 0 && a->end_bit <= 32 && a->begin_bit <= a->end_bit, "rs_radix_sort_pairs32: bad bit range");
+    if (a->result_in_b)
+        *a->result_in_b = 0;
+    RS_CHECK(a->n <= 0 || a->end_bit == a->begin_bit || a->vals_a != nullptr, "rs_radix_sort_pairs32: null pointer");
+    int passes = 0;
+    const int e = radix_sort_impl<uint32_t>(a->n, a->n_dev, a->begin_bit, a->end_bit,
+                                            reinterpret_cast<const uint32_t *>(a->keys_a), a->vals_a,
+                                            reinterpret_cast<uint32_t *>(a->keys_b), a->vals_b,
+                                            reinterpret_cast<uint32_t *>(a->keys_a), a->vals_a, a->workspace,
                                             a->workspace_bytes, &passes, (cudaStream_t)stream);
     if (e == 0 && a->result_in_b)
         *a->result_in_b = passes & 1;

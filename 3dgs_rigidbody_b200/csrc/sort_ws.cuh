@@ -2,7 +2,9 @@
 // for it (isect.cu: the emission kernel builds the tile-key histograms while it writes the keys).
 #pragma once
 #define SORT_THREADS 256
+#ifndef SORT_ITEMS
 #define SORT_ITEMS 16
+#endif
 #define SORT_TILE (SORT_THREADS * SORT_ITEMS)
 #define SORT_WARPS (SORT_THREADS / 32)
 #define RADIX_BITS 8

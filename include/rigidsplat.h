@@ -193,6 +193,9 @@ typedef struct {
 } rs_sort_args;
 uint64_t rs_radix_sort_workspace_bytes(int64_t n);
 int rs_radix_sort_pairs(const rs_sort_args *a, rs_stream_t stream);
+/* the same sort for 32-bit keys (keys_a / keys_b are uint32 arrays, end_bit <= 32): what the binning path runs on the
+ * depth keys and on the (image | tile) keys */
+int rs_radix_sort_pairs32(const rs_sort_args *a, rs_stream_t stream);
 
 int rs_isect_offsets(const int64_t *isect_ids_sorted, int64_t n_isects, const int32_t *n_isects_dev /*optional*/,
                      int32_t I, int32_t tile_width, int32_t tile_height, int32_t *offsets /*[I*th*tw]*/,
