@@ -18,21 +18,8 @@
 // its SASS: sigma = fma(dy, b*dx, 0.5 * fma(dx, a*dx, (c*dy)*dy)), alpha = min(.999, op * ex2(-sigma*log2e)), FTZ) so
 // that images, alphas and last_ids are bit-identical to the reference on identical inputs.
 // This stage is issue-bound (FP32 + MUFU), not HBM-bound.
-#include "common.cuh"
+#include "raster_common.cuh"
 
-
-__device__ __forceinline__ void rs_cp_async16(void *smem, const void *gmem) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void rs_cp_async4(void *smem, const void *gmem) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void rs_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N> __device__ __forceinline__ void rs_cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
-}
 
 // records [n, 8] from the operator-level tensors (means2d, conics, opacities)
 __global__ void __launch_bounds__(256) rs_raster_pack_kernel(const rs_raster_fwd_args a, const int64_t n_rows) {
@@ -47,35 +34,6 @@ __global__ void __launch_bounds__(256) rs_raster_pack_kernel(const rs_raster_fwd
     rec[1] = make_float4(cb, cc, rs_cull_limit(ca, cb, cc, op), 0.f);
 }
 
-// ---- mbarrier helpers (shared::cta) --------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned rs_smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void rs_mbar_init(uint64_t *bar, unsigned count) {
-    asm volatile("mbarrier.init.shared.b64 [%0], %1;\n" ::"r"(rs_smem_addr(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ bool rs_mbar_try_wait(uint64_t *bar, unsigned parity) {
-    unsigned ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                 : "=r"(ok)
-                 : "r"(rs_smem_addr(bar)), "r"(parity)
-                 : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void rs_mbar_arrive(uint64_t *bar) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared.b64 st, [%0];\n\t}\n" ::"r"(rs_smem_addr(bar)) : "memory");
-}
-// arrives on `bar` once all cp.async copies issued so far by this thread have landed (does not bump the pending count)
-__device__ __forceinline__ void rs_cp_async_mbar_arrive(uint64_t *bar) {
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];\n" ::"r"(rs_smem_addr(bar)) : "memory");
-}
-
-#ifdef RS_RASTER_STATS
-__device__ unsigned long long rs_stats[8];
-extern "C" void rs_raster_stats(unsigned long long *out) { // {iterations, with >= 1 passing lane, passing, active, chunks}
-    cudaMemcpyFromSymbol(out, rs_stats, sizeof(unsigned long long) * 8);
-    unsigned long long z[8] = {0};
-    cudaMemcpyToSymbol(rs_stats, z, sizeof(z));
-}
-#endif
 // explicit shared-space loads from 32-bit shared addresses (keeps the generic->shared conversion out of the inner loop)
 __device__ __forceinline__ float4 rs_lds128(unsigned addr) {
     float4 v;
@@ -421,6 +379,16 @@ int rs_check_raster_args(const rs_raster_fwd_args *a, const char *who) {
     return 0;
 }
 
+int rs_raster_pack_records(const rs_raster_fwd_args &a, cudaStream_t s) {
+    RS_CHECK(a.means2d && a.conics && a.opacities && a.records, "rs_raster pack: null pointer");
+    RS_CHECK(a.n_rows > 0 || a.n_isects == 0, "rs_raster pack: n_rows required to pack records");
+    if (a.n_rows > 0) {
+        rs_raster_pack_kernel<<<rs_cdiv(a.n_rows, 256), 256, 0, s>>>(a, a.n_rows);
+        RS_LAUNCH_CHECK("rs_raster_pack_kernel");
+    }
+    return 0;
+}
+
 extern "C" int rs_raster_fwd(const rs_raster_fwd_args *a, rs_stream_t stream) {
     if (int e = rs_check_raster_args(a, "rs_raster_fwd"))
         return e;
@@ -432,12 +400,8 @@ extern "C" int rs_raster_fwd(const rs_raster_fwd_args *a, rs_stream_t stream) {
     RS_CHECK(a->records != nullptr && (reinterpret_cast<uintptr_t>(a->records) & 15) == 0,
              "rs_raster_fwd: records scratch ([rows, 8] float, 16-byte aligned) is required");
     if (!a->records_ready) {
-        RS_CHECK(a->means2d && a->conics && a->opacities, "rs_raster_fwd: null pointer");
-        RS_CHECK(a->n_rows > 0 || a->n_isects == 0, "rs_raster_fwd: n_rows required to pack records");
-        if (a->n_rows > 0) {
-            rs_raster_pack_kernel<<<rs_cdiv(a->n_rows, 256), 256, 0, (cudaStream_t)stream>>>(*a, a->n_rows);
-            RS_LAUNCH_CHECK("rs_raster_pack_kernel");
-        }
+        if (int e = rs_raster_pack_records(*a, (cudaStream_t)stream))
+            return e;
     }
     for (int off = 0; off < a->channels; off += 32) {
         const int cnt = a->channels - off < 32 ? a->channels - off : 32;
