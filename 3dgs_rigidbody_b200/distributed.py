@@ -81,8 +81,12 @@ class GaussianShardExchange:
         D = colors.shape[-1]
         Cl = self.local_cameras
         if packed:
+            # rows are ordered by camera, so the rows owned by rank r are the contiguous run of cameras [r*Cl, (r+1)*Cl):
+            # two binary searches per rank instead of a histogram over all rows
+            edges = torch.arange(self.world + 1, device=camera_ids.device, dtype=camera_ids.dtype) * Cl
+            cuts = torch.searchsorted(camera_ids.contiguous(), edges)
+            send_t = cuts[1:] - cuts[:-1]
             owner = torch.div(camera_ids, Cl, rounding_mode="floor")
-            send_t = torch.bincount(owner, minlength=self.world)[: self.world]
             recv_t = torch.empty_like(send_t)
             if self.world > 1:
                 dist.all_to_all_single(recv_t, send_t, group=self.group)
@@ -92,12 +96,13 @@ class GaussianShardExchange:
             nnz = means2d.shape[0]
             fl = torch.cat([means2d, depths.reshape(nnz, 1), conics, opacities.reshape(nnz, 1), colors.reshape(nnz, D)],
                            dim=1)
-            ints = torch.stack([radii[:, 0].long(), radii[:, 1].long(), camera_ids - owner * Cl,
-                                gaussian_ids + self.gaussian_base], dim=1)
+            assert sum(self.n_per_rank) < 2**31, "global Gaussian ids must fit int32 for the exchange"
+            ints = torch.cat([radii.to(torch.int32), (camera_ids - owner * Cl).to(torch.int32).unsqueeze(1),
+                              (gaussian_ids + self.gaussian_base).to(torch.int32).unsqueeze(1)], dim=1)
             fl = self._swap(fl, send, recv, True)
             ints = self._swap(ints, send, recv, False)
-            return (ints[:, :2].to(torch.int32).contiguous(), fl[:, 0:2], fl[:, 2], fl[:, 3:6], fl[:, 6], fl[:, 7:],
-                    ints[:, 2].contiguous(), ints[:, 3].contiguous())
+            return (ints[:, :2].contiguous(), fl[:, 0:2], fl[:, 2], fl[:, 3:6], fl[:, 6], fl[:, 7:],
+                    ints[:, 2].long(), ints[:, 3].long())
 
         Ct, Nl = self.total_cameras, self.n_local
         assert means2d.shape[:2] == (Ct, Nl), means2d.shape

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--packed", type=int, default=1)
+    ap.add_argument("--profile", type=int, default=0, help="print the top CUDA ops of one step on rank 0 (torch.profiler)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -67,6 +68,14 @@ def main():
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     stats = torch.tensor([float(meta["flatten_ids"].numel()), float(alpha.mean())], dtype=torch.float64, device=dev)
     dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    if args.profile:
+        from torch.profiler import ProfilerActivity, profile
+
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+            step()
+            torch.cuda.synchronize()
+        if rank == 0:
+            print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
     if rank == 0:
         ms = float(t[0]) / args.steps
         print(json.dumps({"workload": "c5: Gaussian-sharded render, all-to-all of projected splats", "n_gpus": world,
