@@ -212,6 +212,172 @@ def projection_ewa_3dgs_fused_bwd(
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# packed (COO) projection (Ops.h:98-151; csrc/Projection.cpp:283-547)
+# ---------------------------------------------------------------------------------------------------------------------
+def projection_ewa_3dgs_packed_fwd(
+    means: Tensor,  # [..., N, 3]
+    covars: Optional[Tensor],  # [..., N, 6]
+    quats: Optional[Tensor],  # [..., N, 4]
+    scales: Optional[Tensor],  # [..., N, 3]
+    opacities: Optional[Tensor],  # [..., N]
+    viewmats: Tensor,  # [..., C, 4, 4]
+    Ks: Tensor,  # [..., C, 3, 3]
+    image_width: int,
+    image_height: int,
+    eps2d: float,
+    near_plane: float,
+    far_plane: float,
+    radius_clip: float,
+    calc_compensations: bool,
+    camera_model: int,
+    rigid: Optional[RigidPoses] = None,
+    _capacity: Optional[int] = None,
+) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Optional[Tensor]]:
+    """-> (indptr i32 [B*C+1], batch_ids, camera_ids, gaussian_ids i64 [nnz], radii i32 [nnz,2], means2d [nnz,2],
+    depths [nnz], conics [nnz,3], compensations [nnz] or None), rows in (batch, camera, gaussian) order.
+
+    One projection pass (the reference runs two, csrc/Projection.cpp:331-413): the rows are written into buffers of
+    `_capacity` rows (default: every pair, which cannot overflow) and the returned tensors are views of the first nnz
+    rows; reading nnz is the one host sync of the call, as in the reference (Projection.cpp:369)."""
+    lib = _lib.load()
+    _check(means, "means", torch.float32)
+    _check(viewmats, "viewmats", torch.float32)
+    _check(Ks, "Ks", torch.float32)
+    if covars is not None:
+        _check(covars, "covars", torch.float32)
+    else:
+        if quats is None or scales is None:
+            raise RuntimeError("either covars or (quats, scales) must be provided")
+        _check(quats, "quats", torch.float32)
+        _check(scales, "scales", torch.float32)
+    if opacities is not None:
+        _check(opacities, "opacities", torch.float32)
+    N = means.shape[-2]
+    C = viewmats.shape[-3]
+    B = means.numel() // (N * 3) if N > 0 else 1
+    dev = means.device
+    if rigid is not None:
+        rigid.validate(N, dev)
+    total = B * C * N
+    with torch.cuda.device(dev):
+        indptr = torch.empty(B * C + 1, dtype=torch.int32, device=dev)
+        nnz_dev = torch.empty(1, dtype=torch.int64, device=dev)
+        cap = total if _capacity is None else min(int(_capacity), total)
+        while True:
+            ids = torch.empty((3, cap), dtype=torch.int64, device=dev)
+            radii = torch.empty((cap, 2), dtype=torch.int32, device=dev)
+            means2d = torch.empty((cap, 2), dtype=torch.float32, device=dev)
+            depths = torch.empty((cap,), dtype=torch.float32, device=dev)
+            conics = torch.empty((cap, 3), dtype=torch.float32, device=dev)
+            compensations = torch.zeros((cap,), dtype=torch.float32, device=dev) if calc_compensations else None
+            ws = torch.empty(max(int(lib.rs_project_packed_workspace_bytes(B, C, N)), 16), dtype=torch.uint8, device=dev)
+            pa = _lib.rs_project_packed_fwd_args()
+            a = pa.proj
+            a.B, a.C, a.N = B, C, N
+            a.image_width, a.image_height = int(image_width), int(image_height)
+            a.camera_model = _cam(camera_model)
+            a.eps2d, a.near_plane, a.far_plane, a.radius_clip = eps2d, near_plane, far_plane, radius_clip
+            a.means, a.covars = _ptr(means), _ptr(covars)
+            a.quats, a.scales = _ptr(None if covars is not None else quats), _ptr(None if covars is not None else scales)
+            a.opacities, a.viewmats, a.Ks = _ptr(opacities), _ptr(viewmats), _ptr(Ks)
+            if rigid is not None:
+                rigid.fill(a.rigid)
+            a.radii, a.means2d, a.depths, a.conics = _ptr(radii), _ptr(means2d), _ptr(depths), _ptr(conics)
+            a.compensations = _ptr(compensations)
+            pa.capacity = cap
+            pa.indptr = _ptr(indptr)
+            pa.batch_ids, pa.camera_ids, pa.gaussian_ids = ids[0].data_ptr(), ids[1].data_ptr(), ids[2].data_ptr()
+            pa.nnz = _ptr(nnz_dev)
+            pa.workspace = _ptr(ws)
+            _lib.check(lib.rs_project_packed_fwd(ctypes.byref(pa), _stream()))
+            nnz = int(nnz_dev.item())
+            if nnz <= cap:
+                break
+            cap = nnz  # the caller's capacity hint was too small: run again with room for every row
+    comp = compensations[:nnz] if compensations is not None else None
+    return indptr, ids[0, :nnz], ids[1, :nnz], ids[2, :nnz], radii[:nnz], means2d[:nnz], depths[:nnz], conics[:nnz], comp
+
+
+def projection_ewa_3dgs_packed_bwd(
+    means: Tensor,
+    covars: Optional[Tensor],
+    quats: Optional[Tensor],
+    scales: Optional[Tensor],
+    viewmats: Tensor,
+    Ks: Tensor,
+    image_width: int,
+    image_height: int,
+    eps2d: float,
+    camera_model: int,
+    batch_ids: Tensor,  # [nnz] int64
+    camera_ids: Tensor,  # [nnz] int64
+    gaussian_ids: Tensor,  # [nnz] int64
+    conics: Tensor,  # [nnz, 3]
+    compensations: Optional[Tensor],  # [nnz]
+    v_means2d: Tensor,  # [nnz, 2]
+    v_depths: Tensor,  # [nnz]
+    v_conics: Tensor,  # [nnz, 3]
+    v_compensations: Optional[Tensor],  # [nnz]
+    viewmats_requires_grad: bool,
+    sparse_grad: bool,
+    rigid: Optional[RigidPoses] = None,
+) -> Tuple[Tensor, Optional[Tensor], Optional[Tensor], Optional[Tensor], Optional[Tensor]]:
+    """-> (v_means, v_covars, v_quats, v_scales, v_viewmats); [nnz, ...] rows when sparse_grad, else dense accumulators
+    shaped like the inputs (csrc/Projection.cpp:415-547)."""
+    lib = _lib.load()
+    for t, n in ((means, "means"), (viewmats, "viewmats"), (Ks, "Ks"), (conics, "conics"), (v_means2d, "v_means2d"),
+                 (v_depths, "v_depths"), (v_conics, "v_conics")):
+        _check(t, n, torch.float32)
+    for t, n in ((batch_ids, "batch_ids"), (camera_ids, "camera_ids"), (gaussian_ids, "gaussian_ids")):
+        _check(t, n, torch.int64)
+    nnz = gaussian_ids.shape[0]
+    N = means.shape[-2]
+    C = viewmats.shape[-3]
+    B = means.numel() // (N * 3) if N > 0 else 1
+    dev = means.device
+    if rigid is not None:
+        rigid.validate(N, dev)
+
+    def out_like(t: Tensor) -> Tensor:
+        if sparse_grad:
+            return torch.zeros((nnz,) + tuple(t.shape[-1:]), dtype=t.dtype, device=dev)
+        return torch.zeros_like(t)
+
+    with torch.cuda.device(dev):
+        v_means = out_like(means)
+        v_covars = v_quats = v_scales = None
+        if covars is not None:
+            _check(covars, "covars", torch.float32)
+            v_covars = out_like(covars)
+        else:
+            _check(quats, "quats", torch.float32)
+            _check(scales, "scales", torch.float32)
+            v_quats = out_like(quats)
+            v_scales = out_like(scales)
+        v_viewmats = torch.zeros_like(viewmats) if viewmats_requires_grad else None
+        a = _lib.rs_project_bwd_args()
+        a.B, a.C, a.N = B, C, N
+        a.image_width, a.image_height = int(image_width), int(image_height)
+        a.camera_model = _cam(camera_model)
+        a.eps2d = eps2d
+        a.means, a.covars = _ptr(means), _ptr(covars)
+        a.quats, a.scales = _ptr(None if covars is not None else quats), _ptr(None if covars is not None else scales)
+        a.viewmats, a.Ks = _ptr(viewmats), _ptr(Ks)
+        if rigid is not None:
+            rigid.fill(a.rigid)
+        a.radii, a.conics, a.compensations = None, _ptr(conics), _ptr(compensations)
+        a.v_means2d, a.v_depths, a.v_conics = _ptr(v_means2d), _ptr(v_depths), _ptr(v_conics)
+        a.v_compensations = _ptr(v_compensations)
+        a.v_means, a.v_covars, a.v_quats, a.v_scales = _ptr(v_means), _ptr(v_covars), _ptr(v_quats), _ptr(v_scales)
+        a.v_viewmats = _ptr(v_viewmats)
+        a.batch_ids, a.camera_ids, a.gaussian_ids = _ptr(batch_ids), _ptr(camera_ids), _ptr(gaussian_ids)
+        a.nnz = nnz
+        a.sparse_grad = 1 if sparse_grad else 0
+        _lib.check(lib.rs_project_bwd(ctypes.byref(a), _stream()))
+    return v_means, v_covars, v_quats, v_scales, v_viewmats
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # tile intersection (Ops.h:186-204; csrc/Intersect.cpp:15-168)
 # ---------------------------------------------------------------------------------------------------------------------
 def intersect_tile(

@@ -42,6 +42,8 @@ extern "C" uint64_t rs_sizeof_args(int which) {
         return sizeof(rs_isect_sorted_args);
     case 9:
         return sizeof(rs_sh_args);
+    case 10:
+        return sizeof(rs_project_packed_fwd_args);
     default:
         return 0;
     }

@@ -5,6 +5,8 @@
 // elements, 4 per thread in a coalesced stride-256 pattern, so the per-CTA set-up (pose table, camera) is amortised
 // and every thread has 4 independent load chains in flight.  Algorithmic bytes per element: 48 read (mean 12,
 // quat 16, scale 12, opacity 4, cluster id 4) + 32 written (radii 8, mean2d 8, depth 4, conic 12) + 4 (tile count).
+#include <string.h>
+
 #include "project_math.cuh"
 #include "sh_math.cuh"
 
@@ -24,20 +26,154 @@ __device__ __forceinline__ void rs_project_sh_color(const rs_project_fwd_args &a
     a.sh_colors[idx * 3 + 2] = fmaxf(c[2] + 0.5f, 0.f);
 }
 
+
+// Output of one (image, Gaussian) pair at `row`: the dense index for rs_project_fwd, the packed row for
+// rs_project_packed_fwd.
+__device__ __forceinline__ void rs_store_projected(const rs_project_fwd_args &a, size_t row, const RsProjected &o, bool ok,
+                                                   float opac) {
+    reinterpret_cast<int2 *>(a.radii)[row] = make_int2(o.rx, o.ry);
+    reinterpret_cast<float2 *>(a.means2d)[row] = make_float2(o.mx, o.my);
+    a.depths[row] = o.depth;
+    a.conics[row * 3 + 0] = o.ca;
+    a.conics[row * 3 + 1] = o.cb;
+    a.conics[row * 3 + 2] = o.cc;
+    if (a.compensations != nullptr)
+        a.compensations[row] = o.comp;
+    if (a.records != nullptr && ok) { // compositing record (see raster_fwd.cu); culled rows are never referenced
+        float4 *rec = reinterpret_cast<float4 *>(a.records) + row * 2;
+        rec[0] = make_float4(o.mx, o.my, opac, o.ca);
+        rec[1] = make_float4(o.cb, o.cc, rs_cull_limit(o.ca, o.cb, o.cc, opac), 0.f);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Packed (COO) placement.  Chunks of 256 (image, Gaussian) pairs are taken in ticket order (so every predecessor of a
+// running chunk has started) and the first packed row of a chunk is the number of visible pairs in all earlier chunks,
+// found by a decoupled look-back over one 64-bit status word per chunk: {flag : 32 | count : 32}, flag 0 = not
+// published, 1 = the chunk's own count, 2 = inclusive prefix.  One warp inspects 32 predecessors per round trip.
+// ---------------------------------------------------------------------------------------------------------------------
+#define RS_PACK_AGG (1ull << 32)
+#define RS_PACK_PREFIX (2ull << 32)
+struct PackCtl {
+    unsigned int ticket;
+    unsigned int _pad[3];
+    unsigned long long state[1]; // [n_chunks]
+};
+struct PackSmem {
+    int warp_excl[8];
+    unsigned int base;
+    unsigned int total;
+    unsigned int chunk;
+};
+
+__device__ __forceinline__ unsigned int rs_pack_take_chunk(PackCtl *ctl, PackSmem &ps) {
+    if (threadIdx.x == 0)
+        ps.chunk = atomicAdd(&ctl->ticket, 1u);
+    __syncthreads();
+    return ps.chunk;
+}
+
+// Packed row of the calling thread (meaningful when `valid`); every thread of the 256-thread CTA must call.
+// `chunk_total` / `chunk_base` are returned to all threads.
+__device__ __forceinline__ unsigned int rs_pack_place(bool valid, unsigned int chunk, PackCtl *ctl, PackSmem &ps,
+                                                      unsigned int &chunk_base, unsigned int &chunk_total) {
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned bal = __ballot_sync(0xffffffffu, valid);
+    if (lane == 0)
+        ps.warp_excl[warp] = __popc(bal);
+    __syncthreads();
+    if (warp == 0) {
+        const int v = lane < 8 ? ps.warp_excl[lane] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o)
+                incl += n;
+        }
+        const unsigned int total = (unsigned int)__shfl_sync(0xffffffffu, incl, 7);
+        unsigned int prefix = 0;
+        volatile unsigned long long *state = ctl->state;
+        if (chunk > 0) {
+            if (lane == 0)
+                state[chunk] = RS_PACK_AGG | total;
+            int look = (int)chunk - 1;
+            while (true) {
+                const int j = look - (int)lane;
+                unsigned long long s;
+                do {
+                    s = j >= 0 ? state[j] : RS_PACK_PREFIX;
+                } while (__any_sync(0xffffffffu, (s >> 32) == 0ull));
+                const unsigned pm = __ballot_sync(0xffffffffu, (s >> 32) == 2ull);
+                unsigned int val = (unsigned int)s;
+                if (pm != 0u && lane > (unsigned)(__ffs(pm) - 1))
+                    val = 0u; // behind the nearest published prefix
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                    val += __shfl_xor_sync(0xffffffffu, val, o);
+                prefix += val;
+                if (pm != 0u)
+                    break;
+                look -= 32;
+            }
+        }
+        if (lane == 0) {
+            state[chunk] = RS_PACK_PREFIX | (unsigned long long)(prefix + total);
+            ps.base = prefix;
+        }
+        if (lane < 8)
+            ps.warp_excl[lane] = incl - v;
+        if (lane == 8)
+            ps.total = total;
+    }
+    __syncthreads();
+    chunk_base = ps.base;
+    chunk_total = ps.total;
+    return chunk_base + (unsigned int)ps.warp_excl[warp] + (unsigned int)__popc(bal & rs_lanemask_lt());
+}
+
+struct PackOut {
+    long long capacity;
+    int32_t *indptr;
+    long long *batch_ids, *camera_ids, *gaussian_ids;
+    long long *nnz;
+    PackCtl *ctl;
+    unsigned int n_chunks, chunks_per_image;
+};
+#define RS_PACK_CHUNK 256
+
+
+// The thread holding the first Gaussian of an image records where the image's rows start (its own exclusive rank, visible
+// or not); the last chunk closes indptr and publishes the row count.
+__device__ __forceinline__ void rs_pack_finish(const PackOut &po, unsigned int chunk, unsigned int img, unsigned int gid,
+                                               bool in_range, unsigned int n_images, unsigned int row,
+                                               unsigned int chunk_base, unsigned int chunk_total) {
+    if (in_range && gid == 0u && po.indptr != nullptr)
+        po.indptr[img] = (int32_t)row;
+    if (threadIdx.x == 0 && chunk == po.n_chunks - 1) {
+        if (po.indptr != nullptr)
+            po.indptr[n_images] = (int32_t)(chunk_base + chunk_total);
+        *po.nnz = (long long)chunk_base + chunk_total;
+    }
+}
+
 struct ProjSmem {
     float cam[2][16];
     int sums[8];
 };
 
-template <bool HAS_RIGID>
+template <bool HAS_RIGID, bool PACKED>
 __global__ void __launch_bounds__(RS_ISECT_THREADS, 3)
-rs_project_fwd_kernel(const rs_project_fwd_args a) {
+rs_project_fwd_kernel(const rs_project_fwd_args a, const PackOut po) {
     extern __shared__ __align__(16) float smem_dyn[]; // pose table (HAS_RIGID only)
     __shared__ ProjSmem sm;
+    __shared__ PackSmem ps; // PACKED only
 
     const uint32_t N = a.N, C = a.C;
     const uint64_t total = (uint64_t)a.B * C * N;
-    const uint64_t block_base = (uint64_t)blockIdx.x * RS_ISECT_BLOCK;
+    // PACKED: one 256-pair chunk per CTA, taken in ticket order; else 1024 pairs per CTA
+    const unsigned int chunk = PACKED ? rs_pack_take_chunk(po.ctl, ps) : 0u;
+    const uint64_t block_base = PACKED ? (uint64_t)chunk * RS_PACK_CHUNK : (uint64_t)blockIdx.x * RS_ISECT_BLOCK;
 
     if (HAS_RIGID)
         rs_load_pose_table(a.rigid, smem_dyn);
@@ -62,10 +198,14 @@ rs_project_fwd_kernel(const rs_project_fwd_args a) {
 
     int my_tiles = 0;
 #pragma unroll 1
-    for (int it = 0; it < RS_ISECT_BLOCK / RS_ISECT_THREADS; ++it) {
-        const uint64_t idx = block_base + (uint64_t)it * RS_ISECT_THREADS + threadIdx.x;
-        if (idx >= total)
+    for (int it = 0; it < (PACKED ? 1 : RS_ISECT_BLOCK / RS_ISECT_THREADS); ++it) {
+        const uint64_t idx_raw = block_base + (uint64_t)it * RS_ISECT_THREADS + threadIdx.x;
+        const bool in_range = idx_raw < total;
+        if (!PACKED && !in_range)
             break;
+        // PACKED: the placement below is a block-wide step, so the out-of-range threads of the last chunk stay in the
+        // loop body; they re-evaluate the last pair and drop the result
+        const uint64_t idx = PACKED ? min(idx_raw, total - 1) : idx_raw;
         // (image, gaussian) of this element; the common single-image case needs no division at all and totals below
         // 2^32 avoid the 64-bit divide
         uint32_t img, gid;
@@ -151,33 +291,33 @@ rs_project_fwd_kernel(const rs_project_fwd_args a) {
             opac = a.opacities[gsrc];
 
         RsProjected o;
-        const bool ok = rs_project_gaussian(mean, covar, cam, a.camera_model, (uint32_t)a.image_width,
-                                            (uint32_t)a.image_height, a.eps2d, a.near_plane, a.far_plane,
-                                            a.radius_clip, a.opacities != nullptr ? &opac : nullptr,
-                                            a.compensations != nullptr, o);
+        bool ok = rs_project_gaussian(mean, covar, cam, a.camera_model, (uint32_t)a.image_width,
+                                      (uint32_t)a.image_height, a.eps2d, a.near_plane, a.far_plane, a.radius_clip,
+                                      a.opacities != nullptr ? &opac : nullptr, a.compensations != nullptr, o);
+        if (PACKED)
+            ok = ok && in_range;
         if (!ok) {
             o.mx = o.my = o.depth = o.ca = o.cb = o.cc = 0.f;
             o.comp = 0.f;
         }
-        reinterpret_cast<int2 *>(a.radii)[idx] = make_int2(o.rx, o.ry);
-        reinterpret_cast<float2 *>(a.means2d)[idx] = make_float2(o.mx, o.my);
-        a.depths[idx] = o.depth;
-        a.conics[idx * 3 + 0] = o.ca;
-        a.conics[idx * 3 + 1] = o.cb;
-        a.conics[idx * 3 + 2] = o.cc;
-        if (a.compensations != nullptr)
-            a.compensations[idx] = o.comp;
-        if (a.records != nullptr && ok) { // compositing record (see raster_fwd.cu); culled rows are never referenced
-            float4 *rec = reinterpret_cast<float4 *>(a.records) + idx * 2;
-            rec[0] = make_float4(o.mx, o.my, opac, o.ca);
-            rec[1] = make_float4(o.cb, o.cc, rs_cull_limit(o.ca, o.cb, o.cc, opac), 0.f);
+        size_t row = (size_t)idx;
+        if (PACKED) {
+            unsigned int cb, ct;
+            row = rs_pack_place(ok, chunk, po.ctl, ps, cb, ct);
+            rs_pack_finish(po, chunk, img, gid, in_range, (uint32_t)a.B * C, (unsigned int)row, cb, ct);
+            if (!ok || (long long)row >= po.capacity)
+                break; // nothing else is block-wide in PACKED mode (block_sums is rejected by the host side)
+            po.batch_ids[row] = bid;
+            po.camera_ids[row] = img - bid * C;
+            po.gaussian_ids[row] = gid;
         }
+        rs_store_projected(a, row, o, ok, opac);
         if (a.sh_coeffs != nullptr && ok)
-            rs_project_sh_color(a, cam, mean, gsrc, (size_t)idx);
+            rs_project_sh_color(a, cam, mean, gsrc, row);
         if (a.tiles_per_gauss != nullptr) {
             int cnt = rs_tile_count(o.rx, o.ry, o.mx, o.my, (uint32_t)a.tile_size, (uint32_t)a.tile_width,
                                     (uint32_t)a.tile_height);
-            a.tiles_per_gauss[idx] = cnt;
+            a.tiles_per_gauss[row] = cnt;
             my_tiles += cnt;
         }
     }
@@ -215,16 +355,19 @@ __device__ __forceinline__ void rs_bulk_g2s(void *smem_dst, const void *gmem_src
                  : "memory");
 }
 
-template <bool HAS_RIGID>
+template <bool HAS_RIGID, bool PACKED>
 __global__ void __launch_bounds__(PROJ_CHUNK, 3)
-rs_project_fwd_staged_kernel(const rs_project_fwd_args a) {
+rs_project_fwd_staged_kernel(const rs_project_fwd_args a, const PackOut po) {
     extern __shared__ __align__(16) float smem_dyn[]; // pose table (HAS_RIGID only)
     __shared__ __align__(16) ProjStage st;
+    __shared__ PackSmem ps; // PACKED only
 
     const uint32_t N = a.N, C = a.C;
-    const uint32_t img = blockIdx.y; // bid * C + cid
+    // PACKED: chunks in ticket order over a 1-D grid, image-major; else blockIdx = (chunk of the image, image)
+    const unsigned int chunk = PACKED ? rs_pack_take_chunk(po.ctl, ps) : 0u;
+    const uint32_t img = PACKED ? chunk / po.chunks_per_image : blockIdx.y; // bid * C + cid
     const uint32_t bid = img / C;
-    const uint32_t g0 = blockIdx.x * PROJ_CHUNK;
+    const uint32_t g0 = (PACKED ? chunk - img * po.chunks_per_image : blockIdx.x) * PROJ_CHUNK;
     const uint32_t n_valid = min((uint32_t)PROJ_CHUNK, N - g0);
     const size_t src0 = (size_t)bid * N + g0; // first row of this chunk in the per-batch Gaussian arrays
     const bool full = n_valid == PROJ_CHUNK;
@@ -277,12 +420,15 @@ rs_project_fwd_staged_kernel(const rs_project_fwd_args a) {
                          : "memory");
     }
 
-    int my_tiles = 0;
     const uint32_t t = threadIdx.x;
-    if (t < n_valid) {
-        const uint32_t gid = g0 + t;
-        const size_t idx = (size_t)img * N + gid;
-        RsCam cam;
+    const bool in_range = t < n_valid;
+    const uint32_t gid = g0 + t;
+    RsProjected o;
+    RsCam cam;
+    float mean[3] = {0.f, 0.f, 0.f};
+    float opac = 0.f;
+    bool ok = false;
+    if (in_range) {
         cam.R[0] = st.cam[0];
         cam.R[1] = st.cam[1];
         cam.R[2] = st.cam[2];
@@ -299,11 +445,13 @@ rs_project_fwd_staged_kernel(const rs_project_fwd_args a) {
         cam.fy = st.cam[13];
         cam.cx = st.cam[14];
         cam.cy = st.cam[15];
-        float mean[3] = {st.means[t * 3 + 0], st.means[t * 3 + 1], st.means[t * 3 + 2]};
+        mean[0] = st.means[t * 3 + 0];
+        mean[1] = st.means[t * 3 + 1];
+        mean[2] = st.means[t * 3 + 2];
         const float4 q4 = reinterpret_cast<const float4 *>(st.quats)[t];
         float quat[4] = {q4.x, q4.y, q4.z, q4.w};
         float scale[3] = {st.scales[t * 3 + 0], st.scales[t * 3 + 1], st.scales[t * 3 + 2]};
-        const float opac = st.opacities[t];
+        opac = st.opacities[t];
         if (HAS_RIGID) {
             const int k = st.ids[t];
             if (k >= 0 && k < a.rigid.K) {
@@ -318,94 +466,156 @@ rs_project_fwd_staged_kernel(const rs_project_fwd_args a) {
         }
         float covar[9];
         rs_quat_scale_to_covar(quat, scale, covar, nullptr);
-        RsProjected o;
-        const bool ok = rs_project_gaussian(mean, covar, cam, a.camera_model, (uint32_t)a.image_width,
-                                            (uint32_t)a.image_height, a.eps2d, a.near_plane, a.far_plane, a.radius_clip,
-                                            &opac, a.compensations != nullptr, o);
+        ok = rs_project_gaussian(mean, covar, cam, a.camera_model, (uint32_t)a.image_width, (uint32_t)a.image_height,
+                                 a.eps2d, a.near_plane, a.far_plane, a.radius_clip, &opac, a.compensations != nullptr, o);
         if (!ok) {
             o.mx = o.my = o.depth = o.ca = o.cb = o.cc = 0.f;
             o.comp = 0.f;
         }
-        reinterpret_cast<int2 *>(a.radii)[idx] = make_int2(o.rx, o.ry);
-        reinterpret_cast<float2 *>(a.means2d)[idx] = make_float2(o.mx, o.my);
-        a.depths[idx] = o.depth;
-        a.conics[idx * 3 + 0] = o.ca;
-        a.conics[idx * 3 + 1] = o.cb;
-        a.conics[idx * 3 + 2] = o.cc;
-        if (a.compensations != nullptr)
-            a.compensations[idx] = o.comp;
-        if (a.records != nullptr && ok) {
-            float4 *rec = reinterpret_cast<float4 *>(a.records) + idx * 2;
-            rec[0] = make_float4(o.mx, o.my, opac, o.ca);
-            rec[1] = make_float4(o.cb, o.cc, rs_cull_limit(o.ca, o.cb, o.cc, opac), 0.f);
-        }
-        if (a.sh_coeffs != nullptr && ok)
-            rs_project_sh_color(a, cam, mean, src0 + t, idx);
-        if (a.tiles_per_gauss != nullptr) {
-            my_tiles = rs_tile_count(o.rx, o.ry, o.mx, o.my, (uint32_t)a.tile_size, (uint32_t)a.tile_width,
-                                     (uint32_t)a.tile_height);
-            a.tiles_per_gauss[idx] = my_tiles;
-        }
     }
-    (void)my_tiles;
+    size_t row = (size_t)img * N + gid;
+    if (PACKED) {
+        unsigned int cb, ct;
+        row = rs_pack_place(ok, chunk, po.ctl, ps, cb, ct);
+        rs_pack_finish(po, chunk, img, gid, in_range, (uint32_t)a.B * C, (unsigned int)row, cb, ct);
+        if (!ok || (long long)row >= po.capacity)
+            return;
+        po.batch_ids[row] = bid;
+        po.camera_ids[row] = img - bid * C;
+        po.gaussian_ids[row] = gid;
+    }
+    if (in_range) {
+        rs_store_projected(a, row, o, ok, opac);
+        if (a.sh_coeffs != nullptr && ok)
+            rs_project_sh_color(a, cam, mean, src0 + t, row);
+        if (a.tiles_per_gauss != nullptr)
+            a.tiles_per_gauss[row] = rs_tile_count(o.rx, o.ry, o.mx, o.my, (uint32_t)a.tile_size, (uint32_t)a.tile_width,
+                                                   (uint32_t)a.tile_height);
+    }
 }
 
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-extern "C" int rs_project_fwd(const rs_project_fwd_args *a, rs_stream_t stream) {
-    RS_CHECK(a != nullptr, "rs_project_fwd: null args");
-    RS_CHECK(a->B >= 0 && a->C >= 0 && a->N >= 0, "rs_project_fwd: negative sizes");
+// validation + launch shared by the dense and the packed entry points (po == nullptr: dense)
+static int rs_project_launch(const rs_project_fwd_args *a, PackOut *po, cudaStream_t s, const char *who) {
+    RS_CHECK(a->B >= 0 && a->C >= 0 && a->N >= 0, "%s: negative sizes", who);
     RS_CHECK(a->camera_model == RS_PINHOLE || a->camera_model == RS_ORTHO || a->camera_model == RS_FISHEYE,
-             "rs_project_fwd: unsupported camera model %d (ftheta is only available through the reference's UT path)",
+             "%s: unsupported camera model %d (ftheta is only available through the reference's UT path)", who,
              a->camera_model);
     RS_CHECK((a->covars != nullptr) != (a->quats != nullptr && a->scales != nullptr),
-             "rs_project_fwd: exactly one of covars or (quats, scales) must be given");
+             "%s: exactly one of covars or (quats, scales) must be given", who);
     const int64_t total = (int64_t)a->B * a->C * a->N;
     if (total == 0)
         return 0;
-    RS_CHECK(total < (int64_t)1 << 31, "rs_project_fwd: B*C*N = %lld exceeds int32 indexing", (long long)total);
+    RS_CHECK(total < (int64_t)1 << 31, "%s: B*C*N = %lld exceeds int32 indexing", who, (long long)total);
     RS_CHECK(a->means && a->viewmats && a->Ks && a->radii && a->means2d && a->depths && a->conics,
-             "rs_project_fwd: null required pointer");
+             "%s: null required pointer", who);
     if (a->tiles_per_gauss != nullptr)
         RS_CHECK(a->tile_size > 0 && a->tile_width > 0 && a->tile_height > 0,
-                 "rs_project_fwd: tile geometry required for fused tile counting");
+                 "%s: tile geometry required for fused tile counting", who);
     if (a->sh_coeffs != nullptr)
         RS_CHECK(a->sh_colors != nullptr && a->sh_degree >= 0 && a->sh_degree <= 4 &&
                      (a->sh_degree + 1) * (a->sh_degree + 1) <= a->sh_K,
-                 "rs_project_fwd: bad SH arguments (degree %d, K %d)", a->sh_degree, a->sh_K);
+                 "%s: bad SH arguments (degree %d, K %d)", who, a->sh_degree, a->sh_K);
     const bool rigid = a->rigid.cluster_ids != nullptr;
     if (rigid)
-        RS_CHECK(a->rigid.body_quats && a->rigid.body_trans && a->rigid.K > 0,
-                 "rs_project_fwd: rigid table incomplete (K=%d)", a->rigid.K);
-    cudaStream_t s = (cudaStream_t)stream;
+        RS_CHECK(a->rigid.body_quats && a->rigid.body_trans && a->rigid.K > 0, "%s: rigid table incomplete (K=%d)", who,
+                 a->rigid.K);
+    const size_t pose_smem =
+        rigid && a->rigid.K <= RS_MAX_SMEM_BODIES ? (size_t)a->rigid.K * RS_BODY_FLOATS * sizeof(float) : 0;
+    const bool packed = po != nullptr;
+    PackOut none;
+    memset(&none, 0, sizeof(none));
     // fast path: TMA-staged inputs (see rs_project_fwd_staged_kernel).  block_sums are only needed by the unsorted
     // rs_isect_emit path, which takes them from rs_isect_count, so the staged kernel does not produce them.
     if (a->quats != nullptr && a->opacities != nullptr && a->block_sums == nullptr && aligned16(a->means) &&
         aligned16(a->quats) && aligned16(a->scales) && aligned16(a->opacities) &&
         (!rigid || aligned16(a->rigid.cluster_ids)) && (a->B == 1 || a->N % 4 == 0) && (int64_t)a->B * a->C <= 65535) {
-        const dim3 grid2((unsigned)((a->N + PROJ_CHUNK - 1) / PROJ_CHUNK), (unsigned)(a->B * a->C));
+        const unsigned chunks_per_image = (unsigned)((a->N + PROJ_CHUNK - 1) / PROJ_CHUNK);
         if (rigid) {
-            size_t smem = a->rigid.K <= RS_MAX_SMEM_BODIES ? (size_t)a->rigid.K * RS_BODY_FLOATS * sizeof(float) : 0;
             static bool attr_set = false; // pose table + input stage can exceed the 48 KB default
             if (!attr_set) {
-                RS_CUDA(cudaFuncSetAttribute(rs_project_fwd_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             RS_MAX_SMEM_BODIES * RS_BODY_FLOATS * (int)sizeof(float)));
+                const int bytes = RS_MAX_SMEM_BODIES * RS_BODY_FLOATS * (int)sizeof(float);
+                RS_CUDA(cudaFuncSetAttribute(rs_project_fwd_staged_kernel<true, false>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+                RS_CUDA(cudaFuncSetAttribute(rs_project_fwd_staged_kernel<true, true>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
                 attr_set = true;
             }
-            rs_project_fwd_staged_kernel<true><<<grid2, PROJ_CHUNK, smem, s>>>(*a);
+        }
+        if (packed) {
+            po->chunks_per_image = chunks_per_image;
+            po->n_chunks = chunks_per_image * (unsigned)(a->B * a->C);
+            if (rigid)
+                rs_project_fwd_staged_kernel<true, true><<<po->n_chunks, PROJ_CHUNK, pose_smem, s>>>(*a, *po);
+            else
+                rs_project_fwd_staged_kernel<false, true><<<po->n_chunks, PROJ_CHUNK, 0, s>>>(*a, *po);
         } else {
-            rs_project_fwd_staged_kernel<false><<<grid2, PROJ_CHUNK, 0, s>>>(*a);
+            const dim3 grid2(chunks_per_image, (unsigned)(a->B * a->C));
+            if (rigid)
+                rs_project_fwd_staged_kernel<true, false><<<grid2, PROJ_CHUNK, pose_smem, s>>>(*a, none);
+            else
+                rs_project_fwd_staged_kernel<false, false><<<grid2, PROJ_CHUNK, 0, s>>>(*a, none);
         }
         RS_LAUNCH_CHECK("rs_project_fwd_staged_kernel");
         return 0;
     }
-    const int grid = rs_isect_num_blocks(total);
-    if (rigid) {
-        size_t smem = a->rigid.K <= RS_MAX_SMEM_BODIES ? (size_t)a->rigid.K * RS_BODY_FLOATS * sizeof(float) : 0;
-        rs_project_fwd_kernel<true><<<grid, RS_ISECT_THREADS, smem, s>>>(*a);
+    if (packed) {
+        po->chunks_per_image = 0; // chunks run over the flat (image, Gaussian) index
+        po->n_chunks = (unsigned)((total + RS_PACK_CHUNK - 1) / RS_PACK_CHUNK);
+        if (rigid)
+            rs_project_fwd_kernel<true, true><<<po->n_chunks, RS_ISECT_THREADS, pose_smem, s>>>(*a, *po);
+        else
+            rs_project_fwd_kernel<false, true><<<po->n_chunks, RS_ISECT_THREADS, 0, s>>>(*a, *po);
     } else {
-        rs_project_fwd_kernel<false><<<grid, RS_ISECT_THREADS, 0, s>>>(*a);
+        const int grid = rs_isect_num_blocks(total);
+        if (rigid)
+            rs_project_fwd_kernel<true, false><<<grid, RS_ISECT_THREADS, pose_smem, s>>>(*a, none);
+        else
+            rs_project_fwd_kernel<false, false><<<grid, RS_ISECT_THREADS, 0, s>>>(*a, none);
     }
     RS_LAUNCH_CHECK("rs_project_fwd_kernel");
     return 0;
+}
+
+extern "C" int rs_project_fwd(const rs_project_fwd_args *a, rs_stream_t stream) {
+    RS_CHECK(a != nullptr, "rs_project_fwd: null args");
+    return rs_project_launch(a, nullptr, (cudaStream_t)stream, "rs_project_fwd");
+}
+
+// ticket + one status word per 256-pair chunk (the staged kernel chunks per image, the general one over the flat index;
+// the former never has fewer chunks)
+extern "C" uint64_t rs_project_packed_workspace_bytes(int32_t B, int32_t C, int32_t N) {
+    const uint64_t chunks = (uint64_t)((N + PROJ_CHUNK - 1) / PROJ_CHUNK) * (uint64_t)B * (uint64_t)C;
+    return sizeof(PackCtl) + (chunks + 1) * sizeof(unsigned long long);
+}
+
+extern "C" int rs_project_packed_fwd(const rs_project_packed_fwd_args *pa, rs_stream_t stream) {
+    RS_CHECK(pa != nullptr, "rs_project_packed_fwd: null args");
+    const rs_project_fwd_args *a = &pa->proj;
+    RS_CHECK(pa->nnz != nullptr, "rs_project_packed_fwd: nnz is required");
+    RS_CHECK(a->block_sums == nullptr, "rs_project_packed_fwd: block_sums is not available for packed rows");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t total = (int64_t)a->B * a->C * a->N;
+    if (total <= 0) { // no rows: indptr all zero
+        RS_CHECK(a->B >= 0 && a->C >= 0 && a->N >= 0, "rs_project_packed_fwd: negative sizes");
+        RS_CUDA(cudaMemsetAsync(pa->nnz, 0, sizeof(int64_t), s));
+        if (pa->indptr != nullptr)
+            RS_CUDA(cudaMemsetAsync(pa->indptr, 0, ((size_t)a->B * a->C + 1) * sizeof(int32_t), s));
+        return 0;
+    }
+    RS_CHECK(pa->capacity >= 0 && pa->workspace != nullptr, "rs_project_packed_fwd: workspace / capacity missing");
+    RS_CHECK(pa->capacity == 0 || (pa->batch_ids && pa->camera_ids && pa->gaussian_ids),
+             "rs_project_packed_fwd: id outputs are required");
+    RS_CUDA(cudaMemsetAsync(pa->workspace, 0, rs_project_packed_workspace_bytes(a->B, a->C, a->N), s));
+    PackOut po;
+    po.capacity = pa->capacity;
+    po.indptr = pa->indptr;
+    po.batch_ids = (long long *)pa->batch_ids;
+    po.camera_ids = (long long *)pa->camera_ids;
+    po.gaussian_ids = (long long *)pa->gaussian_ids;
+    po.nnz = (long long *)pa->nnz;
+    po.ctl = (PackCtl *)pa->workspace;
+    po.n_chunks = po.chunks_per_image = 0;
+    return rs_project_launch(a, &po, s, "rs_project_packed_fwd");
 }

@@ -156,7 +156,8 @@ __global__ void __launch_bounds__(RS_ISECT_THREADS)
 rs_project_bwd_kernel(const rs_project_bwd_args a) {
     extern __shared__ __align__(16) float smem_dyn[];
     const uint32_t N = a.N, C = a.C;
-    const uint64_t total = (uint64_t)a.B * C * N;
+    const bool packed = a.gaussian_ids != nullptr; // rows are (batch, camera, gaussian) triples, all visible
+    const uint64_t total = packed ? (uint64_t)a.nnz : (uint64_t)a.B * C * N;
     const uint64_t block_base = (uint64_t)blockIdx.x * RS_ISECT_BLOCK;
     if (HAS_RIGID) {
         rs_load_pose_table(a.rigid, smem_dyn);
@@ -167,7 +168,11 @@ rs_project_bwd_kernel(const rs_project_bwd_args a) {
         const uint64_t idx = block_base + (uint64_t)it * RS_ISECT_THREADS + threadIdx.x;
         bool active = idx < total;
         uint32_t img = 0, gid = 0, bid = 0;
-        if (active) {
+        if (active && packed) {
+            bid = (uint32_t)a.batch_ids[idx];
+            img = bid * C + (uint32_t)a.camera_ids[idx];
+            gid = (uint32_t)a.gaussian_ids[idx];
+        } else if (active) {
             const int2 r = reinterpret_cast<const int2 *>(a.radii)[idx];
             active = r.x > 0 && r.y > 0;
             img = (uint32_t)(idx / N);
@@ -310,10 +315,12 @@ rs_project_bwd_kernel(const rs_project_bwd_args a) {
                 v_mean[1] = vm3[1];
                 v_mean[2] = vm3[2];
             }
+            // sparse_grad (packed only): one output row per packed row instead of the dense per-Gaussian accumulators
+            const size_t orow = (packed && a.sparse_grad) ? (size_t)idx : gsrc;
             if (a.v_means != nullptr) {
-                atomicAdd(a.v_means + gsrc * 3 + 0, v_mean[0]);
-                atomicAdd(a.v_means + gsrc * 3 + 1, v_mean[1]);
-                atomicAdd(a.v_means + gsrc * 3 + 2, v_mean[2]);
+                atomicAdd(a.v_means + orow * 3 + 0, v_mean[0]);
+                atomicAdd(a.v_means + orow * 3 + 1, v_mean[1]);
+                atomicAdd(a.v_means + orow * 3 + 2, v_mean[2]);
             }
             if (!has_quat) {
                 if (a.v_covars != nullptr) {
@@ -322,7 +329,7 @@ rs_project_bwd_kernel(const rs_project_bwd_args a) {
                         rs_mm3_tn(body, v_covar, t1);
                         rs_mm3(t1, body, v_covar);
                     }
-                    float *o = a.v_covars + gsrc * 6;
+                    float *o = a.v_covars + orow * 6;
                     atomicAdd(o + 0, v_covar[0]);
                     atomicAdd(o + 1, v_covar[1] + v_covar[3]);
                     atomicAdd(o + 2, v_covar[2] + v_covar[6]);
@@ -379,14 +386,14 @@ rs_project_bwd_kernel(const rs_project_bwd_args a) {
                     v_quat[3] = w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2;
                 }
                 if (a.v_quats != nullptr) {
-                    float *o = a.v_quats + gsrc * 4;
+                    float *o = a.v_quats + orow * 4;
                     atomicAdd(o + 0, v_quat[0]);
                     atomicAdd(o + 1, v_quat[1]);
                     atomicAdd(o + 2, v_quat[2]);
                     atomicAdd(o + 3, v_quat[3]);
                 }
                 if (a.v_scales != nullptr) {
-                    float *o = a.v_scales + gsrc * 3;
+                    float *o = a.v_scales + orow * 3;
                     atomicAdd(o + 0, v_scale[0]);
                     atomicAdd(o + 1, v_scale[1]);
                     atomicAdd(o + 2, v_scale[2]);
@@ -433,11 +440,17 @@ extern "C" int rs_project_bwd(const rs_project_bwd_args *a, rs_stream_t stream) 
              "rs_project_bwd: unsupported camera model %d", a->camera_model);
     RS_CHECK((a->covars != nullptr) != (a->quats != nullptr && a->scales != nullptr),
              "rs_project_bwd: exactly one of covars or (quats, scales) must be given");
-    const int64_t total = (int64_t)a->B * a->C * a->N;
+    const bool packed = a->gaussian_ids != nullptr;
+    if (packed)
+        RS_CHECK(a->batch_ids && a->camera_ids && a->nnz >= 0, "rs_project_bwd: packed rows need batch / camera ids and nnz");
+    else
+        RS_CHECK(!a->sparse_grad, "rs_project_bwd: sparse_grad needs packed rows");
+    const int64_t total = packed ? a->nnz : (int64_t)a->B * a->C * a->N;
     if (total == 0)
         return 0;
-    RS_CHECK(total < (int64_t)1 << 31, "rs_project_bwd: B*C*N exceeds int32 indexing");
-    RS_CHECK(a->means && a->viewmats && a->Ks && a->radii && a->conics && a->v_means2d && a->v_depths && a->v_conics,
+    RS_CHECK(total < (int64_t)1 << 31, "rs_project_bwd: row count exceeds int32 indexing");
+    RS_CHECK(a->means && a->viewmats && a->Ks && (packed || a->radii) && a->conics && a->v_means2d && a->v_depths &&
+                 a->v_conics,
              "rs_project_bwd: null required pointer");
     RS_CHECK((a->v_compensations == nullptr) || (a->compensations != nullptr),
              "rs_project_bwd: v_compensations given without compensations");

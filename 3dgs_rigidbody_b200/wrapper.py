@@ -94,25 +94,17 @@ def fully_fused_projection(
     viewmats = viewmats.contiguous()
     Ks = Ks.contiguous()
 
-    radii, means2d, depths, conics, compensations = _FullyFusedProjection.apply(
+    if packed:
+        # COO rows of the visible (batch, camera, gaussian) triples, in row-major order: one projection pass that places its
+        # rows by a decoupled look-back (reference: two passes + cumsum, csrc/ProjectionEWA3DGSPacked.cu:17-375)
+        return _FullyFusedProjectionPacked.apply(
+            means, covars, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip,
+            sparse_grad, calc_compensations, camera_model, opacities, rigid,
+        )
+    return _FullyFusedProjection.apply(
         means, covars, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane, radius_clip,
         calc_compensations, camera_model, opacities, rigid,
     )
-    if not packed:
-        return radii, means2d, depths, conics, compensations
-
-    # packed (COO) view of the same result: rows where both radii are positive, in (batch, camera, gaussian) order
-    # (reference: csrc/ProjectionEWA3DGSPacked.cu:17-375 produces the same rows with a two-pass compaction).
-    B = math.prod(batch_dims)
-    sel = (radii > 0).all(dim=-1).reshape(B, C, N)
-    batch_ids, camera_ids, gaussian_ids = torch.nonzero(sel, as_tuple=True)
-    flat = (batch_ids * C + camera_ids) * N + gaussian_ids
-    radii_p = radii.reshape(-1, 2)[flat]
-    means2d_p = means2d.reshape(-1, 2)[flat]
-    depths_p = depths.reshape(-1)[flat]
-    conics_p = conics.reshape(-1, 3)[flat]
-    comp_p = compensations.reshape(-1)[flat] if compensations is not None else None
-    return batch_ids, camera_ids, gaussian_ids, radii_p, means2d_p, depths_p, conics_p, comp_p
 
 
 @torch.no_grad()
@@ -280,6 +272,65 @@ class _FullyFusedProjection(torch.autograd.Function):
         if not ctx.needs_input_grad[4]:
             v_viewmats = None
         return (v_means, v_covars, v_quats, v_scales, v_viewmats) + (None,) * 11
+
+
+class _FullyFusedProjectionPacked(torch.autograd.Function):
+    """Projects Gaussians to 2D, packed rows (reference: _wrapper.py:1579-1796), with the rigid transform fused in."""
+
+    @staticmethod
+    def forward(ctx, means, covars, quats, scales, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
+                radius_clip, sparse_grad, calc_compensations, camera_model, opacities, rigid):
+        assert (
+            camera_model != "ftheta"
+        ), "ftheta camera is only supported via UT, please set with_ut=True in the rasterization()"
+        camera_model_type = _CAMERA_MODELS[camera_model]
+        (_indptr, batch_ids, camera_ids, gaussian_ids, radii, means2d, depths, conics,
+         compensations) = _C.projection_ewa_3dgs_packed_fwd(
+            means, covars, quats, scales, opacities, viewmats, Ks, width, height, eps2d, near_plane, far_plane,
+            radius_clip, calc_compensations, camera_model_type, rigid,
+        )
+        if not calc_compensations:
+            compensations = None
+        ctx.save_for_backward(batch_ids, camera_ids, gaussian_ids, means, covars, quats, scales, viewmats, Ks, conics,
+                              compensations)
+        ctx.width = width
+        ctx.height = height
+        ctx.eps2d = eps2d
+        ctx.sparse_grad = sparse_grad
+        ctx.camera_model_type = camera_model_type
+        ctx.rigid = rigid
+        ctx.mark_non_differentiable(batch_ids, camera_ids, gaussian_ids, radii)
+        return batch_ids, camera_ids, gaussian_ids, radii, means2d, depths, conics, compensations
+
+    @staticmethod
+    def backward(ctx, v_batch_ids, v_camera_ids, v_gaussian_ids, v_radii, v_means2d, v_depths, v_conics,
+                 v_compensations):
+        (batch_ids, camera_ids, gaussian_ids, means, covars, quats, scales, viewmats, Ks, conics,
+         compensations) = ctx.saved_tensors
+        sparse_grad = ctx.sparse_grad
+        if v_compensations is not None:
+            v_compensations = v_compensations.contiguous()
+        v_means, v_covars, v_quats, v_scales, v_viewmats = _C.projection_ewa_3dgs_packed_bwd(
+            means, covars, quats, scales, viewmats, Ks, ctx.width, ctx.height, ctx.eps2d, ctx.camera_model_type,
+            batch_ids, camera_ids, gaussian_ids, conics, compensations, v_means2d.contiguous(), v_depths.contiguous(),
+            v_conics.contiguous(), v_compensations, ctx.needs_input_grad[4], sparse_grad, ctx.rigid,
+        )
+
+        def finish(needed: bool, values: Optional[Tensor], like: Optional[Tensor]):
+            if not needed or values is None:
+                return None
+            if sparse_grad:  # [nnz, D] rows -> sparse COO over the Gaussian axis (_wrapper.py:1726-1772)
+                return torch.sparse_coo_tensor(indices=gaussian_ids[None], values=values, size=like.shape,
+                                               is_coalesced=len(viewmats) == 1)
+            return values
+
+        return (
+            finish(ctx.needs_input_grad[0], v_means, means),
+            finish(ctx.needs_input_grad[1], v_covars, covars),
+            finish(ctx.needs_input_grad[2], v_quats, quats),
+            finish(ctx.needs_input_grad[3], v_scales, scales),
+            v_viewmats if ctx.needs_input_grad[4] else None,
+        ) + (None,) * 12
 
 
 class _RasterizeToPixels(torch.autograd.Function):

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RS_ABI_VERSION 4
+#define RS_ABI_VERSION 5
 
 /* gsplat/cuda/include/Common.h:46-51 (CameraModelType) */
 enum { RS_PINHOLE = 0, RS_ORTHO = 1, RS_FISHEYE = 2, RS_FTHETA = 3 };
@@ -124,8 +124,40 @@ typedef struct {
     float *v_quats;              /* [B,N,4] optional */
     float *v_scales;             /* [B,N,3] optional */
     float *v_viewmats;           /* [B,C,4,4] optional */
+    /* packed (COO) rows, replaces `projection_ewa_3dgs_packed_bwd` (Ops.h:125-151, csrc/Projection.cpp:415-547, kernel
+     * csrc/ProjectionEWA3DGSPacked.cu:378-758): when gaussian_ids != NULL the per-row tensors (conics, compensations,
+     * v_means2d, v_depths, v_conics, v_compensations) are [nnz, ...], row r belongs to (batch_ids[r], camera_ids[r],
+     * gaussian_ids[r]), `radii` is ignored (every row is visible), and with sparse_grad != 0 the v_means / v_covars /
+     * v_quats / v_scales outputs are [nnz, ...] rows instead of dense accumulators. */
+    const int64_t *batch_ids, *camera_ids, *gaussian_ids;
+    int64_t nnz;
+    int32_t sparse_grad;
+    int32_t _pad2;
 } rs_project_bwd_args;
 int rs_project_bwd(const rs_project_bwd_args *a, rs_stream_t stream);
+
+/* rs_project_packed_fwd: replaces `projection_ewa_3dgs_packed_fwd` (Ops.h:98-124, csrc/Projection.cpp:283-413, kernels
+ * csrc/ProjectionEWA3DGSPacked.cu:17-375).  The reference runs the projection TWICE (count pass, at::cumsum, a host
+ * sync, write pass); here ONE pass projects every (image, Gaussian) pair and places the visible ones with a decoupled
+ * look-back over 256-pair chunks taken in ticket order, so the rows come out in the reference's row-major
+ * (batch, camera, gaussian) order without a second evaluation and without a host round trip inside the call.
+ *   - `proj` holds the inputs of rs_project_fwd; its output pointers (radii, means2d, depths, conics, compensations and,
+ *     if wanted, records / sh_colors / tiles_per_gauss) are PACKED rows [capacity, ...]; block_sums must be NULL.
+ *   - rows beyond `capacity` are dropped but still counted: *nnz > capacity tells the caller to regrow.
+ *   - indptr[i] = first row of image i (i = batch * C + camera), indptr[B*C] = nnz.
+ *   - workspace: rs_project_packed_workspace_bytes(B, C, N) bytes of scratch (zeroed by the call itself). */
+typedef struct {
+    rs_project_fwd_args proj;
+    int64_t capacity;
+    int32_t *indptr;            /* [B*C+1] out, optional */
+    int64_t *batch_ids;         /* [capacity] out */
+    int64_t *camera_ids;        /* [capacity] out */
+    int64_t *gaussian_ids;      /* [capacity] out */
+    int64_t *nnz;               /* [1] device, out */
+    void *workspace;
+} rs_project_packed_fwd_args;
+uint64_t rs_project_packed_workspace_bytes(int32_t B, int32_t C, int32_t N);
+int rs_project_packed_fwd(const rs_project_packed_fwd_args *a, rs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Tile intersection.  Replaces `intersect_tile` (Ops.h:186-198, csrc/Intersect.cpp:15-149, kernels
