@@ -11,15 +11,23 @@ ONE row -- [means2d 2 | depth 1 | conic 3 | opacity 1 | colour D] float32 -- sen
 `all_to_all_single`, and one more for the integer columns (radii, and the ids when packed), so a frame costs two NCCL
 collectives over NVLink instead of four to eight.  Frames / cameras sharding (c2, c4) needs no collective at all and does
 not come through here.
+
+`PeerSplatExchange` is the NVLink-native form of the same step for packed rows when no gradient has to flow back (the
+render / animation path): no NCCL call at all -- one kernel per rank stores its rows straight into the receive arrays of
+the ranks that own the cameras, over peer-mapped memory (csrc/exchange.cu).  The NCCL route above stays for training,
+where autograd needs the transposed exchange.
 """
 from __future__ import annotations
 
-from typing import List, Optional, Tuple
+import ctypes
+from typing import Dict, List, Optional, Tuple
 
 import torch
 import torch.distributed as dist
 import torch.distributed.nn.functional as dist_fn
 from torch import Tensor
+
+from . import _lib
 
 
 def _world() -> Tuple[int, int]:
@@ -119,3 +127,126 @@ class GaussianShardExchange:
 
         fl, ri = regroup(fl), regroup(ri)
         return (ri.contiguous(), fl[..., 0:2], fl[..., 2], fl[..., 3:6], fl[..., 6], fl[..., 7:], None, None)
+
+
+class _DeviceArray:
+    """Raw device memory presented to torch through __cuda_array_interface__ (no copy; `owner` keeps it alive)."""
+
+    def __init__(self, ptr: int, shape: Tuple[int, ...], typestr: str, owner):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2,
+                                         "strides": None}
+        self._owner = owner
+
+
+class _PeerBuffers:
+    """One receive allocation per rank, mapped by every peer (legacy CUDA IPC over cudaMalloc memory)."""
+
+    def __init__(self, lib, group, device: torch.device, capacity: int, channels: int):
+        self.lib, self.capacity, self.channels = lib, capacity, channels
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        offsets = (ctypes.c_uint64 * 9)()
+        _lib.check(lib.rs_exchange_layout(capacity, channels, offsets))
+        self.offsets = list(offsets)
+        own = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(lib.rs_peer_alloc(self.offsets[-1], ctypes.byref(own)))
+            handle = ctypes.create_string_buffer(64)
+            _lib.check(lib.rs_peer_export(own, handle))
+            handles: List[Optional[bytes]] = [None] * world
+            dist.all_gather_object(handles, handle.raw, group=group)
+            self.own = own.value
+            self.mapped: List[int] = []
+            for s in range(world):
+                if s == rank:
+                    self.mapped.append(self.own)
+                    continue
+                p = ctypes.c_void_p()
+                _lib.check(lib.rs_peer_open(handles[s], ctypes.byref(p)))
+                self.mapped.append(p.value)
+            self.table = torch.tensor(self.mapped, dtype=torch.int64, device=device)
+            self.rank = rank
+        dist.barrier(group=group)
+
+    def column(self, i: int, rows: int, tail: Tuple[int, ...], typestr: str, dtype: torch.dtype, device) -> Tensor:
+        if rows == 0:
+            return torch.empty((0,) + tail, dtype=dtype, device=device)
+        return torch.as_tensor(_DeviceArray(self.own + self.offsets[i], (rows,) + tail, typestr, self), device=device)
+
+    def release(self) -> None:
+        for s, p in enumerate(self.mapped):
+            if s != self.rank:
+                self.lib.rs_peer_close(ctypes.c_void_p(p))
+        self.lib.rs_peer_free(ctypes.c_void_p(self.own))
+        self.mapped = []
+
+
+class PeerSplatExchange:
+    """Packed projected splats -> the ranks owning their cameras, through peer memory (rs_exchange_push / _wait).
+
+    One instance per (process group, device, channel count), kept for the life of the process: the receive arrays are
+    persistent and the returned tensors are views of them, valid until the next exchange() of the same instance.
+    All ranks of the group must call exchange() the same number of times (it is a collective)."""
+
+    _instances: Dict[Tuple, "PeerSplatExchange"] = {}
+    enabled: bool = True  # False routes no-grad packed calls through the NCCL all-to-all too (A/B measurements)
+    initial_capacity: Optional[int] = None  # rows; None = this rank's row count of the first call (regrown on demand)
+
+    @classmethod
+    def get(cls, group, device: torch.device, channels: int) -> "PeerSplatExchange":
+        key = (id(group) if group is not None else None, device.index, channels)
+        if key not in cls._instances:
+            cls._instances[key] = cls(group, device, channels)
+        return cls._instances[key]
+
+    def __init__(self, group, device: torch.device, channels: int):
+        self.lib = _lib.load()
+        self.group, self.device, self.channels = group, device, channels
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        assert self.world <= 16, "PeerSplatExchange: at most 16 ranks (one NVLink domain)"
+        self.epoch = 0
+        self.buffers: Optional[_PeerBuffers] = None
+        self.totals = torch.zeros(3, dtype=torch.int64, device=device)
+
+    def _regrow(self, capacity: int) -> None:
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)  # every rank's wait kernel has finished, so nobody still writes the old arrays
+        if self.buffers is not None:
+            self.buffers.release()
+        self.buffers = _PeerBuffers(self.lib, self.group, self.device, capacity, self.channels)
+
+    def exchange(self, cameras_per_rank: int, indptr: Tensor, camera_ids: Tensor, gaussian_ids: Tensor, radii: Tensor,
+                 means2d: Tensor, depths: Tensor, conics: Tensor, compensations: Optional[Tensor], opacities: Tensor,
+                 opacities_per_row: bool, colors: Tensor, colors_per_row: bool, gaussian_base: int):
+        """-> (radii, means2d, depths, conics, opacities, colors, camera_ids (local), gaussian_ids (global)) of the rows
+        this rank composites, ordered (source rank, camera, Gaussian)."""
+        if self.buffers is None:
+            self._regrow(self.initial_capacity or max(int(camera_ids.shape[0]), 1024))
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        keep = [t.contiguous() for t in (indptr, camera_ids, gaussian_ids, radii, means2d, depths, conics, opacities, colors)]
+        comp = compensations.contiguous() if compensations is not None else None
+        while True:
+            self.epoch += 1
+            a = _lib.rs_exchange_args()
+            a.world, a.rank, a.cameras_per_rank, a.channels = self.world, self.rank, cameras_per_rank, self.channels
+            a.capacity, a.epoch = self.buffers.capacity, self.epoch
+            a.colors_per_row, a.opacities_per_row = int(colors_per_row), int(opacities_per_row)
+            a.peer_base = self.buffers.table.data_ptr()
+            (a.indptr, a.camera_ids, a.gaussian_ids, a.radii, a.means2d, a.depths, a.conics, a.opacities,
+             a.colors) = [t.data_ptr() for t in keep]
+            a.compensations = comp.data_ptr() if comp is not None else None
+            a.gaussian_base = gaussian_base
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.rs_exchange_push(ctypes.byref(a), stream))
+                _lib.check(self.lib.rs_exchange_wait(ctypes.byref(a), self.totals.data_ptr(), stream))
+            got, worst, err = self.totals.tolist()  # the one host sync of the exchange (sizes of the returned views)
+            if err == 1:
+                raise RuntimeError("PeerSplatExchange: a peer did not arrive within the spin limit")
+            if err == 0:
+                break
+            self._regrow(int(worst * 1.25) + 1024)  # identical decision on every rank: `worst` comes from the full matrix
+        b, dev = self.buffers, self.device
+        return (b.column(5, got, (2,), "<i4", torch.int32, dev), b.column(0, got, (2,), "<f4", torch.float32, dev),
+                b.column(1, got, (), "<f4", torch.float32, dev), b.column(2, got, (3,), "<f4", torch.float32, dev),
+                b.column(3, got, (), "<f4", torch.float32, dev),
+                b.column(4, got, (self.channels,), "<f4", torch.float32, dev),
+                b.column(6, got, (), "<i8", torch.int64, dev), b.column(7, got, (), "<i8", torch.int64, dev))

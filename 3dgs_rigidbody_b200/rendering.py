@@ -202,12 +202,40 @@ def rasterization(
         viewmats, Ks = shard.gather_cameras(viewmats, Ks)
         d.C = viewmats.shape[0]
 
+    # Gaussian-sharded render without gradients: packed rows go to their cameras' ranks through NVLink peer memory, one
+    # kernel per rank and no NCCL call on the data path (distributed.PeerSplatExchange); training keeps the
+    # differentiable all-to-all below.
+    needs_grad = torch.is_grad_enabled() and any(
+        t is not None and t.requires_grad for t in (means, quats, scales, covars, opacities, colors, viewmats))
+    peer_path = shard is not None and packed and means.is_cuda and not needs_grad
+    if peer_path:
+        from .distributed import PeerSplatExchange
+
+        peer_path = PeerSplatExchange.enabled
+
     # ---- 1. project (rigid transform fused in) ---------------------------------------------------------------------------
-    projected = fully_fused_projection(
-        means, covars, quats, scales, viewmats, Ks, width, height, eps2d=eps2d, packed=packed, near_plane=near_plane,
-        far_plane=far_plane, radius_clip=radius_clip, sparse_grad=sparse_grad,
-        calc_compensations=(rasterize_mode == "antialiased"), camera_model=camera_model, opacities=opacities, rigid=rigid)
-    if packed:
+    if peer_path:
+        from . import _C
+        from .wrapper import _CAMERA_MODELS
+
+        indptr, batch_ids, camera_ids, gaussian_ids, radii, means2d, depths, conics, compensations = (
+            _C.projection_ewa_3dgs_packed_fwd(
+                means.contiguous(), None if covars is None else covars.contiguous(),
+                None if quats is None else quats.contiguous(), None if scales is None else scales.contiguous(),
+                opacities.contiguous(), viewmats.contiguous(), Ks.contiguous(), width, height, eps2d, near_plane,
+                far_plane, radius_clip, rasterize_mode == "antialiased", _CAMERA_MODELS[camera_model], rigid))
+        projected = None
+    else:
+        projected = fully_fused_projection(
+            means, covars, quats, scales, viewmats, Ks, width, height, eps2d=eps2d, packed=packed, near_plane=near_plane,
+            far_plane=far_plane, radius_clip=radius_clip, sparse_grad=sparse_grad,
+            calc_compensations=(rasterize_mode == "antialiased"), camera_model=camera_model, opacities=opacities,
+            rigid=rigid)
+    if peer_path:
+        rows = (batch_ids, camera_ids, gaussian_ids)
+        alpha_in = None  # opacity x compensation is formed inside the exchange kernel
+        image_ids = camera_ids
+    elif packed:
         batch_ids, camera_ids, gaussian_ids, radii, means2d, depths, conics, compensations = projected
         rows = (batch_ids, camera_ids, gaussian_ids)
         alpha_in = opacities.reshape(d.B, d.N)[batch_ids, gaussian_ids]  # [nnz]
@@ -216,26 +244,40 @@ def rasterization(
         radii, means2d, depths, conics, compensations = projected
         batch_ids = camera_ids = gaussian_ids = image_ids = rows = None
         alpha_in = opacities.unsqueeze(-2).expand(d.batch + (d.C, d.N))  # stride-0 view, consumed without a copy
-    if compensations is not None:
+    if compensations is not None and not peer_path:
         alpha_in = alpha_in * compensations
-    meta: Dict = dict(batch_ids=batch_ids, camera_ids=camera_ids, gaussian_ids=gaussian_ids, radii=radii, means2d=means2d,
-                      depths=depths, conics=conics, opacities=alpha_in)
-
     # ---- 2. shade ----------------------------------------------------------------------------------------------------------
-    if sh_degree is None:
+    if peer_path and sh_degree is None and not per_camera_colors:
+        shaded = None  # the exchange kernel gathers the colour row of each splat itself
+    elif sh_degree is None:
         shaded = _plain_colors(d, colors, per_camera_colors, packed, rows)
     else:
         shaded = _view_dependent_colors(d, colors, per_camera_colors, sh_degree, means, rigid, viewmats, radii, packed, rows)
 
     # ---- 2b. exchange (Gaussian-sharded scenes only) ---------------------------------------------------------------------
     n_images = d.B * d.C
-    if shard is not None:
+    if peer_path:
+        per_row = shaded is not None
+        table = shaded if per_row else colors
+        peer = PeerSplatExchange.get(shard.group, device, int(table.shape[-1]))
+        radii, means2d, depths, conics, alpha_in, shaded, camera_ids, gaussian_ids = peer.exchange(
+            shard.local_cameras, indptr, camera_ids, gaussian_ids, radii, means2d, depths, conics, compensations,
+            opacities, False, table, per_row, shard.gaussian_base)
+        d.C = shard.local_cameras
+        n_images = d.C
+        image_ids = camera_ids
+        batch_ids = torch.zeros_like(camera_ids)
+    elif shard is not None:
         out = shard.exchange(packed, radii, means2d, depths, conics, alpha_in, shaded, camera_ids, gaussian_ids)
         radii, means2d, depths, conics, alpha_in, shaded, camera_ids, gaussian_ids = out
         d.C = shard.local_cameras
         n_images = d.C
         if packed:
             image_ids = camera_ids
+            batch_ids = torch.zeros_like(camera_ids)
+    # the splats this rank composites (after the exchange, as in rendering.py:651-665)
+    meta: Dict = dict(batch_ids=batch_ids, camera_ids=camera_ids, gaussian_ids=gaussian_ids, radii=radii, means2d=means2d,
+                      depths=depths, conics=conics, opacities=alpha_in)
 
     shaded, backgrounds = _attach_depth(render_mode, shaded, depths, backgrounds, d.batch + (d.C,))
 

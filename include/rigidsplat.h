@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RS_ABI_VERSION 5
+#define RS_ABI_VERSION 6
 
 /* gsplat/cuda/include/Common.h:46-51 (CameraModelType) */
 enum { RS_PINHOLE = 0, RS_ORTHO = 1, RS_FISHEYE = 2, RS_FTHETA = 3 };
@@ -158,6 +158,58 @@ typedef struct {
 } rs_project_packed_fwd_args;
 uint64_t rs_project_packed_workspace_bytes(int32_t B, int32_t C, int32_t N);
 int rs_project_packed_fwd(const rs_project_packed_fwd_args *a, rs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Gaussian-sharded scenes: the exchange of projected splats between the ranks of one NVLink domain.  Replaces the
+ * all-to-alls of gsplat/rendering.py:527-611 on top of gsplat/distributed.py:10-257 (count exchange, then one NCCL
+ * all-to-all per attribute list) for packed rows: every rank projects ITS Gaussians to ALL cameras
+ * (rs_project_packed_fwd; rows ordered by camera, so the rows owed to one rank are contiguous), and ONE kernel per rank
+ * stores them straight into the receive arrays of the ranks owning the cameras, over peer-mapped memory.  Rows land
+ * compact and in (source rank, camera, Gaussian) order -- where the reference's all-to-all puts them -- with camera ids
+ * made local and Gaussian ids made global.  See csrc/exchange.cu for the protocol.
+ *
+ * Receive allocation of a rank (identical layout on every rank): RS_EXCHANGE_CTL_BYTES of control block, then the
+ * columns means2d f32[cap,2] | depths f32[cap] | conics f32[cap,3] | opacities f32[cap] | colors f32[cap,channels] |
+ * radii i32[cap,2] | camera_ids i64[cap] | gaussian_ids i64[cap], each starting at offsets[i] (rs_exchange_layout).
+ * It must be ZERO-filled when created (rs_peer_alloc does that) and mapped by every peer (rs_peer_export/open).
+ * ------------------------------------------------------------------------------------------------------------ */
+#define RS_EXCHANGE_MAX_WORLD 16
+#define RS_EXCHANGE_COLUMNS 8
+#define RS_EXCHANGE_CTL_BYTES 4096
+#define RS_PEER_HANDLE_BYTES 64
+int rs_exchange_layout(int64_t capacity, int32_t channels, uint64_t *offsets /* [RS_EXCHANGE_COLUMNS + 1]; last = total bytes */);
+uint64_t rs_exchange_bytes(int64_t capacity, int32_t channels);
+int rs_peer_alloc(uint64_t bytes, void **ptr);
+int rs_peer_free(void *ptr);
+int rs_peer_export(void *ptr, uint8_t *handle /* [RS_PEER_HANDLE_BYTES] out */);
+int rs_peer_open(const uint8_t *handle, void **ptr);
+int rs_peer_close(void *ptr);
+typedef struct {
+    int32_t world, rank;
+    int32_t cameras_per_rank;    /* camera c of the gathered list belongs to rank c / cameras_per_rank */
+    int32_t channels;
+    int64_t capacity;            /* rows of every rank's receive arrays */
+    uint32_t epoch;              /* frame counter, > 0, the same on every rank, +1 per exchange */
+    int32_t colors_per_row;      /* colors is [nnz,channels] (1) or per local Gaussian [N,channels] (0) */
+    int32_t opacities_per_row;   /* opacities is [nnz] (1) or per local Gaussian [N] (0) */
+    int32_t _pad;
+    void *const *peer_base;      /* device array [world]: this rank's mapping of every rank's receive allocation */
+    /* this rank's packed rows (outputs of rs_project_packed_fwd with B = 1): */
+    const int32_t *indptr;       /* [world*cameras_per_rank + 1] */
+    const int64_t *camera_ids, *gaussian_ids;
+    const int32_t *radii;
+    const float *means2d, *depths, *conics;
+    const float *compensations;  /* [nnz] optional: multiplied into the opacity on the way */
+    const float *opacities;
+    const float *colors;
+    int64_t gaussian_base;       /* global index of this rank's first Gaussian */
+} rs_exchange_args;
+/* publish counts, place, store rows into the peers, raise the data flags (one kernel) */
+int rs_exchange_push(const rs_exchange_args *a, rs_stream_t stream);
+/* hold `stream` until every source's rows of this epoch have landed; totals_dev (device, int64[3]) = {rows received,
+ * largest row count any rank receives (capacity needed, identical on all ranks), error: 0 ok | 1 timeout | 2 capacity
+ * exceeded -- nothing was written for the overfull destination} */
+int rs_exchange_wait(const rs_exchange_args *a, int64_t *totals_dev, rs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Tile intersection.  Replaces `intersect_tile` (Ops.h:186-198, csrc/Intersect.cpp:15-149, kernels

@@ -78,3 +78,73 @@ def test_gaussian_sharded_render_matches_single_gpu(rs, packed):
         p.join(timeout=60)
     for rank, msg in results:
         assert msg == "ok", f"rank {rank}:\n{msg}"
+
+
+def _peer_worker(rank, world, port, q):
+    """no_grad + packed: the NVLink peer-memory exchange (rs_exchange_push / _wait) must deliver exactly the rows the NCCL
+    all-to-all delivers -- same order, same values -- for several frames, through a forced regrow, with per-Gaussian
+    colours, per-row (SH) colours and antialiased compensations."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from conftest import pinhole_cameras, synthetic_scene
+
+        rs = importlib.import_module("3dgs_rigidbody_b200")
+        dmod = importlib.import_module("3dgs_rigidbody_b200.distributed")
+        dmod.PeerSplatExchange.initial_capacity = 64  # far too small: the first frame must regrow on every rank
+        W, H, N, Cl = 320, 240, 30_000, 2
+        s = synthetic_scene(3, N, K=3)
+        vm, Ks = pinhole_cameras(world * Cl, W, H)
+        t = {k: torch.from_numpy(v).to(dev) for k, v in s.items()}
+        vm, Ks = torch.from_numpy(vm).to(dev), torch.from_numpy(Ks).to(dev)
+        mine = slice(rank * Cl, (rank + 1) * Cl)
+        lo, hi = rank * N // world, (rank + 1) * N // world
+        g = torch.Generator(device=dev).manual_seed(7)
+        sh = torch.randn(N, 16, 3, device=dev, generator=g) * 0.2
+        for frame in range(3):
+            rigid = dict(cluster_ids=t["cluster_ids"][lo:hi], body_quats=t["body_quats"],
+                         body_trans=t["body_trans"] + 0.05 * frame, body_centers=t["body_centers"])
+            for variant in ("rgb", "sh", "aa"):
+                colors = sh[lo:hi] if variant == "sh" else t["colors"][lo:hi]
+                kw = dict(packed=True, distributed=True, sh_degree=3 if variant == "sh" else None,
+                          rasterize_mode="antialiased" if variant == "aa" else "classic",
+                          render_mode="RGB+ED" if variant == "aa" else "RGB", **rigid)
+                args = (t["quats"][lo:hi], t["scales"][lo:hi], t["opacities"][lo:hi], colors, vm[mine], Ks[mine], W, H)
+                with torch.no_grad():
+                    img_p, alpha_p, meta_p = rs.rasterization(t["means"][lo:hi], *args, **kw)
+                    keep = {k: meta_p[k].clone() for k in ("gaussian_ids", "camera_ids", "radii", "means2d", "opacities")}
+                means = t["means"][lo:hi].clone().requires_grad_(True)  # grad needed -> NCCL all-to-all route
+                img_n, alpha_n, meta_n = rs.rasterization(means, *args, **kw)
+                assert img_p.shape == (Cl, H, W, 4 if variant == "aa" else 3)
+                for k, v in keep.items():
+                    assert torch.equal(v, meta_n[k].detach()), (frame, variant, k)
+                assert torch.equal(img_p, img_n.detach()) and torch.equal(alpha_p, alpha_n.detach()), (frame, variant)
+                assert float(alpha_p.mean()) > 0.01
+        peer = next(iter(dmod.PeerSplatExchange._instances.values()))
+        assert peer.buffers.capacity > 64 and peer.epoch >= 9
+        q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_memory_exchange_equals_nccl_exchange(rs):
+    world = min(torch.cuda.device_count(), 4)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in results:
+        assert msg == "ok", f"rank {rank}:\n{msg}"

@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--packed", type=int, default=1)
+    ap.add_argument("--exchange", choices=("peer", "nccl"), default="peer",
+                    help="packed rows: NVLink peer-memory kernel (rs_exchange_push) or the NCCL all-to-all route")
     ap.add_argument("--profile", type=int, default=0, help="print the top CUDA ops of one step on rank 0 (torch.profiler)")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -34,6 +36,7 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     rs = importlib.import_module("3dgs_rigidbody_b200")
+    importlib.import_module("3dgs_rigidbody_b200.distributed").PeerSplatExchange.enabled = args.exchange == "peer"
     W, H = 1920, 1080
     n_local = args.gaussians // world
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -80,6 +83,7 @@ def main():
         ms = float(t[0]) / args.steps
         print(json.dumps({"workload": "c5: Gaussian-sharded render, all-to-all of projected splats", "n_gpus": world,
                           "gaussians_total": n_local * world, "cameras": world, "packed": bool(args.packed),
+                          "exchange": (args.exchange if args.packed else "nccl"),
                           "ms_per_step": round(ms, 3), "frames_per_s": round(world / (ms * 1e-3), 2),
                           "n_isects_total": int(stats[0]), "mean_alpha": round(float(stats[1]) / world, 4)}))
     dist.destroy_process_group()
