@@ -60,3 +60,86 @@ def make_rigid(cluster_ids: Optional[Tensor], body_quats: Optional[Tensor], body
         body_trans.to(device=dev, dtype=torch.float32).contiguous(),
         None if body_centers is None else body_centers.to(device=dev, dtype=torch.float32).contiguous(),
     )
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Data contract either side of the renderer: clustering output -> cluster ids, per-body rigid parameters,
+# physics poses -> pose tables.  Host-side glue (numpy / torch), nothing here is on the per-frame path.
+# ---------------------------------------------------------------------------------------------------------------------
+def load_cluster_groups(path: str, num_gaussians: int, device: Optional[torch.device] = None) -> Tuple[Tensor, Dict[int, str]]:
+    """Reads the `cluster_groups` archive written by examples/load_identity_encodings.py:566-568 (np.savez_compressed of
+    {str(object id) -> Gaussian indices, "background" -> indices}; main.py:280-297 loads it with np.load) and returns the
+    dense (cluster_ids [N] int32, {body index -> object id}) form the projection kernel consumes."""
+    with np.load(path, allow_pickle=False) as z:
+        groups = {k: z[k] for k in z.files}
+    return cluster_ids_from_groups(groups, num_gaussians, device)
+
+
+def instance_mask_path(data_dir: str, image_name: str) -> str:
+    """Where the per-image instance-id map of an image lives (examples/datasets/colmap.py:498-512; written by
+    utils/instance_maps_to_npy.py:7-40): `<data_dir>/masks/instance_ids_npy/<stem>_instance_id.npy`, [H, W] ints, 0 = bg."""
+    import os
+
+    stem = os.path.splitext(os.path.basename(image_name))[0]
+    return os.path.join(data_dir, "masks", "instance_ids_npy", f"{stem}_instance_id.npy")
+
+
+def body_properties(means: Tensor, scales: Tensor, opacities: Tensor, cluster_ids: Tensor, K: int):
+    """Rigid-body parameters of every cluster (README.md:12, workflow step 2): mass, centre of mass and inertia tensor about
+    the centre of mass, treating each Gaussian as a point mass m_g = opacity_g * prod(scale_g) (its alpha-weighted volume
+    up to a constant) plus the inertia of its own ellipsoid about its principal axes being neglected.
+
+    Returns (mass [K], com [K,3], inertia [K,3,3]); bodies without Gaussians get zeros."""
+    valid = cluster_ids >= 0
+    idx = cluster_ids[valid].long()
+    m = (opacities[valid] * scales[valid].prod(dim=-1)).to(torch.float64)
+    x = means[valid].to(torch.float64)
+    mass = torch.zeros(K, dtype=torch.float64, device=means.device).index_add_(0, idx, m)
+    com = torch.zeros(K, 3, dtype=torch.float64, device=means.device).index_add_(0, idx, x * m[:, None])
+    com = com / mass.clamp_min(1e-300)[:, None]
+    r = x - com[idx]
+    r2 = (r * r).sum(-1)
+    per = m[:, None, None] * (r2[:, None, None] * torch.eye(3, dtype=torch.float64, device=means.device) - r[:, :, None] * r[:, None, :])
+    inertia = torch.zeros(K, 3, 3, dtype=torch.float64, device=means.device).index_add_(0, idx, per)
+    return mass.to(means.dtype), com.to(means.dtype), inertia.to(means.dtype)
+
+
+class PoseStream:
+    """Per-frame rigid poses of K bodies, [F, K, 7] = (quat wxyz | position of the body origin), as a physics engine
+    reports them for bodies whose local origin is their rest-pose centre of mass (README.md:13-14, steps 3-4).
+
+    frame(f) returns the (body_quats [K,4], body_trans [K,3]) tables of rasterization()/FrameRenderer for the pivot
+    `centers` = rest-pose centres: x' = R (x - c) + c + t with t = p_f - c."""
+
+    def __init__(self, poses, rest_centers):
+        poses = torch.as_tensor(poses, dtype=torch.float32)
+        rest_centers = torch.as_tensor(rest_centers, dtype=torch.float32)
+        assert poses.dim() == 3 and poses.shape[-1] == 7, poses.shape
+        assert tuple(rest_centers.shape) == (poses.shape[1], 3), rest_centers.shape
+        self.quats = poses[..., :4].contiguous()
+        self.trans = (poses[..., 4:] - rest_centers.to(poses.device)[None]).contiguous()
+        self.centers = rest_centers
+
+    @classmethod
+    def load(cls, path: str) -> "PoseStream":
+        """npz with `poses` [F,K,7] and `rest_centers` [K,3]."""
+        with np.load(path, allow_pickle=False) as z:
+            return cls(z["poses"], z["rest_centers"])
+
+    def save(self, path: str) -> None:
+        poses = torch.cat([self.quats, self.trans + self.centers[None]], dim=-1)
+        np.savez_compressed(path, poses=poses.cpu().numpy(), rest_centers=self.centers.cpu().numpy())
+
+    def __len__(self) -> int:
+        return self.quats.shape[0]
+
+    @property
+    def num_bodies(self) -> int:
+        return self.quats.shape[1]
+
+    def to(self, device) -> "PoseStream":
+        self.quats, self.trans, self.centers = self.quats.to(device), self.trans.to(device), self.centers.to(device)
+        return self
+
+    def frame(self, f: int) -> Tuple[Tensor, Tensor]:
+        return self.quats[f], self.trans[f]
