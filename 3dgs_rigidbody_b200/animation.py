@@ -117,9 +117,13 @@ class FrameRenderer:
         return a
 
     def render(self, viewmats: Tensor, Ks: Tensor, body_quats: Optional[Tensor] = None,
-               body_trans: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+               body_trans: Optional[Tensor] = None, composite_stream: Optional[torch.cuda.Stream] = None
+               ) -> Tuple[Tensor, Tensor]:
         """Enqueue one frame on the current stream.  Returns views of the renderer-owned output buffers
-        (render_colors [C,H,W,D], render_alphas [C,H,W,1]); they are overwritten by the next call."""
+        (render_colors [C,H,W,D], render_alphas [C,H,W,1]); they are overwritten by the next call.
+
+        With `composite_stream`, projection + binning go to the current stream and compositing to `composite_stream`
+        (ordered after them); the frame is complete when `composite_stream` is."""
         _check(viewmats, "viewmats", torch.float32, (self.C, 4, 4), self.device)
         _check(Ks, "Ks", torch.float32, (self.C, 3, 3), self.device)
         if self.cluster_ids is not None:
@@ -131,7 +135,16 @@ class FrameRenderer:
         with torch.cuda.device(self.device):
             a = self._fill(viewmats, Ks, body_quats, body_trans)
             self._args = a
-            _lib.check(self.lib.rs_render_frame(ctypes.byref(a), torch.cuda.current_stream().cuda_stream))
+            cur = torch.cuda.current_stream()
+            if composite_stream is None:
+                _lib.check(self.lib.rs_render_frame(ctypes.byref(a), cur.cuda_stream))
+            else:
+                a.stages = 1  # RS_FRAME_BIN
+                _lib.check(self.lib.rs_render_frame(ctypes.byref(a), cur.cuda_stream))
+                composite_stream.wait_stream(cur)
+                a.stages = 2  # RS_FRAME_COMPOSITE
+                _lib.check(self.lib.rs_render_frame(ctypes.byref(a), composite_stream.cuda_stream))
+                a.stages = 0
         return self.render_colors, self.render_alphas
 
     def render_timed(self, viewmats: Tensor, Ks: Tensor, body_quats: Optional[Tensor] = None,
@@ -207,12 +220,15 @@ class FramePipeline:
     The returned buffers belong to the renderer that drew the frame and are overwritten `depth` submissions later.
     """
 
-    def __init__(self, depth: int, *args, **kwargs):
+    def __init__(self, depth: int, *args, split: bool = True, **kwargs):
         assert depth >= 1
         self.renderers = [FrameRenderer(*args, **kwargs) for _ in range(depth)]
         dev = self.renderers[0].device
         with torch.cuda.device(dev):
             self.streams = [torch.cuda.Stream(device=dev) for _ in range(depth)]
+            # projection + binning of a frame run on a HIGH-priority stream: their short kernels are then dispatched as
+            # soon as a slot frees instead of queueing behind the thousands of compositing CTAs of the frames in front
+            self.bin_streams = [torch.cuda.Stream(device=dev, priority=-1) for _ in range(depth)] if split else None
         self.device = dev
         self.count = 0
 
@@ -221,11 +237,20 @@ class FramePipeline:
         k = self.count % len(self.renderers)
         self.count += 1
         stream = self.streams[k]
-        stream.wait_stream(torch.cuda.current_stream(self.device))  # the frame's inputs were produced there
-        with torch.cuda.stream(stream):
-            img, alpha = self.renderers[k].render(viewmats, Ks, body_quats, body_trans)
-            done = torch.cuda.Event()
-            done.record(stream)
+        if self.bin_streams is None:
+            stream.wait_stream(torch.cuda.current_stream(self.device))  # the frame's inputs were produced there
+            with torch.cuda.stream(stream):
+                img, alpha = self.renderers[k].render(viewmats, Ks, body_quats, body_trans)
+                done = torch.cuda.Event()
+                done.record(stream)
+            return img, alpha, done
+        front = self.bin_streams[k]
+        front.wait_stream(torch.cuda.current_stream(self.device))  # the frame's inputs were produced there
+        front.wait_stream(stream)  # the slot's previous frame has been composited out of this workspace
+        with torch.cuda.stream(front):
+            img, alpha = self.renderers[k].render(viewmats, Ks, body_quats, body_trans, composite_stream=stream)
+        done = torch.cuda.Event()
+        done.record(stream)
         return img, alpha, done
 
     def join(self) -> None:

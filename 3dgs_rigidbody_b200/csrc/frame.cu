@@ -170,10 +170,13 @@ static int render_frame_impl(const rs_frame_args *a, rs_stream_t stream, cudaEve
         p.sh_colors = reinterpret_cast<float *>(w + L.sh_colors);
     p.tiles_per_gauss = reinterpret_cast<int32_t *>(w + L.tiles_per_gauss);
     p.block_sums = nullptr; // the depth-ordered binning computes its own block sums
+    RS_CHECK(a->stages >= 0 && a->stages <= 3, "rs_render_frame: bad stages %d", a->stages);
+    const bool do_bin = a->stages == 0 || (a->stages & RS_FRAME_BIN), do_composite = a->stages == 0 || (a->stages & RS_FRAME_COMPOSITE);
     if (ev)
         RS_CUDA(cudaEventRecord(ev[0], s));
-    if (int e = rs_project_fwd(&p, stream))
-        return e;
+    if (do_bin)
+        if (int e = rs_project_fwd(&p, stream))
+            return e;
     if (ev)
         RS_CUDA(cudaEventRecord(ev[1], s));
 
@@ -184,8 +187,9 @@ static int render_frame_impl(const rs_frame_args *a, rs_stream_t stream, cudaEve
     sa.tile_offsets = offsets;
     sa.workspace = w + L.bin_ws;
     sa.workspace_bytes = L.bin_ws_bytes;
-    if (int e = rs_isect_sorted(&sa, stream))
-        return e;
+    if (do_bin)
+        if (int e = rs_isect_sorted(&sa, stream))
+            return e;
     const int32_t *vals_sorted = sa.isect.flatten_ids;
     if (ev)
         RS_CUDA(cudaEventRecord(ev[2], s));
@@ -218,8 +222,9 @@ static int render_frame_impl(const rs_frame_args *a, rs_stream_t stream, cudaEve
     r.records = p.records;
     r.records_ready = 1;
     r.n_rows = (int64_t)p.C * p.N;
-    if (int e = rs_raster_fwd(&r, stream))
-        return e;
+    if (do_composite)
+        if (int e = rs_raster_fwd(&r, stream))
+            return e;
     if (ev)
         RS_CUDA(cudaEventRecord(ev[3], s));
     return 0;

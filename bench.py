@@ -356,7 +356,7 @@ def ours_arm(args):
     # ---- device-resident throughput ------------------------------------------------------------------------------
     pipe = rs.FramePipeline(args.in_flight, sc["means"], sc["quats"], sc["scales"], sc["opacities"], sc["colors"], WIDTH,
                             HEIGHT, cluster_ids=sc["cluster_ids"], body_centers=sc["body_centers"],
-                            max_isects=args.max_isects)
+                            max_isects=args.max_isects, split=not args.no_split)
     for f in frames[:args.warmup]:
         fr.render(sc["viewmats"], sc["Ks"], q_all[f], t_all[f])
         pipe.submit(sc["viewmats"], sc["Ks"], q_all[f], t_all[f])
@@ -487,6 +487,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--max-isects", type=int, default=24_000_000)
     ap.add_argument("--in-flight", type=int, default=4, help="frames in flight per GPU (streams + workspaces)")
+    ap.add_argument("--no-split", action="store_true",
+                    help="one stream per in-flight frame instead of (high-priority binning stream, compositing stream)")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-extras", action="store_true", help="skip stages / roofline / cpu_baseline (profiling runs)")
     args = ap.parse_args()

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RS_ABI_VERSION 6
+#define RS_ABI_VERSION 7
 
 /* gsplat/cuda/include/Common.h:46-51 (CameraModelType) */
 enum { RS_PINHOLE = 0, RS_ORTHO = 1, RS_FISHEYE = 2, RS_FTHETA = 3 };
@@ -381,7 +381,15 @@ typedef struct {
     int32_t *status;             /* device int32[4] out */
     /* optional exports of the sorted intersection data (`meta` of rendering.py:651-665); NULL to skip */
     int32_t *out_tile_offsets;   /* [C,tile_h,tile_w] */
+    /* which part of the frame this call enqueues: 0 = all of it; RS_FRAME_BIN = rigid + projection + binning only;
+     * RS_FRAME_COMPOSITE = compositing only (of a frame whose RS_FRAME_BIN part was enqueued with the same arguments).
+     * Lets a caller put the short latency-bound binning kernels of the next frame on a high-priority stream so that they
+     * are dispatched underneath the compositing of the previous one (FramePipeline). */
+    int32_t stages;
+    int32_t _pad;
 } rs_frame_args;
+#define RS_FRAME_BIN 1
+#define RS_FRAME_COMPOSITE 2
 uint64_t rs_frame_workspace_bytes(int32_t C, int32_t N, int32_t image_width, int32_t image_height, int32_t tile_size,
                                   int32_t channels, int64_t max_isects);
 int rs_render_frame(const rs_frame_args *a, rs_stream_t stream);
