@@ -41,6 +41,7 @@ class FrameRenderer:
         backgrounds: Optional[Tensor] = None,  # [C,D]
         camera_model: int = PINHOLE,
         sh_degree: Optional[int] = None,  # with it, `colors` holds SH coefficients [N,K,3] (main.py renders with degree 3)
+        rgb8: bool = False,  # also keep the frame as uint8 [C,H,W,3] (`render_rgb8`), quantised like save_rendered_image
     ):
         self.lib = _lib.load()
         dev = means.device
@@ -74,6 +75,11 @@ class FrameRenderer:
             self.render_colors = torch.empty(self.C, self.H, self.W, D, dtype=torch.float32, device=dev)
             self.render_alphas = torch.empty(self.C, self.H, self.W, 1, dtype=torch.float32, device=dev)
             self.status = torch.zeros(4, dtype=torch.int32, device=dev)
+            # the 8-bit frame the reference's loop writes to disk (main.py:140-171 -> torchvision save_image), produced by
+            # the compositing epilogue instead of four torch passes over the float image
+            self.render_rgb8 = torch.empty(self.C, self.H, self.W, 3, dtype=torch.uint8, device=dev) if rgb8 else None
+        if rgb8:
+            assert D >= 3, "rgb8 output needs at least 3 colour channels"
         self._args = None
 
     def _alloc(self, max_isects: int) -> None:
@@ -113,6 +119,7 @@ class FrameRenderer:
         a.render_colors = self.render_colors.data_ptr()
         a.render_alphas = self.render_alphas.data_ptr()
         a.status = self.status.data_ptr()
+        a.render_rgb8 = self.render_rgb8.data_ptr() if self.render_rgb8 is not None else None
         a.out_tile_offsets = None
         return a
 

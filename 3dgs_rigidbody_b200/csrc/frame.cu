@@ -218,6 +218,7 @@ static int render_frame_impl(const rs_frame_args *a, rs_stream_t stream, cudaEve
     r.flatten_ids = vals_sorted;
     r.render_colors = a->render_colors;
     r.render_alphas = a->render_alphas;
+    r.render_rgb8 = a->render_rgb8;
     r.last_ids = reinterpret_cast<int32_t *>(w + L.last_ids);
     r.records = p.records;
     r.records_ready = 1;

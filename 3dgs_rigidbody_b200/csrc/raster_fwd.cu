@@ -95,6 +95,12 @@ rs_raster_fwd_kernel(const rs_raster_fwd_args a, const int ch_off, const int ch_
         if (inside) {
             for (int k = 0; k < ch_cnt; ++k)
                 a.render_colors[pix_id * a.channels + ch_off + k] = bg == nullptr ? 0.0f : bg[k];
+            if (a.render_rgb8 != nullptr && ch_off == 0)
+                for (int k = 0; k < 3 && k < ch_cnt; ++k) {
+                    const float v = bg == nullptr ? 0.0f : bg[k];
+                    a.render_rgb8[pix_id * 3 + k] =
+                        (uint8_t)__float2uint_rz(fminf(fmaxf(__fadd_rn(__fmul_rn(v, 255.f), 0.5f), 0.f), 255.f));
+                }
         }
         return;
     }
@@ -316,6 +322,15 @@ rs_raster_fwd_kernel(const rs_raster_fwd_args a, const int ch_off, const int ch_
         for (int k = 0; k < CDIM; ++k)
             if (k < ch_cnt)
                 out[k] = bg == nullptr ? pix_out[k] : __fmaf_rn(T, bg[k], pix_out[k]);
+        if (a.render_rgb8 != nullptr && ch_off == 0) { // 8-bit copy of the frame, quantised like torchvision save_image
+            uint8_t *q = a.render_rgb8 + pix_id * 3;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (k < CDIM) {
+                    const float v = bg == nullptr ? pix_out[k] : __fmaf_rn(T, bg[k], pix_out[k]);
+                    q[k] = (uint8_t)__float2uint_rz(fminf(fmaxf(__fadd_rn(__fmul_rn(v, 255.f), 0.5f), 0.f), 255.f));
+                }
+        }
         a.last_ids[pix_id] = (int32_t)cur_idx;
     }
 }
@@ -397,6 +412,7 @@ extern "C" int rs_raster_fwd(const rs_raster_fwd_args *a, rs_stream_t stream) {
     RS_CHECK(a->colors && a->tile_offsets && a->render_colors && a->render_alphas && a->last_ids,
              "rs_raster_fwd: null pointer");
     RS_CHECK(a->n_isects == 0 || a->flatten_ids != nullptr, "rs_raster_fwd: null flatten_ids");
+    RS_CHECK(a->render_rgb8 == nullptr || a->channels >= 3, "rs_raster_fwd: render_rgb8 needs at least 3 channels");
     RS_CHECK(a->records != nullptr && (reinterpret_cast<uintptr_t>(a->records) & 15) == 0,
              "rs_raster_fwd: records scratch ([rows, 8] float, 16-byte aligned) is required");
     if (!a->records_ready) {

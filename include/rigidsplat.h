@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RS_ABI_VERSION 7
+#define RS_ABI_VERSION 8
 
 /* gsplat/cuda/include/Common.h:46-51 (CameraModelType) */
 enum { RS_PINHOLE = 0, RS_ORTHO = 1, RS_FISHEYE = 2, RS_FTHETA = 3 };
@@ -322,6 +322,10 @@ typedef struct {
     int32_t records_ready;
     int32_t _pad;
     int64_t n_rows;              /* rows of means2d / conics (I*N, or nnz when packed); needed when records_ready == 0 */
+    /* optional 8-bit frame [I,H,W,3] of the first three channels, quantised the way the reference's animation loop stores
+     * a frame (main.py:140-171 save_rendered_image -> torchvision save_image: x * 255 + 0.5, clamp to [0, 255], truncate);
+     * needs channels >= 3.  Written by the compositing epilogue next to the float image. */
+    uint8_t *render_rgb8;
 } rs_raster_fwd_args;
 int rs_raster_fwd(const rs_raster_fwd_args *a, rs_stream_t stream);
 
@@ -387,6 +391,7 @@ typedef struct {
      * are dispatched underneath the compositing of the previous one (FramePipeline). */
     int32_t stages;
     int32_t _pad;
+    uint8_t *render_rgb8;        /* [C,H,W,3] out, optional: the frame as 8-bit RGB (see rs_raster_fwd_args.render_rgb8) */
 } rs_frame_args;
 #define RS_FRAME_BIN 1
 #define RS_FRAME_COMPOSITE 2

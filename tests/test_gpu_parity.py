@@ -542,3 +542,21 @@ def test_frame_renderer_sh_matches_rasterization(rs):
     want1, _, _ = rs.rasterization(t["means"], t["quats"], t["scales"], t["opacities"], coeffs, T(vm), T(Ks), W, H,
                                    sh_degree=1, packed=False, **rigid)
     assert float((img1 - want1).abs().max()) <= 1e-4
+
+
+def test_frame_renderer_rgb8_is_the_quantised_float_frame(rs):
+    """The 8-bit frame written by the compositing epilogue equals torchvision save_image's quantisation of the float frame
+    (what main.py:140-171 save_rendered_image stores): x * 255 + 0.5, clamp to [0, 255], truncate -- with a background."""
+    W, H, N = 333, 201, 20_000
+    s = synthetic_scene(31, N, K=3, s_max=0.15)
+    vm, Ks = pinhole_cameras(2, W, H)
+    t = {k: torch.from_numpy(v).to(DEV) for k, v in s.items()}
+    bg = torch.tensor([[0.2, 0.9, 1.3], [0.0, 0.5, 0.25]], device=DEV)
+    fr = rs.FrameRenderer(t["means"], t["quats"], t["scales"], t["opacities"], t["colors"] * 1.4, W, H,
+                          cluster_ids=t["cluster_ids"], body_centers=t["body_centers"], n_cameras=2, backgrounds=bg,
+                          rgb8=True)
+    img, _ = fr.render(torch.from_numpy(vm).to(DEV), torch.from_numpy(Ks).to(DEV), t["body_quats"], t["body_trans"])
+    want = img.mul(255).add_(0.5).clamp_(0, 255).to(torch.uint8)
+    assert fr.render_rgb8.dtype == torch.uint8 and fr.render_rgb8.shape == (2, H, W, 3)
+    assert torch.equal(fr.render_rgb8, want)
+    assert int(want.max()) == 255 and int(want.min()) < 64  # saturated and dark pixels are both present
