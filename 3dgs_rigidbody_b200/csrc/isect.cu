@@ -215,6 +215,10 @@ rs_isect_offsets_kernel(const KeyT *__restrict__ isect_ids, int64_t n_bound, con
             const int64_t idx = base + (int64_t)u * blockDim.x + threadIdx.x;
             if (idx >= n_isects)
                 continue;
+            // only the few thousand boundary elements do any index arithmetic; every other element is two compares
+            const bool boundary = idx > 0 && prev[u] != cur[u];
+            if (!(boundary || idx == 0 || idx == n_isects - 1))
+                continue;
             const int64_t id_curr = (cur[u] >> tile_n_bits) * n_tiles + (cur[u] & ((1ll << tile_n_bits) - 1));
             if (idx == 0) {
                 for (int64_t i = 0; i < id_curr + 1; ++i)
@@ -224,7 +228,7 @@ rs_isect_offsets_kernel(const KeyT *__restrict__ isect_ids, int64_t n_bound, con
                 for (int64_t i = id_curr + 1; i < (int64_t)I * n_tiles; ++i)
                     offsets[i] = (int32_t)n_isects;
             }
-            if (idx > 0 && prev[u] != cur[u]) {
+            if (boundary) {
                 const int64_t id_prev = (prev[u] >> tile_n_bits) * n_tiles + (prev[u] & ((1ll << tile_n_bits) - 1));
                 for (int64_t i = id_prev + 1; i < id_curr + 1; ++i)
                     offsets[i] = (int32_t)idx;
@@ -383,7 +387,7 @@ rs_bin_emit_kernel(const rs_isect_args a, const int32_t *__restrict__ elems, uin
     __shared__ BinEmitSmem sm;
     // digit histograms of the keys this CTA emits, for every pass of the tile sort that follows (saves that sort its own
     // read of all M keys)
-    const int sort_passes = (sort_bits + RADIX_BITS - 1) / RADIX_BITS;
+    const int sort_passes = sort_num_passes(sort_bits), sort_width = sort_digit_width(sort_bits);
     for (int i = threadIdx.x; i < sort_passes * RADIX; i += RS_ISECT_THREADS)
         sm.hist[i] = 0;
     const int64_t base = (int64_t)blockIdx.x * RS_ISECT_BLOCK;
@@ -509,8 +513,8 @@ rs_bin_emit_kernel(const rs_isect_args a, const int32_t *__restrict__ elems, uin
             const unsigned act = __ballot_sync(0xffffffffu, live);
             if (act != 0u) {
                 for (int p = 0; p < sort_passes; ++p) {
-                    const int bits = min(RADIX_BITS, sort_bits - p * RADIX_BITS);
-                    const uint32_t d = (key >> (p * RADIX_BITS)) & ((1u << bits) - 1u);
+                    const int bits = min(sort_width, sort_bits - p * sort_width);
+                    const uint32_t d = (key >> (p * sort_width)) & ((1u << bits) - 1u);
                     const uint32_t d0 = __shfl_sync(0xffffffffu, d, __ffs(act) - 1);
                     const unsigned same = __ballot_sync(0xffffffffu, live && d == d0);
                     if (same == act) { // a whole warp on one digit (the high tile bits): one add

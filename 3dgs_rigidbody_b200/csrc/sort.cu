@@ -74,6 +74,7 @@ sort_hist_kernel(const KeyT *__restrict__ keys, int64_t n_bound, const int32_t *
         h[p][threadIdx.x] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
+    const int width = sort_digit_width(end_bit - begin_bit);
     constexpr int UNROLL = 4; // independent loads in flight per thread
     for (int64_t base = (int64_t)blockIdx.x * (SORT_THREADS * UNROLL); base < n;
          base += (int64_t)gridDim.x * (SORT_THREADS * UNROLL)) {
@@ -89,8 +90,8 @@ sort_hist_kernel(const KeyT *__restrict__ keys, int64_t n_bound, const int32_t *
         for (int u = 0; u < UNROLL; ++u) {
             const unsigned act = __ballot_sync(0xffffffffu, valid[u]);
             for (int p = 0; p < passes; ++p) {
-                const int shift = begin_bit + p * RADIX_BITS;
-                const int bits = min(RADIX_BITS, end_bit - shift);
+                const int shift = begin_bit + p * width;
+                const int bits = min(width, end_bit - shift);
                 const uint32_t d = (uint32_t)(key[u] >> shift) & ((1u << bits) - 1u);
                 // nearly sorted inputs (tile ids in emission order) put a whole warp on one digit: one add for all
                 const uint32_t d0 = __shfl_sync(0xffffffffu, d, __ffs(act | 0x80000000u) - 1);
@@ -360,7 +361,8 @@ static int radix_sort_impl(int64_t n_bound, const int32_t *n_dev, int begin_bit,
         *passes_out = 0;
     if (n_bound <= 0 || end_bit <= begin_bit)
         return 0;
-    const int passes = (end_bit - begin_bit + RADIX_BITS - 1) / RADIX_BITS;
+    const int passes = sort_num_passes(end_bit - begin_bit);
+    const int width = sort_digit_width(end_bit - begin_bit);
     RS_CHECK(passes <= SORT_MAX_PASSES, "rs_radix_sort_pairs: too many key bits");
     RS_CHECK(keys_in && kbuf0 && vbuf0 && workspace && (passes < 2 || (kbuf1 && vbuf1)),
              "rs_radix_sort_pairs: null pointer");
@@ -389,8 +391,8 @@ static int radix_sort_impl(int64_t n_bound, const int32_t *n_dev, int begin_bit,
     const KeyT *kin = keys_in;
     const int32_t *vin = vals_in;
     for (int p = 0; p < passes; ++p) {
-        const int shift = begin_bit + p * RADIX_BITS;
-        const int bits = min(RADIX_BITS, end_bit - shift);
+        const int shift = begin_bit + p * width;
+        const int bits = min(width, end_bit - shift);
         const uint32_t mask = (1u << bits) - 1u;
         KeyT *kout = (p & 1) ? kbuf1 : kbuf0;
         int32_t *vout = (p & 1) ? vbuf1 : vbuf0;

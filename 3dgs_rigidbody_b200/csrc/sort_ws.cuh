@@ -15,3 +15,12 @@
 #define WS_HIST 0
 #define WS_TICKET (SORT_MAX_PASSES * RADIX)
 #define WS_LOOKBACK (WS_TICKET + 256)
+
+// Digit layout of a sort over key bits [begin_bit, end_bit): the fewest 8-bit-or-narrower passes, with the bits spread
+// EVENLY over them (14 bits -> 7 + 7, not 8 + 6; 32 -> 8 x 4).  Narrower digits in every pass mean fewer, longer runs per
+// 4096-pair tile when the re-ordered tile is written out, i.e. fuller sectors for the scattered stores.
+__host__ __device__ inline int sort_num_passes(int total_bits) { return (total_bits + RADIX_BITS - 1) / RADIX_BITS; }
+__host__ __device__ inline int sort_digit_width(int total_bits) {
+    const int passes = sort_num_passes(total_bits);
+    return passes > 0 ? (total_bits + passes - 1) / passes : RADIX_BITS;
+}
