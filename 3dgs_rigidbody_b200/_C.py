@@ -355,6 +355,8 @@ def projection_ewa_3dgs_packed_bwd(
             v_quats = out_like(quats)
             v_scales = out_like(scales)
         v_viewmats = torch.zeros_like(viewmats) if viewmats_requires_grad else None
+        if nnz == 0:  # no visible pair: every gradient is zero (the row pointers are empty)
+            return v_means, v_covars, v_quats, v_scales, v_viewmats
         a = _lib.rs_project_bwd_args()
         a.B, a.C, a.N = B, C, N
         a.image_width, a.image_height = int(image_width), int(image_height)

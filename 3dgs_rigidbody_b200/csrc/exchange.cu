@@ -248,13 +248,22 @@ __global__ void __launch_bounds__(256) rs_exchange_push_kernel(const rs_exchange
 
 // Holds the stream until the rows of every source have landed; then totals[0] = rows received by this rank,
 // totals[1] = the largest row count any rank receives (what `capacity` must hold; identical on every rank),
-// totals[2] = error code of this frame (0 ok, 1 timeout, 2 capacity).
+// totals[2] = error code of this frame (0 ok, 1 timeout, 2 capacity), totals[3] = flags still behind (diagnostics).
 __global__ void rs_exchange_wait_kernel(const rs_exchange_args a, long long *totals) {
     char *const *peers = (char *const *)a.peer_base;
     ExchangeCtl *mine = (ExchangeCtl *)peers[a.rank];
     const unsigned int par = a.epoch & 1u;
     const bool ok = wait_flags(mine->data_flag, a.world, a.epoch);
     if (threadIdx.x == 0) {
+        // diagnostics for a timed-out frame: which sources' flags are behind (bit s = data flag, bit 16 + s = count flag)
+        long long behind = 0;
+        for (int s = 0; s < a.world; ++s) {
+            if ((int)(ld_sys(&mine->data_flag[s]) - a.epoch) < 0)
+                behind |= 1ll << s;
+            if ((int)(ld_sys(&mine->cnt_flag[par][s]) - a.epoch) < 0)
+                behind |= 1ll << (16 + s);
+        }
+        totals[3] = behind;
         long long worst = 0, got = 0;
         for (int d = 0; d < a.world; ++d) {
             long long t = 0;
@@ -287,8 +296,9 @@ static int exchange_check(const rs_exchange_args *a, const char *who) {
 extern "C" int rs_exchange_push(const rs_exchange_args *a, rs_stream_t stream) {
     if (int rc = exchange_check(a, "rs_exchange_push"))
         return rc;
-    RS_CHECK(a->indptr && a->camera_ids && a->gaussian_ids && a->radii && a->means2d && a->depths && a->conics &&
-                 a->opacities && a->colors,
+    RS_CHECK(a->indptr != nullptr && a->nnz >= 0, "rs_exchange_push: indptr / nnz missing");
+    RS_CHECK(a->nnz == 0 || (a->camera_ids && a->gaussian_ids && a->radii && a->means2d && a->depths && a->conics &&
+                             a->opacities && a->colors),
              "rs_exchange_push: null row pointer");
     ExchangeLayout lay;
     uint64_t off[RS_EXCHANGE_COLUMNS + 1];

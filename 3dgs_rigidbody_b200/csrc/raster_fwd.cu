@@ -395,8 +395,8 @@ int rs_check_raster_args(const rs_raster_fwd_args *a, const char *who) {
 }
 
 int rs_raster_pack_records(const rs_raster_fwd_args &a, cudaStream_t s) {
-    RS_CHECK(a.means2d && a.conics && a.opacities && a.records, "rs_raster pack: null pointer");
     RS_CHECK(a.n_rows > 0 || a.n_isects == 0, "rs_raster pack: n_rows required to pack records");
+    RS_CHECK(a.n_rows == 0 || (a.means2d && a.conics && a.opacities && a.records), "rs_raster pack: null pointer");
     if (a.n_rows > 0) {
         rs_raster_pack_kernel<<<rs_cdiv(a.n_rows, 256), 256, 0, s>>>(a, a.n_rows);
         RS_LAUNCH_CHECK("rs_raster_pack_kernel");
@@ -409,13 +409,16 @@ extern "C" int rs_raster_fwd(const rs_raster_fwd_args *a, rs_stream_t stream) {
         return e;
     if (a->I == 0)
         return 0;
-    RS_CHECK(a->colors && a->tile_offsets && a->render_colors && a->render_alphas && a->last_ids,
+    // no projected splat at all (zero packed rows: every Gaussian culled): the kernel only writes backgrounds, and the
+    // per-splat arrays may legitimately be empty (NULL)
+    const bool no_rows = a->n_isects == 0 && a->n_isects_dev == nullptr;
+    RS_CHECK((a->colors || no_rows) && a->tile_offsets && a->render_colors && a->render_alphas && a->last_ids,
              "rs_raster_fwd: null pointer");
     RS_CHECK(a->n_isects == 0 || a->flatten_ids != nullptr, "rs_raster_fwd: null flatten_ids");
     RS_CHECK(a->render_rgb8 == nullptr || a->channels >= 3, "rs_raster_fwd: render_rgb8 needs at least 3 channels");
-    RS_CHECK(a->records != nullptr && (reinterpret_cast<uintptr_t>(a->records) & 15) == 0,
+    RS_CHECK((a->records != nullptr || no_rows) && (reinterpret_cast<uintptr_t>(a->records) & 15) == 0,
              "rs_raster_fwd: records scratch ([rows, 8] float, 16-byte aligned) is required");
-    if (!a->records_ready) {
+    if (!a->records_ready && !no_rows) {
         if (int e = rs_raster_pack_records(*a, (cudaStream_t)stream))
             return e;
     }

@@ -152,8 +152,10 @@ class _PeerBuffers:
             _lib.check(lib.rs_peer_alloc(self.offsets[-1], ctypes.byref(own)))
             handle = ctypes.create_string_buffer(64)
             _lib.check(lib.rs_peer_export(own, handle))
-            handles: List[Optional[bytes]] = [None] * world
-            dist.all_gather_object(handles, handle.raw, group=group)
+            cards: List[Optional[Tuple[bytes, int, int]]] = [None] * world
+            dist.all_gather_object(cards, (handle.raw, capacity, channels), group=group)
+            # the layout of the arrays follows from (capacity, channels): it must be the same on every rank
+            assert all(c[1] == capacity and c[2] == channels for c in cards), f"peer buffers disagree: {[c[1:] for c in cards]}"
             self.own = own.value
             self.mapped: List[int] = []
             for s in range(world):
@@ -161,7 +163,7 @@ class _PeerBuffers:
                     self.mapped.append(self.own)
                     continue
                 p = ctypes.c_void_p()
-                _lib.check(lib.rs_peer_open(handles[s], ctypes.byref(p)))
+                _lib.check(lib.rs_peer_open(cards[s][0], ctypes.byref(p)))
                 self.mapped.append(p.value)
             self.table = torch.tensor(self.mapped, dtype=torch.int64, device=device)
             self.rank = rank
@@ -172,10 +174,11 @@ class _PeerBuffers:
             return torch.empty((0,) + tail, dtype=dtype, device=device)
         return torch.as_tensor(_DeviceArray(self.own + self.offsets[i], (rows,) + tail, typestr, self), device=device)
 
-    def release(self) -> None:
+    def release(self, group) -> None:
         for s, p in enumerate(self.mapped):
             if s != self.rank:
                 self.lib.rs_peer_close(ctypes.c_void_p(p))
+        dist.barrier(group=group)  # nobody still maps this rank's allocation when it is freed
         self.lib.rs_peer_free(ctypes.c_void_p(self.own))
         self.mapped = []
 
@@ -205,13 +208,13 @@ class PeerSplatExchange:
         assert self.world <= 16, "PeerSplatExchange: at most 16 ranks (one NVLink domain)"
         self.epoch = 0
         self.buffers: Optional[_PeerBuffers] = None
-        self.totals = torch.zeros(3, dtype=torch.int64, device=device)
+        self.totals = torch.zeros(4, dtype=torch.int64, device=device)
 
     def _regrow(self, capacity: int) -> None:
         torch.cuda.synchronize(self.device)
         dist.barrier(group=self.group)  # every rank's wait kernel has finished, so nobody still writes the old arrays
         if self.buffers is not None:
-            self.buffers.release()
+            self.buffers.release(self.group)
         self.buffers = _PeerBuffers(self.lib, self.group, self.device, capacity, self.channels)
 
     def exchange(self, cameras_per_rank: int, indptr: Tensor, camera_ids: Tensor, gaussian_ids: Tensor, radii: Tensor,
@@ -220,7 +223,12 @@ class PeerSplatExchange:
         """-> (radii, means2d, depths, conics, opacities, colors, camera_ids (local), gaussian_ids (global)) of the rows
         this rank composites, ordered (source rank, camera, Gaussian)."""
         if self.buffers is None:
-            self._regrow(self.initial_capacity or max(int(camera_ids.shape[0]), 1024))
+            # first call: every rank must size its arrays identically (the layout follows from the capacity), so start
+            # from the largest row count any rank holds; the exchange regrows on demand from then on
+            cap = torch.tensor([self.initial_capacity or max(int(camera_ids.shape[0]), 1024)], dtype=torch.int64,
+                               device=self.device)
+            dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=self.group)
+            self._regrow(int(cap.item()))
         stream = torch.cuda.current_stream(self.device).cuda_stream
         keep = [t.contiguous() for t in (indptr, camera_ids, gaussian_ids, radii, means2d, depths, conics, opacities, colors)]
         comp = compensations.contiguous() if compensations is not None else None
@@ -235,12 +243,15 @@ class PeerSplatExchange:
              a.colors) = [t.data_ptr() for t in keep]
             a.compensations = comp.data_ptr() if comp is not None else None
             a.gaussian_base = gaussian_base
+            a.nnz = int(camera_ids.shape[0])
             with torch.cuda.device(self.device):
                 _lib.check(self.lib.rs_exchange_push(ctypes.byref(a), stream))
                 _lib.check(self.lib.rs_exchange_wait(ctypes.byref(a), self.totals.data_ptr(), stream))
-            got, worst, err = self.totals.tolist()  # the one host sync of the exchange (sizes of the returned views)
+            got, worst, err, behind = self.totals.tolist()  # the one host sync of the exchange (sizes of the views)
             if err == 1:
-                raise RuntimeError("PeerSplatExchange: a peer did not arrive within the spin limit")
+                raise RuntimeError(f"PeerSplatExchange rank {self.rank} epoch {self.epoch}: a peer did not arrive within "
+                                   f"the spin limit (data flags behind: {behind & 0xffff:#x}, count flags behind: "
+                                   f"{behind >> 16:#x})")
             if err == 0:
                 break
             self._regrow(int(worst * 1.25) + 1024)  # identical decision on every rank: `worst` comes from the full matrix

@@ -176,6 +176,9 @@ def rasterize_to_pixels(
     image_dims = means2d.shape[:-2]
     channels = colors.shape[-1]
     if packed:
+        # the reference takes image_dims from means2d here too, i.e. () for packed rows, and then rejects every
+        # [..., C, channels] background (_wrapper.py:582, 598-599); the image dims of packed rows are those of the offsets
+        image_dims = isect_offsets.shape[:-2]
         nnz = means2d.size(0)
         assert means2d.shape == (nnz, 2), means2d.shape
         assert conics.shape == (nnz, 3), conics.shape

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RS_ABI_VERSION 8
+#define RS_ABI_VERSION 9
 
 /* gsplat/cuda/include/Common.h:46-51 (CameraModelType) */
 enum { RS_PINHOLE = 0, RS_ORTHO = 1, RS_FISHEYE = 2, RS_FTHETA = 3 };
@@ -203,12 +203,14 @@ typedef struct {
     const float *opacities;
     const float *colors;
     int64_t gaussian_base;       /* global index of this rank's first Gaussian */
+    int64_t nnz;                 /* rows this rank holds (= indptr[last]); with 0 the row pointers may be NULL */
 } rs_exchange_args;
 /* publish counts, place, store rows into the peers, raise the data flags (one kernel) */
 int rs_exchange_push(const rs_exchange_args *a, rs_stream_t stream);
-/* hold `stream` until every source's rows of this epoch have landed; totals_dev (device, int64[3]) = {rows received,
+/* hold `stream` until every source's rows of this epoch have landed; totals_dev (device, int64[4]) = {rows received,
  * largest row count any rank receives (capacity needed, identical on all ranks), error: 0 ok | 1 timeout | 2 capacity
- * exceeded -- nothing was written for the overfull destination} */
+ * exceeded -- nothing was written for the overfull destination, diagnostics: bit s = source s's data flag is behind,
+ * bit 16 + s = its count flag is behind} */
 int rs_exchange_wait(const rs_exchange_args *a, int64_t *totals_dev, rs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -26,7 +26,7 @@ def test_struct_layouts_match(rs):
     for which, st in enumerate(order):
         assert lib.rs_sizeof_args(which) == ctypes.sizeof(st), st.__name__
     assert lib.rs_sizeof_args(99) == 0
-    assert lib.rs_abi_version() == 8
+    assert lib.rs_abi_version() == 9
 
 
 def test_host_only_entry_points(rs):

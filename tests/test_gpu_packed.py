@@ -227,3 +227,24 @@ def test_rasterization_packed_equals_unpacked(rs, sparse_grad):
     assert torch.equal(i0, i1) and torch.equal(a0, a1)
     for x, y in zip(g0, g1):
         assert rel_err(y, x) < 2e-3
+
+
+@pytest.mark.parametrize("packed", [False, True])
+def test_rasterization_with_no_visible_gaussian(rs, packed):
+    """A camera that sees nothing (every Gaussian behind it): zero packed rows / zero intersections all the way through
+    projection, binning and compositing, forward and backward -> background-only image, zero alpha, zero gradients."""
+    N, W, H = 5_000, 96, 64
+    s = synthetic_scene(2, N, s_max=0.1)
+    vm, Ks = pinhole_cameras(2, W, H)
+    means = (T(s["means"]) - torch.tensor([0.0, 0.0, 100.0], device=DEV)).requires_grad_()
+    colors = T(s["colors"]).requires_grad_()
+    bg = torch.tensor([[0.1, 0.2, 0.3], [0.4, 0.5, 0.6]], device=DEV)
+    img, alpha, meta = rs.rasterization(means, T(s["quats"]), T(s["scales"]), T(s["opacities"]), colors, T(vm), T(Ks), W, H,
+                                        packed=packed, backgrounds=bg)
+    assert meta["flatten_ids"].numel() == 0 and int(meta["isect_offsets"].abs().max()) == 0
+    assert float(alpha.abs().max()) == 0.0
+    assert torch.equal(img, bg[:, None, None, :].expand(2, H, W, 3))
+    if packed:
+        assert meta["gaussian_ids"].numel() == 0 and meta["means2d"].shape == (0, 2)
+    img.sum().backward()
+    assert float(means.grad.abs().max()) == 0.0 and float(colors.grad.abs().max()) == 0.0
