@@ -302,11 +302,13 @@ def stage_breakdown(fr, sc, q_all, t_all, frames, peak_gbs, peak_src, n_tiles):
     roofline = {
         "bound": "hbm", "kernel": "rs_raster_fwd_kernel (compositing, 1 launch/frame: the largest share of the step)",
         "achieved": round(achieved, 1), "peak": peak_gbs, "unit": "GB/s", "frac": round(achieved / peak_gbs, 4),
-        "traffic": 70.46e6, "traffic_source": "ncu --set full r01 (profiles/r01c_kernels_ncu_full.txt): dram read+write per launch",
+        "traffic": 61.26e6, "traffic_source": "ncu --set full r01 (profiles/r01_frame_kernels_ncu_full.txt): dram read 48.80 MB + write 12.46 MB per launch",
         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg["composite"], "ms_per_launch": round(float(mean[2]), 4),
         "frames_timed": int(len(frames)),
-        "note": "this kernel is bound by SM issue (FP32 FMA + MUFU.EX2 + LDS), not by HBM: see profiles/ for issue-slot "
-                "utilisation; HBM-bound stages are in `stages`",
+        "note": "this kernel is bound by SM issue (FP32 FMA + MUFU.EX2 + LDS), not by HBM: 66 % issue-slot utilisation, "
+                "1.09e8 warp instructions per launch, 4 % DRAM throughput (profiles/r01_frame_kernels_ncu_full.txt); the gathers "
+                "hit in L2, so DRAM traffic is far BELOW the algorithmic bytes; the other stages are in `stages`",
+        "issue_slot_utilisation": 0.662,
     }
     return stages, roofline, float(mean[3]), M
 
