@@ -10,12 +10,22 @@ Public surface (mirrors the reference):
     fully_fused_projection, isect_tiles, isect_offset_encode, rasterize_to_pixels   gsplat/cuda/_wrapper.py
     _C                                 stand-in for the pybind module gsplat/cuda/ext.cpp (same names / positional args)
     RigidPoses, FrameRenderer          rigid-pose table; sync-free fused per-frame renderer (animation loop)
+    cgc_contrastive_clustering_loss    examples/utils.py:828-904 (identity-feature training step)
+    load_cluster_groups, body_properties, PoseStream   clustering / physics data contract (rigid.py)
 """
 from . import _C  # noqa: F401
 from ._C import RigidPoses, RigidSplatError  # noqa: F401
 from .animation import FramePipeline, FrameRenderer  # noqa: F401
 from .rendering import rasterization  # noqa: F401
-from .rigid import body_centers, cluster_ids_from_groups, make_rigid  # noqa: F401
+from .identity import cgc_contrastive_clustering_loss, cluster_tables  # noqa: F401
+from .rigid import (  # noqa: F401
+    PoseStream,
+    body_centers,
+    body_properties,
+    cluster_ids_from_groups,
+    load_cluster_groups,
+    make_rigid,
+)
 from .sh import spherical_harmonics  # noqa: F401
 from .wrapper import (  # noqa: F401
     fully_fused_projection,

@@ -46,6 +46,8 @@ extern "C" uint64_t rs_sizeof_args(int which) {
         return sizeof(rs_project_packed_fwd_args);
     case 11:
         return sizeof(rs_exchange_args);
+    case 12:
+        return sizeof(rs_cgc_args);
     default:
         return 0;
     }

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define RS_ABI_VERSION 9
+#define RS_ABI_VERSION 10
 
 /* gsplat/cuda/include/Common.h:46-51 (CameraModelType) */
 enum { RS_PINHOLE = 0, RS_ORTHO = 1, RS_FISHEYE = 2, RS_FTHETA = 3 };
@@ -363,6 +363,37 @@ typedef struct {
 } rs_sh_args;
 int rs_sh_fwd(const rs_sh_args *a, rs_stream_t stream);
 int rs_sh_bwd(const rs_sh_args *a, rs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Contrastive clustering loss of the identity-feature training step (the consumer of the c3 compositing pass).
+ * rs_cgc_fwd / rs_cgc_bwd replace `cgc_contrastive_clustering_loss` (examples/utils.py:828-904, called at
+ * examples/simple_trainer.py:945-975 on the rendered [H,W,D] feature map) and its autograd: three passes over the
+ * feature map forward, one more backward, instead of ~25 torch kernels each way.  The host derives, from the instance mask
+ * alone, for every pixel its `member` cluster (index among the K valid foreground clusters, -1 otherwise) and its `target`
+ * (same, except that -- a quirk of the reference reproduced on purpose, utils.py:878-883 -- background pixels are active
+ * with the LAST foreground cluster as target when that cluster is valid), plus the per-cluster pixel counts.
+ * ------------------------------------------------------------------------------------------------------------ */
+#define RS_CGC_MAX_DIM 32
+#define RS_CGC_MAX_CLUSTERS 128
+typedef struct {
+    int64_t P;                   /* pixels */
+    int64_t A;                   /* active pixels (target >= 0), >= 1 */
+    int32_t D;                   /* feature channels, 1..RS_CGC_MAX_DIM */
+    int32_t K;                   /* valid clusters, 2..RS_CGC_MAX_CLUSTERS */
+    float eps;                   /* floor of the temperatures (reference default 1e-6) */
+    int32_t accumulate_grad;     /* rs_cgc_fwd: also accumulate what rs_cgc_bwd needs */
+    const float *features;       /* [P,D] rendered feature map (un-normalised) */
+    const int32_t *target;       /* [P] */
+    const int32_t *member;       /* [P] */
+    const float *n_member;       /* [K] member pixels per cluster (all >= min_cluster_size) */
+    const float *n_active;       /* [K] active pixels per target */
+    float *ws;                   /* rs_cgc_workspace_floats(K, D) floats; ws[last] = the loss after rs_cgc_fwd */
+    const float *grad_loss;      /* [1] device, optional upstream gradient (default 1) */
+    float *v_features;           /* [P,D] out (rs_cgc_bwd) */
+} rs_cgc_args;
+uint64_t rs_cgc_workspace_floats(int32_t K, int32_t D);
+int rs_cgc_fwd(const rs_cgc_args *a, rs_stream_t stream);
+int rs_cgc_bwd(const rs_cgc_args *a, rs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * rs_render_frame: the whole per-frame hot path in one call with NO host synchronisation -- what the commented-out

@@ -22,11 +22,11 @@ def test_struct_layouts_match(rs):
     lib = _lib.load()
     order = [_lib.rs_project_fwd_args, _lib.rs_project_bwd_args, _lib.rs_isect_args, _lib.rs_sort_args,
              _lib.rs_raster_fwd_args, _lib.rs_raster_bwd_args, _lib.rs_frame_args, _lib.rs_rigid_t,
-             _lib.rs_isect_sorted_args, _lib.rs_sh_args, _lib.rs_project_packed_fwd_args, _lib.rs_exchange_args]
+             _lib.rs_isect_sorted_args, _lib.rs_sh_args, _lib.rs_project_packed_fwd_args, _lib.rs_exchange_args, _lib.rs_cgc_args]
     for which, st in enumerate(order):
         assert lib.rs_sizeof_args(which) == ctypes.sizeof(st), st.__name__
     assert lib.rs_sizeof_args(99) == 0
-    assert lib.rs_abi_version() == 9
+    assert lib.rs_abi_version() == 10
 
 
 def test_host_only_entry_points(rs):
