@@ -18,6 +18,7 @@ from ._C import RigidPoses, RigidSplatError  # noqa: F401
 from .animation import FramePipeline, FrameRenderer  # noqa: F401
 from .rendering import rasterization  # noqa: F401
 from .identity import cgc_contrastive_clustering_loss, cluster_tables  # noqa: F401
+from .io import load_ply  # noqa: F401
 from .rigid import (  # noqa: F401
     PoseStream,
     body_centers,
