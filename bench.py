@@ -313,6 +313,63 @@ def stage_breakdown(fr, sc, q_all, t_all, frames, peak_gbs, peak_src, n_tiles):
     return stages, roofline, float(mean[3]), M
 
 
+def other_configs(rs, sc, q_all, t_all, steps=10):
+    """Extra information next to the c2 headline (not the metric): the same scene through the drop-in `rasterization()` call
+    (operator path, with the host reads the reference API implies), and BASELINE configs[2] (c3): 16 identity-feature
+    channels, forward + backward, plus the contrastive clustering loss on the rendered map.  CUDA events, ms per step."""
+    import torch
+
+    dev = sc["means"].device
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return round(e0.elapsed_time(e1) / steps, 4)
+
+    rigid = lambda f: dict(cluster_ids=sc["cluster_ids"], body_quats=q_all[f], body_trans=t_all[f],
+                           body_centers=sc["body_centers"])
+    base = (sc["means"], sc["quats"], sc["scales"], sc["opacities"])
+    out = {}
+    with torch.no_grad():
+        out["c2_rasterization_api_ms"] = timed(lambda i=0: rs.rasterization(
+            *base, sc["colors"], sc["viewmats"], sc["Ks"], WIDTH, HEIGHT, packed=False, **rigid(60 + i)))
+        out["c2_rasterization_api_packed_ms"] = timed(lambda i=0: rs.rasterization(
+            *base, sc["colors"], sc["viewmats"], sc["Ks"], WIDTH, HEIGHT, packed=True, **rigid(60 + i)))
+    g = torch.Generator(device=dev).manual_seed(42)
+    feats = torch.randn(sc["means"].shape[0], 16, device=dev, generator=g).requires_grad_()
+    w = torch.rand(1, HEIGHT, WIDTH, 16, device=dev, generator=g)
+    leaves = [t.clone().requires_grad_() for t in base]
+
+    def c3_step(i=0):
+        for t in leaves + [feats]:
+            t.grad = None
+        img, _, _ = rs.rasterization(*leaves, feats, sc["viewmats"], sc["Ks"], WIDTH, HEIGHT, packed=False, **rigid(60 + i))
+        (img * w).sum().backward()
+
+    out["c3_fwd_bwd_16ch_ms"] = timed(c3_step)
+    # instance mask: one box per domino in screen space is not available here; a 6 x 4 grid of instances stands in
+    mask = torch.zeros(HEIGHT, WIDTH, dtype=torch.long, device=dev)
+    for a in range(4):
+        for b in range(6):
+            mask[20 + a * 260:20 + a * 260 + 240, 20 + b * 315:20 + b * 315 + 290] = 1 + a * 6 + b
+    tables = rs.cluster_tables(mask, 30)
+    fmap = torch.randn(HEIGHT, WIDTH, 16, device=dev, generator=g).requires_grad_()
+
+    def cgc_step(i=0):
+        fmap.grad = None
+        rs.cgc_contrastive_clustering_loss(fmap, mask, tables=tables).backward()
+
+    out["c3_contrastive_loss_fwd_bwd_ms"] = timed(cgc_step)
+    return out
+
+
 def ours_arm(args):
     import torch
 
@@ -485,6 +542,11 @@ def ours_arm(args):
         line["config"]["frame_ms_with_stage_events"] = round(frame_ms, 4)
         torch.cuda.empty_cache()
         budget = args.cpu_budget
+        try:
+            line["other_configs"] = other_configs(rs, sc, q_all, t_all)
+        except Exception as e:  # extra information only: never let it take the headline line down
+            line["other_configs"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
         cpu_frames = [(60 + 37 * i) % N_FRAMES for i in range(64)]  # stops at the CPU budget below
         times, threads = run_cpu_port(sc_np, cpu_frames, budget_s=budget)
         cpu_fps = len(times) / sum(times)
