@@ -23,15 +23,29 @@
 #define CGC_THREADS 128
 #define CGC_TILE 128 // pixels per CTA iteration (one per thread)
 
-__device__ __forceinline__ float cgc_normalize(const float *x, int D, float *f) {
+// Per-pixel feature vectors live in registers: every loop over channels has the compile-time bound DM (16 or 32) and is
+// fully unrolled; channels beyond the runtime D hold zeros, so no guard is needed inside dot products.
+template <int DM> __device__ __forceinline__ float cgc_normalize(const float (&x)[DM], float (&f)[DM]) {
     float n2 = 0.f;
-    for (int d = 0; d < D; ++d)
+#pragma unroll
+    for (int d = 0; d < DM; ++d)
         n2 = fmaf(x[d], x[d], n2);
     const float nrm = fmaxf(sqrtf(n2), 1e-12f); // F.normalize: x / max(|x|, eps)
     const float inv = 1.f / nrm;
-    for (int d = 0; d < D; ++d)
+#pragma unroll
+    for (int d = 0; d < DM; ++d)
         f[d] = x[d] * inv;
     return nrm;
+}
+
+// f . c_k for a centroid row in shared memory (row pitch D)
+template <int DM> __device__ __forceinline__ float cgc_dot(const float (&f)[DM], const float *row, int D) {
+    float s = 0.f;
+#pragma unroll
+    for (int d = 0; d < DM; ++d)
+        if (d < D)
+            s = fmaf(f[d], row[d], s);
+    return s;
 }
 
 // workspace layout (floats): [S_member K*D | S_active K*D | U0 K*D | possum K | h K | loss 1]
@@ -64,39 +78,77 @@ __device__ __forceinline__ void cgc_phi(const rs_cgc_args &a, float *phi) {
         phi[k] = fmaxf(ws_possum(a)[k] / fmaxf(a.n_active[k], 1.f), a.eps);
 }
 
-__device__ __forceinline__ void cgc_load_pixel(const rs_cgc_args &a, int64_t p, float *x) {
+template <int DM> __device__ __forceinline__ void cgc_load_pixel(const rs_cgc_args &a, int64_t p, float (&x)[DM]) {
     const float *src = a.features + p * a.D;
     if ((a.D & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.features) & 15) == 0)) {
-        for (int d = 0; d < a.D; d += 4) {
-            const float4 q = *reinterpret_cast<const float4 *>(src + d);
+#pragma unroll
+        for (int d = 0; d < DM; d += 4) {
+            float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (d < a.D)
+                q = *reinterpret_cast<const float4 *>(src + d);
             x[d] = q.x, x[d + 1] = q.y, x[d + 2] = q.z, x[d + 3] = q.w;
         }
     } else {
-        for (int d = 0; d < a.D; ++d)
-            x[d] = src[d];
+#pragma unroll
+        for (int d = 0; d < DM; ++d)
+            x[d] = d < a.D ? src[d] : 0.f;
     }
 }
 
 // ---- pass 1: per-cluster sums of the normalised features (members and active pixels) ---------------------------------
-__global__ void __launch_bounds__(CGC_THREADS) rs_cgc_sums_kernel(const rs_cgc_args a) {
+template <int DM> __global__ void __launch_bounds__(CGC_THREADS) rs_cgc_sums_kernel(const rs_cgc_args a) {
     extern __shared__ float sm[];
     const int K = a.K, D = a.D;
     float *s_mem = sm, *s_act = sm + K * D;
     for (int i = threadIdx.x; i < 2 * K * D; i += blockDim.x)
         sm[i] = 0.f;
     __syncthreads();
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < a.P; p += (int64_t)gridDim.x * blockDim.x) {
-        const int t = a.target[p], m = a.member[p];
-        if (t < 0 && m < 0)
-            continue;
-        float x[RS_CGC_MAX_DIM], f[RS_CGC_MAX_DIM];
-        cgc_load_pixel(a, p, x);
-        cgc_normalize(x, D, f);
-        for (int d = 0; d < D; ++d) {
-            if (m >= 0)
-                atomicAdd(&s_mem[m * D + d], f[d]);
-            if (t >= 0)
-                atomicAdd(&s_act[t * D + d], f[d]);
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p0 = (int64_t)blockIdx.x * blockDim.x; p0 < a.P; p0 += stride) { // warp-uniform trip count
+        const int64_t p = p0 + threadIdx.x;
+        const int t = p < a.P ? a.target[p] : -1, m = p < a.P ? a.member[p] : -1;
+        float x[DM], f[DM];
+#pragma unroll
+        for (int d = 0; d < DM; ++d)
+            f[d] = 0.f;
+        if (t >= 0 || m >= 0) {
+            cgc_load_pixel<DM>(a, p, x);
+            cgc_normalize<DM>(x, f);
+        }
+        // instance masks are spatially coherent: most warps sit inside ONE cluster, and then 32 lanes would hammer the same
+        // D shared-memory addresses.  Uniform warps reduce with shuffles and issue one atomic per channel instead.
+        const int t0 = __shfl_sync(0xffffffffu, t, 0), m0 = __shfl_sync(0xffffffffu, m, 0);
+        if (__all_sync(0xffffffffu, t == t0 && m == m0)) {
+            if (t0 < 0 && m0 < 0)
+                continue;
+#pragma unroll
+            for (int d = 0; d < DM; ++d) {
+                float v = f[d];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                    v += __shfl_xor_sync(0xffffffffu, v, o);
+                f[d] = v;
+            }
+            if (lane == 0) {
+#pragma unroll
+                for (int d = 0; d < DM; ++d)
+                    if (d < D) {
+                        if (m0 >= 0)
+                            atomicAdd(&s_mem[m0 * D + d], f[d]);
+                        if (t0 >= 0)
+                            atomicAdd(&s_act[t0 * D + d], f[d]);
+                    }
+            }
+        } else {
+#pragma unroll
+            for (int d = 0; d < DM; ++d)
+                if (d < D) {
+                    if (m >= 0)
+                        atomicAdd(&s_mem[m * D + d], f[d]);
+                    if (t >= 0)
+                        atomicAdd(&s_act[t * D + d], f[d]);
+                }
         }
     }
     __syncthreads();
@@ -106,7 +158,7 @@ __global__ void __launch_bounds__(CGC_THREADS) rs_cgc_sums_kernel(const rs_cgc_a
 }
 
 // ---- pass 2: sum of the positive similarities per target (-> temperatures) ---------------------------------------------
-__global__ void __launch_bounds__(CGC_THREADS) rs_cgc_pos_kernel(const rs_cgc_args a) {
+template <int DM> __global__ void __launch_bounds__(CGC_THREADS) rs_cgc_pos_kernel(const rs_cgc_args a) {
     extern __shared__ float sm[];
     const int K = a.K, D = a.D;
     float *c = sm, *mn = c + K * D, *ps = mn + K;
@@ -114,17 +166,30 @@ __global__ void __launch_bounds__(CGC_THREADS) rs_cgc_pos_kernel(const rs_cgc_ar
     for (int k = threadIdx.x; k < K; k += blockDim.x)
         ps[k] = 0.f;
     __syncthreads();
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < a.P; p += (int64_t)gridDim.x * blockDim.x) {
-        const int t = a.target[p];
-        if (t < 0)
-            continue;
-        float x[RS_CGC_MAX_DIM], f[RS_CGC_MAX_DIM];
-        cgc_load_pixel(a, p, x);
-        cgc_normalize(x, D, f);
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p0 = (int64_t)blockIdx.x * blockDim.x; p0 < a.P; p0 += stride) {
+        const int64_t p = p0 + threadIdx.x;
+        const int t = p < a.P ? a.target[p] : -1;
         float s = 0.f;
-        for (int d = 0; d < D; ++d)
-            s = fmaf(f[d], c[t * D + d], s);
-        atomicAdd(&ps[t], s);
+        if (t >= 0) {
+            float x[DM], f[DM];
+            cgc_load_pixel<DM>(a, p, x);
+            cgc_normalize<DM>(x, f);
+            s = cgc_dot<DM>(f, c + t * D, D);
+        }
+        const int t0 = __shfl_sync(0xffffffffu, t, 0);
+        if (__all_sync(0xffffffffu, t == t0)) { // one cluster per warp: a shuffle reduction and a single atomic
+            if (t0 < 0)
+                continue;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0)
+                atomicAdd(&ps[t0], s);
+        } else if (t >= 0) {
+            atomicAdd(&ps[t], s);
+        }
     }
     __syncthreads();
     for (int k = threadIdx.x; k < K; k += blockDim.x)
@@ -133,7 +198,7 @@ __global__ void __launch_bounds__(CGC_THREADS) rs_cgc_pos_kernel(const rs_cgc_ar
 }
 
 // ---- pass 3: the loss; with accumulate_grad also U0 = sum_p g_p (x) f_p and h ------------------------------------------
-__global__ void __launch_bounds__(CGC_THREADS) rs_cgc_loss_kernel(const rs_cgc_args a) {
+template <int DM> __global__ void __launch_bounds__(CGC_THREADS) rs_cgc_loss_kernel(const rs_cgc_args a) {
     extern __shared__ float sm[];
     const int K = a.K, D = a.D;
     float *c = sm, *mn = c + K * D, *phi = mn + K, *hs = phi + K;
@@ -157,32 +222,23 @@ __global__ void __launch_bounds__(CGC_THREADS) rs_cgc_loss_kernel(const rs_cgc_a
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t p = tile * CGC_TILE + threadIdx.x;
         const int t = p < a.P ? a.target[p] : -1;
-        float f[RS_CGC_MAX_DIM];
+        float f[DM];
         if (t >= 0) {
-            float x[RS_CGC_MAX_DIM];
-            cgc_load_pixel(a, p, x);
-            cgc_normalize(x, D, f);
+            float x[DM];
+            cgc_load_pixel<DM>(a, p, x);
+            cgc_normalize<DM>(x, f);
             const float inv_tau = 1.f / phi[t];
             // logits and a max-subtracted logsumexp
             float mx = -3e38f;
             for (int k = 0; k < K; ++k) {
-                float s = 0.f;
-                for (int d = 0; d < D; ++d)
-                    s = fmaf(f[d], c[k * D + d], s);
+                const float s = cgc_dot<DM>(f, c + k * D, D);
                 if (bwd)
                     gt[threadIdx.x * (K + 1) + k] = s; // similarities, turned into g below
                 mx = fmaxf(mx, s * inv_tau);
             }
             float den = 0.f, st = 0.f;
             for (int k = 0; k < K; ++k) {
-                float s;
-                if (bwd) {
-                    s = gt[threadIdx.x * (K + 1) + k];
-                } else {
-                    s = 0.f;
-                    for (int d = 0; d < D; ++d)
-                        s = fmaf(f[d], c[k * D + d], s);
-                }
+                const float s = bwd ? gt[threadIdx.x * (K + 1) + k] : cgc_dot<DM>(f, c + k * D, D);
                 den += expf(s * inv_tau - mx);
                 if (k == t)
                     st = s;
@@ -190,16 +246,19 @@ __global__ void __launch_bounds__(CGC_THREADS) rs_cgc_loss_kernel(const rs_cgc_a
             loss_local += (logf(den) + mx - st * inv_tau) * inv_A;
             if (bwd) {
                 float gs = 0.f;
+                const float inv_den = 1.f / den;
                 for (int k = 0; k < K; ++k) {
                     const float s = gt[threadIdx.x * (K + 1) + k];
-                    const float q = expf(s * inv_tau - mx) / den;
+                    const float q = expf(s * inv_tau - mx) * inv_den;
                     const float g = (q - (k == t ? 1.f : 0.f)) * inv_tau * inv_A;
                     gt[threadIdx.x * (K + 1) + k] = g;
                     gs = fmaf(g, s, gs);
                 }
                 atomicAdd(&hs[t], -gs * inv_tau);
-                for (int d = 0; d < D; ++d)
-                    ft[threadIdx.x * (D + 1) + d] = f[d];
+#pragma unroll
+                for (int d = 0; d < DM; ++d)
+                    if (d < D)
+                        ft[threadIdx.x * (D + 1) + d] = f[d];
             }
         } else if (bwd) {
             for (int k = 0; k < K; ++k)
@@ -250,7 +309,7 @@ __global__ void __launch_bounds__(CGC_THREADS) rs_cgc_loss_kernel(const rs_cgc_a
 }
 
 // ---- pass 4: dL/dx per pixel ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CGC_THREADS) rs_cgc_grad_kernel(const rs_cgc_args a) {
+template <int DM> __global__ void __launch_bounds__(CGC_THREADS) rs_cgc_grad_kernel(const rs_cgc_args a) {
     extern __shared__ float sm[];
     const int K = a.K, D = a.D;
     float *c = sm, *mn = c + K * D, *phi = mn + K, *hk = phi + K, *v = hk + K;
@@ -286,46 +345,42 @@ __global__ void __launch_bounds__(CGC_THREADS) rs_cgc_grad_kernel(const rs_cgc_a
                 out[d] = 0.f;
             continue;
         }
-        float x[RS_CGC_MAX_DIM], f[RS_CGC_MAX_DIM], df[RS_CGC_MAX_DIM];
-        cgc_load_pixel(a, p, x);
-        const float nrm = cgc_normalize(x, D, f);
-        for (int d = 0; d < D; ++d)
-            df[d] = m >= 0 ? v[m * D + d] : 0.f;
+        float x[DM], f[DM], df[DM];
+        cgc_load_pixel<DM>(a, p, x);
+        const float nrm = cgc_normalize<DM>(x, f);
+#pragma unroll
+        for (int d = 0; d < DM; ++d)
+            df[d] = (m >= 0 && d < D) ? v[m * D + d] : 0.f;
         if (t >= 0) {
             const float inv_tau = 1.f / phi[t];
             float mx = -3e38f;
-            for (int k = 0; k < K; ++k) {
-                float s = 0.f;
-                for (int d = 0; d < D; ++d)
-                    s = fmaf(f[d], c[k * D + d], s);
-                mx = fmaxf(mx, s * inv_tau);
-            }
+            for (int k = 0; k < K; ++k)
+                mx = fmaxf(mx, cgc_dot<DM>(f, c + k * D, D) * inv_tau);
             float den = 0.f;
+            for (int k = 0; k < K; ++k)
+                den += expf(cgc_dot<DM>(f, c + k * D, D) * inv_tau - mx);
+            const float inv_den = 1.f / den;
             for (int k = 0; k < K; ++k) {
-                float s = 0.f;
-                for (int d = 0; d < D; ++d)
-                    s = fmaf(f[d], c[k * D + d], s);
-                den += expf(s * inv_tau - mx);
-            }
-            for (int k = 0; k < K; ++k) {
-                float s = 0.f;
-                for (int d = 0; d < D; ++d)
-                    s = fmaf(f[d], c[k * D + d], s);
-                const float q = expf(s * inv_tau - mx) / den;
+                const float q = expf(cgc_dot<DM>(f, c + k * D, D) * inv_tau - mx) * inv_den;
                 float G = (q - (k == t ? 1.f : 0.f)) * inv_tau * inv_A;
                 if (k == t)
                     G += hk[k];
-                for (int d = 0; d < D; ++d)
-                    df[d] = fmaf(G, c[k * D + d], df[d]);
+#pragma unroll
+                for (int d = 0; d < DM; ++d)
+                    if (d < D)
+                        df[d] = fmaf(G, c[k * D + d], df[d]);
             }
         }
         float dot = 0.f;
-        for (int d = 0; d < D; ++d)
+#pragma unroll
+        for (int d = 0; d < DM; ++d)
             dot = fmaf(df[d], f[d], dot);
         const float inv = up / nrm;
         const bool tiny = nrm <= 1e-12f; // below F.normalize's floor the norm is a constant
-        for (int d = 0; d < D; ++d)
-            out[d] = (tiny ? df[d] : df[d] - dot * f[d]) * inv;
+#pragma unroll
+        for (int d = 0; d < DM; ++d)
+            if (d < D)
+                out[d] = (tiny ? df[d] : df[d] - dot * f[d]) * inv;
     }
 }
 
@@ -356,23 +411,28 @@ template <typename Kern> static int cgc_launch(Kern kern, const rs_cgc_args *a, 
     return 0;
 }
 
+template <int DM> static int cgc_fwd_impl(const rs_cgc_args *a, cudaStream_t s) {
+    const size_t KD = (size_t)a->K * a->D;
+    if (int e = cgc_launch(rs_cgc_sums_kernel<DM>, a, 2 * KD * sizeof(float), cgc_grid(a->P), s, "rs_cgc_sums_kernel"))
+        return e;
+    if (int e = cgc_launch(rs_cgc_pos_kernel<DM>, a, (KD + 2 * a->K) * sizeof(float), cgc_grid(a->P), s, "rs_cgc_pos_kernel"))
+        return e;
+    size_t smem = (KD + 3 * a->K) * sizeof(float);
+    if (a->accumulate_grad)
+        smem += (size_t)CGC_TILE * (a->D + 1 + a->K + 1) * sizeof(float);
+    const int64_t tiles = (a->P + CGC_TILE - 1) / CGC_TILE;
+    const int64_t grid = tiles < (int64_t)rs_num_sms() * 4 ? tiles : (int64_t)rs_num_sms() * 4;
+    return cgc_launch(rs_cgc_loss_kernel<DM>, a, smem, (int)(grid < 1 ? 1 : grid), s, "rs_cgc_loss_kernel");
+}
+
 // forward: zeroes the workspace, then sums -> temperatures -> loss (ws[last] = loss); with accumulate_grad != 0 the loss pass
 // also leaves what rs_cgc_bwd needs
 extern "C" int rs_cgc_fwd(const rs_cgc_args *a, rs_stream_t stream) {
     if (int e = cgc_check(a, "rs_cgc_fwd"))
         return e;
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t KD = (size_t)a->K * a->D;
     RS_CUDA(cudaMemsetAsync(a->ws, 0, rs_cgc_workspace_floats(a->K, a->D) * sizeof(float), s));
-    if (int e = cgc_launch(rs_cgc_sums_kernel, a, 2 * KD * sizeof(float), cgc_grid(a->P), s, "rs_cgc_sums_kernel"))
-        return e;
-    if (int e = cgc_launch(rs_cgc_pos_kernel, a, (KD + 2 * a->K) * sizeof(float), cgc_grid(a->P), s, "rs_cgc_pos_kernel"))
-        return e;
-    size_t smem = (KD + 3 * a->K) * sizeof(float);
-    if (a->accumulate_grad)
-        smem += (size_t)CGC_TILE * (a->D + 1 + a->K + 1) * sizeof(float);
-    const int grid = (int)((rs_num_sms() * 2 < (a->P + CGC_TILE - 1) / CGC_TILE) ? rs_num_sms() * 2 : (a->P + CGC_TILE - 1) / CGC_TILE);
-    return cgc_launch(rs_cgc_loss_kernel, a, smem, grid < 1 ? 1 : grid, s, "rs_cgc_loss_kernel");
+    return a->D <= 16 ? cgc_fwd_impl<16>(a, s) : cgc_fwd_impl<32>(a, s);
 }
 
 // backward: v_features [P, D] = dL/dx * (*grad_loss), from the workspace of an rs_cgc_fwd run with accumulate_grad != 0
@@ -380,7 +440,9 @@ extern "C" int rs_cgc_bwd(const rs_cgc_args *a, rs_stream_t stream) {
     if (int e = cgc_check(a, "rs_cgc_bwd"))
         return e;
     RS_CHECK(a->v_features != nullptr, "rs_cgc_bwd: v_features is required");
-    const size_t KD = (size_t)a->K * a->D;
-    return cgc_launch(rs_cgc_grad_kernel, a, (2 * KD + 3 * a->K) * sizeof(float), cgc_grid(a->P), (cudaStream_t)stream,
-                      "rs_cgc_grad_kernel");
+    const size_t smem = (2 * (size_t)a->K * a->D + 3 * a->K) * sizeof(float);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (a->D <= 16)
+        return cgc_launch(rs_cgc_grad_kernel<16>, a, smem, cgc_grid(a->P), s, "rs_cgc_grad_kernel");
+    return cgc_launch(rs_cgc_grad_kernel<32>, a, smem, cgc_grid(a->P), s, "rs_cgc_grad_kernel");
 }
