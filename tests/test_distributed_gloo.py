@@ -21,23 +21,27 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _global_problem(world, n_per_rank, cams_per_rank, D, seed=0):
+def _global_problem(world, n_per_rank, cams_per_rank, D, seed=0, sparse=False):
     g = torch.Generator().manual_seed(seed)
     Ct, Nt = world * cams_per_rank, sum(n_per_rank)
+    radii = torch.randint(0, 30, (Ct, Nt, 2), generator=g, dtype=torch.int32)
+    if sparse:  # the last rank's Gaussians are visible nowhere (it packs zero rows) and its cameras see nothing at all
+        radii[:, Nt - n_per_rank[-1]:] = 0
+        radii[(world - 1) * cams_per_rank:] = 0
     return dict(
-        radii=torch.randint(0, 30, (Ct, Nt, 2), generator=g, dtype=torch.int32),
+        radii=radii,
         means2d=torch.randn(Ct, Nt, 2, generator=g), depths=torch.rand(Ct, Nt, generator=g) + 1,
         conics=torch.randn(Ct, Nt, 3, generator=g), opacities=torch.rand(Ct, Nt, generator=g),
         colors=torch.rand(Nt, D, generator=g))
 
 
-def _worker(rank, world, port, n_per_rank, cams, D, q):
+def _worker(rank, world, port, n_per_rank, cams, D, q, sparse=False):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         ex_mod = importlib.import_module("3dgs_rigidbody_b200.distributed")
-        G = _global_problem(world, n_per_rank, cams, D)
+        G = _global_problem(world, n_per_rank, cams, D, sparse=sparse)
         lo = sum(n_per_rank[:rank])
         hi = lo + n_per_rank[rank]
         ex = ex_mod.GaussianShardExchange(n_per_rank[rank], cams, torch.device("cpu"))
@@ -91,6 +95,8 @@ def _worker(rank, world, port, n_per_rank, cams, D, q):
         assert torch.equal(radii, G["radii"][gc, exp_g]) and torch.equal(means2d, G["means2d"][gc, exp_g])
         assert torch.equal(depths, G["depths"][gc, exp_g]) and torch.equal(conics, G["conics"][gc, exp_g])
         assert torch.equal(opac, G["opacities"][gc, exp_g]) and torch.equal(colors, G["colors"][exp_g])
+        if sparse:  # zero rows packed on the last rank, zero rows received by it: the edge that must not strand a rank
+            assert (cam_ids.numel() == 0) == (rank == world - 1) and (gid.numel() == 0) == (rank == world - 1)
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover
         import traceback
@@ -106,6 +112,22 @@ def test_gaussian_shard_exchange_world2_gloo(n_per_rank, cams, D):
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, n_per_rank, cams, D, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in results:
+        assert msg == "ok", f"rank {rank}:\n{msg}"
+
+
+def test_gaussian_shard_exchange_with_empty_ranks_gloo():
+    """Packed exchange when one rank has nothing to send and nothing to receive (its Gaussians are culled everywhere, its
+    cameras look away): sizes of zero must travel through the count exchange and both all-to-alls."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, (300, 200), 2, 3, q, True)) for r in range(2)]
     for p in procs:
         p.start()
     results = [q.get(timeout=240) for _ in procs]
