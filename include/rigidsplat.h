@@ -12,8 +12,10 @@
  *     `3dgs_rigidbody_b200/_C.py` does that with torch and passes the pointers here).
  *   - every function returns 0 on success, non-zero on failure; `rs_last_error()` then holds a message
  *     (thread-local).  Launch errors are checked (the reference does not check them at all).
- *   - nothing here synchronises the stream or the device, except rs_isect_count_total().
+ *   - nothing here synchronises the stream or the device, except rs_isect_count_total() and rs_peer_alloc().
  *   - optional pointers may be NULL where marked "optional".
+ *   - one process drives ONE device (the deployment model: one rank per GPU): kernel attributes such as the opt-in
+ *     shared-memory size are set once per process on the device that is current at the first call.
  */
 #ifndef RIGIDSPLAT_H_
 #define RIGIDSPLAT_H_
