@@ -221,6 +221,8 @@ def run_cpu_port(sc, frames, budget_s=None):
     from oracle import oracle
 
     oracle.build()
+    # all the host threads this process may use, whatever OMP_NUM_THREADS says (torchrun sets it to 1 for every rank)
+    oracle.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     q, t = domino_poses_np(sc["body_centers"].shape[0], frames, sc["body_centers"])
     times = []
     t_begin = time.perf_counter()
