@@ -1,13 +1,14 @@
 """Operator boundary: a stand-in for the reference's pybind module `_C` (gsplat/cuda/ext.cpp:6-104).
 
 Same function names and the same POSITIONAL signatures as the hot-path subset of `_C` (C++ declarations in
-gsplat/cuda/include/Ops.h:42-88, 186-204, 223-263), so `gsplat.cuda._backend._C` can be replaced by this module
+gsplat/cuda/include/Ops.h:42-168, 186-204, 223-263: fused and packed projection fwd/bwd, spherical harmonics, tile
+intersection + offsets, compositing fwd/bwd), so `gsplat.cuda._backend._C` can be replaced by this module
 (see INTEGRATION.md).  Each function validates its inputs like the reference host launchers (CHECK_INPUT ->
 RuntimeError), allocates the outputs with torch exactly where the reference does, and calls the hand-written sm_100a
 kernels through the C ABI (include/rigidsplat.h) on the current CUDA stream.  There is no CPU / eager fallback.
 
-Extension over the reference: `projection_ewa_3dgs_fused_fwd/bwd` take an optional trailing `rigid` argument
-(`RigidPoses`) that fuses main.py's apply_transform() into the projection.
+Extension over the reference: the projection operators (fused and packed, fwd and bwd) take an optional trailing `rigid`
+argument (`RigidPoses`) that fuses main.py's apply_transform() into the projection.
 """
 from __future__ import annotations
 
