@@ -3,7 +3,7 @@
 Same interface as the reference's `spherical_harmonics` (gsplat/cuda/_wrapper.py:151-181, autograd node :1799-1831):
 real SH up to degree 4 of the NORMALISED direction, coefficients [..., K, 3].  Forward and backward are CUDA kernels
 behind the C ABI (`rs_sh_fwd` / `rs_sh_bwd`, csrc/sh.cu) reached through `_C.spherical_harmonics_fwd/bwd`, like every
-other operator; CPU tensors (host-logic tests only) are evaluated by the torch restatement in torch_ref.py.
+other operator; CPU tensors are refused (RuntimeError), there is no CPU path.
 Masked-out entries return 0 (the reference leaves them uninitialised, SphericalHarmonics.cpp:29).
 """
 from typing import Optional
@@ -41,8 +41,6 @@ def spherical_harmonics(degrees_to_use: int, dirs: Tensor, coeffs: Tensor, masks
     if masks is not None:
         assert masks.shape == batch_dims, masks.shape
         masks = masks.contiguous()
-    if not dirs.is_cuda:  # host-logic tests on a CPU box; the product path is CUDA
-        from .torch_ref import spherical_harmonics_torch
-
-        return spherical_harmonics_torch(degrees_to_use, dirs, coeffs, masks)
+    if not (dirs.is_cuda and coeffs.is_cuda):
+        raise RuntimeError("spherical_harmonics: dirs and coeffs must be CUDA tensors (there is no CPU path)")
     return _SphericalHarmonics.apply(degrees_to_use, dirs.contiguous(), coeffs.contiguous(), masks)

@@ -328,9 +328,8 @@ def test_c4_scale_6m_gaussians_4k_two_cameras(rs, ref):
 @pytest.mark.parametrize("deg,K", [(0, 1), (1, 4), (2, 16), (3, 16), (4, 25)])
 def test_spherical_harmonics_fwd_bwd_vs_reference_cuda(rs, ref, deg, K):
     """rs_sh_fwd / rs_sh_bwd against the reference's spherical_harmonics_fwd / _bwd and against float64 torch autograd."""
-    import importlib
+    from oracle import sh_torch
 
-    tr = importlib.import_module("3dgs_rigidbody_b200.torch_ref")
     n = 20_000
     g = torch.Generator(device=DEV).manual_seed(deg)
     dirs = torch.randn(n, 3, device=DEV, generator=g) * 3.0
@@ -349,7 +348,7 @@ def test_spherical_harmonics_fwd_bwd_vs_reference_cuda(rs, ref, deg, K):
     # float64 autograd of the torch restatement
     d64 = dirs.double().requires_grad_(True)
     c64 = coeffs.double().requires_grad_(True)
-    out = tr.spherical_harmonics_torch(deg, d64, c64, masks)
+    out = sh_torch.spherical_harmonics_torch(deg, d64, c64, masks)
     assert float((out.detach() - got.double()).abs().max()) <= 2e-5
     out.backward(v_colors.double())
     assert float((c64.grad - vco.double()).abs().max()) <= 2e-5 * max(1.0, float(c64.grad.abs().max()))

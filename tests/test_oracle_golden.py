@@ -209,15 +209,19 @@ def test_compositing_backward_matches_autograd(orc):
 
 
 def test_sh_matches_reference(rs):
-    """Product-side torch SH (host logic, CPU-runnable) vs the reference's _spherical_harmonics."""
+    """The torch SH checker (oracle/sh_torch.py) vs the reference's _spherical_harmonics; the product refuses CPU tensors."""
     import torch
+
+    from oracle import sh_torch
 
     g = load_golden("spherical_harmonics.npz")
     dirs, coeffs = torch.from_numpy(g["dirs"]), torch.from_numpy(g["coeffs"])
     for deg in range(5):
-        got = rs.spherical_harmonics(deg, dirs, coeffs).numpy()
+        got = sh_torch.spherical_harmonics_torch(deg, dirs, coeffs).numpy()
         np.testing.assert_allclose(got, g[f"deg{deg}"], rtol=1e-4, atol=2e-5)
     masks = torch.zeros(dirs.shape[0], dtype=torch.bool)
     masks[::2] = True
-    got = rs.spherical_harmonics(3, dirs, coeffs, masks=masks)
+    got = sh_torch.spherical_harmonics_torch(3, dirs, coeffs, masks=masks)
     assert not got[1::2].any() and got[::2].abs().sum() > 0
+    with pytest.raises(RuntimeError, match="CUDA"):  # no CPU path behind the public operator
+        rs.spherical_harmonics(3, dirs, coeffs)
