@@ -105,7 +105,11 @@ def projection_ewa_3dgs_fused_fwd(
     camera_model: int,
     rigid: Optional[RigidPoses] = None,
     _tile_count: Optional[Tuple[int, int, int]] = None,
+    _sh: Optional[Tuple[Tensor, int]] = None,
 ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Optional[Tensor]]:
+    """With `_sh = (coeffs [..., N, K, 3], degree)` (an extension: not part of the reference's operator) the view-dependent
+    colours max(SH(degree, moved mean - camera origin) + 0.5, 0) of the visible rows are evaluated by the same kernel and
+    returned as a sixth output [..., C, N, 3] (rendering.py:491-525 without the dirs / inverse / colours passes)."""
     lib = _lib.load()
     _check(means, "means", torch.float32)
     _check(viewmats, "viewmats", torch.float32)
@@ -145,7 +149,16 @@ def projection_ewa_3dgs_fused_fwd(
             rigid.fill(a.rigid)
         a.radii, a.means2d, a.depths, a.conics = _ptr(radii), _ptr(means2d), _ptr(depths), _ptr(conics)
         a.compensations = _ptr(compensations)
+        sh_colors = None
+        if _sh is not None:
+            coeffs, degree = _sh
+            _check(coeffs, "sh coefficients", torch.float32, tuple(batch_dims) + (N, coeffs.shape[-2], 3), dev)
+            sh_colors = torch.zeros(batch_dims + (C, N, 3), dtype=torch.float32, device=dev)
+            a.sh_coeffs, a.sh_colors = _ptr(coeffs), _ptr(sh_colors)
+            a.sh_degree, a.sh_K = int(degree), coeffs.shape[-2]
         _lib.check(lib.rs_project_fwd(ctypes.byref(a), _stream()))
+    if _sh is not None:
+        return radii, means2d, depths, conics, compensations, sh_colors
     return radii, means2d, depths, conics, compensations
 
 
@@ -233,6 +246,7 @@ def projection_ewa_3dgs_packed_fwd(
     camera_model: int,
     rigid: Optional[RigidPoses] = None,
     _capacity: Optional[int] = None,
+    _sh: Optional[Tuple[Tensor, int]] = None,
 ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Optional[Tensor]]:
     """-> (indptr i32 [B*C+1], batch_ids, camera_ids, gaussian_ids i64 [nnz], radii i32 [nnz,2], means2d [nnz,2],
     depths [nnz], conics [nnz,3], compensations [nnz] or None), rows in (batch, camera, gaussian) order.
@@ -271,6 +285,7 @@ def projection_ewa_3dgs_packed_fwd(
             depths = torch.empty((cap,), dtype=torch.float32, device=dev)
             conics = torch.empty((cap, 3), dtype=torch.float32, device=dev)
             compensations = torch.zeros((cap,), dtype=torch.float32, device=dev) if calc_compensations else None
+            sh_colors = torch.empty((cap, 3), dtype=torch.float32, device=dev) if _sh is not None else None
             ws = torch.empty(max(int(lib.rs_project_packed_workspace_bytes(B, C, N)), 16), dtype=torch.uint8, device=dev)
             pa = _lib.rs_project_packed_fwd_args()
             a = pa.proj
@@ -285,6 +300,10 @@ def projection_ewa_3dgs_packed_fwd(
                 rigid.fill(a.rigid)
             a.radii, a.means2d, a.depths, a.conics = _ptr(radii), _ptr(means2d), _ptr(depths), _ptr(conics)
             a.compensations = _ptr(compensations)
+            if _sh is not None:  # view-dependent colours of the packed rows, evaluated by the same kernel (extension)
+                _check(_sh[0], "sh coefficients", torch.float32, None, dev)
+                a.sh_coeffs, a.sh_colors = _ptr(_sh[0]), _ptr(sh_colors)
+                a.sh_degree, a.sh_K = int(_sh[1]), _sh[0].shape[-2]
             pa.capacity = cap
             pa.indptr = _ptr(indptr)
             pa.batch_ids, pa.camera_ids, pa.gaussian_ids = ids[0].data_ptr(), ids[1].data_ptr(), ids[2].data_ptr()
@@ -296,7 +315,8 @@ def projection_ewa_3dgs_packed_fwd(
                 break
             cap = nnz  # the caller's capacity hint was too small: run again with room for every row
     comp = compensations[:nnz] if compensations is not None else None
-    return indptr, ids[0, :nnz], ids[1, :nnz], ids[2, :nnz], radii[:nnz], means2d[:nnz], depths[:nnz], conics[:nnz], comp
+    out = (indptr, ids[0, :nnz], ids[1, :nnz], ids[2, :nnz], radii[:nnz], means2d[:nnz], depths[:nnz], conics[:nnz], comp)
+    return out + (sh_colors[:nnz],) if _sh is not None else out
 
 
 def projection_ewa_3dgs_packed_bwd(

@@ -33,10 +33,10 @@ void rs_set_error(const char *fmt, ...);
         }                                                                                                              \
     } while (0)
 
-void rs_count_launch();
+void rs_count_launch(const char *name);
 #define RS_LAUNCH_CHECK(name)                                                                                          \
     do {                                                                                                               \
-        rs_count_launch();                                                                                             \
+        rs_count_launch(name);                                                                                         \
         cudaError_t err__ = cudaGetLastError();                                                                        \
         if (err__ != cudaSuccess) {                                                                                    \
             rs_set_error("launch of %s failed: %s", name, cudaGetErrorString(err__));                                  \
@@ -56,8 +56,24 @@ static inline __host__ __device__ uint32_t rs_bit_width(uint32_t x) {
     return n;
 }
 
-// number of SMs of the current device (cached)
+// number of SMs of the current device (cached per device)
 int rs_num_sms();
+
+// Per-DEVICE once flags (kernel attributes such as the opt-in shared-memory size are per device, not per process):
+//   static RsPerDevice f;  if (!rs_dev_done(f)) { RS_CUDA(cudaFuncSetAttribute(...)); rs_dev_mark(f); }
+struct RsPerDevice {
+    unsigned long long done[2]; // bit d = set on device d (128 devices; beyond that the attribute is set on every call)
+};
+int rs_current_device();
+static inline bool rs_dev_done(const RsPerDevice &f) {
+    const int d = rs_current_device();
+    return d >= 0 && d < 128 && ((f.done[d >> 6] >> (d & 63)) & 1ull);
+}
+static inline void rs_dev_mark(RsPerDevice &f) {
+    const int d = rs_current_device();
+    if (d >= 0 && d < 128)
+        __atomic_fetch_or(&f.done[d >> 6], 1ull << (d & 63), __ATOMIC_RELAXED);
+}
 
 #ifdef __CUDACC__
 __device__ __forceinline__ unsigned rs_lanemask_lt() {

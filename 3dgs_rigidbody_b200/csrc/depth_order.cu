@@ -1,0 +1,371 @@
+// Depth order of the visible (image, Gaussian) elements: the first half of the depth-ordered binning of isect.cu.
+//
+// What is needed: the visible elements listed in ascending (depth bits, flatten index) order -- the order in which a
+// stable sort of the reference's (image | tile | depth) keys breaks ties inside a tile (csrc/IntersectTile.cu:95-113,
+// 296-339).  Round 1 produced it with four one-sweep LSD passes over all E elements; at E = 1 M every pass is a single
+// wave of CTAs chained through a look-back and costs ~23 us whatever the bandwidth (profiles/r01_sort_microbench.txt).
+//
+// Here the order is produced by a bucket sort whose steps have no serial chain at all:
+//   K0  min / max of the depth bits of the visible elements, and their number V                     (E reads)
+//   K1  fine-bucket histogram: bucket = (bits - min) >> shift, DORD_BUCKETS = 65536 buckets over the ACTUAL range of
+//       this frame (so the resolution adapts to the scene: ~15 elements per bucket at 1 M)            (E reads, V atomics)
+//   K2  exclusive scan of the bucket counts by one CTA; buckets are grouped into sort groups of ~DORD_TARGET elements
+//       (group g starts at the first bucket boundary at or after g * DORD_TARGET)
+//   K3  scatter: every visible element takes the next free slot of its bucket (atomic cursor) and stores the 64-bit
+//       composite (depth bits << 32 | flatten index)                                                  (V atomics, 8 B writes)
+//   K4  one CTA per sort group: the group's composites are sorted in shared memory by a bitonic network (they are unique,
+//       so ascending composite order IS (depth, index) order, whatever order the atomics of K3 produced) and the indices
+//       are written out.  A group that does not fit in shared memory (thousands of elements with depth bits inside one
+//       bucket, e.g. a wall facing an orthographic camera) is sorted by the same CTA in global memory with a stable LSD
+//       radix sort over the bits that actually vary -- slow, but correct for any input.
+// Output: elems[0 .. V) and V (device side).  Everything is sized by the SM count / the element bound; no host sync.
+#include "common.cuh"
+
+#define DORD_BUCKET_BITS 16
+#define DORD_BUCKETS (1 << DORD_BUCKET_BITS)
+#define DORD_TARGET 896   // elements per sort group (plus the tail of the bucket that crosses the boundary)
+#define DORD_CAP 4096     // composites a CTA sorts in shared memory
+#define DORD_THREADS 256
+
+struct DordHeader {          // zero-initialised by one memset per call
+    unsigned int inv_min;    // max over visible elements of ~bits  (min = ~inv_min)
+    unsigned int max;        // max of bits
+    unsigned int n_visible;  // V
+    unsigned int shift;      // bucket = (bits - min) >> shift          (written by K2's prologue ... see dord_shift)
+    unsigned int n_groups;
+    unsigned int _pad[3];
+};
+
+__device__ __forceinline__ unsigned int dord_shift(unsigned int kmin, unsigned int kmax) {
+    const unsigned int range = kmax - kmin; // buckets must cover [0, range]
+    const int width = 32 - __clz(range | 1u);
+    return (unsigned int)max(0, width - DORD_BUCKET_BITS);
+}
+
+// ---- K0 -----------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DORD_THREADS)
+rs_dord_minmax_kernel(int64_t n_elems, const float *__restrict__ depths, const int32_t *__restrict__ tiles,
+                      DordHeader *__restrict__ hdr) {
+    unsigned int inv_min = 0u, mx = 0u, cnt = 0u;
+    for (int64_t i = (int64_t)blockIdx.x * DORD_THREADS + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * DORD_THREADS) {
+        if (tiles[i] > 0) {
+            const unsigned int k = __float_as_uint(depths[i]);
+            inv_min = max(inv_min, ~k);
+            mx = max(mx, k);
+            ++cnt;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        inv_min = max(inv_min, __shfl_xor_sync(0xffffffffu, inv_min, o));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    // one atomic triple per CTA: same-address atomics serialise in L2, so per-warp atomics would dominate the kernel
+    __shared__ unsigned int s_red[3][DORD_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) {
+        s_red[0][warp] = inv_min;
+        s_red[1][warp] = mx;
+        s_red[2][warp] = cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < DORD_THREADS / 32; ++w) {
+            inv_min = max(inv_min, s_red[0][w]);
+            mx = max(mx, s_red[1][w]);
+            cnt += s_red[2][w];
+        }
+        if (cnt != 0u) {
+            atomicMax(&hdr->inv_min, inv_min);
+            atomicMax(&hdr->max, mx);
+            atomicAdd(&hdr->n_visible, cnt);
+        }
+    }
+}
+
+// ---- K1 -----------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DORD_THREADS)
+rs_dord_count_kernel(int64_t n_elems, const float *__restrict__ depths, const int32_t *__restrict__ tiles,
+                     const DordHeader *__restrict__ hdr, unsigned int *__restrict__ counts) {
+    const unsigned int kmin = ~hdr->inv_min, shift = dord_shift(kmin, hdr->max);
+    for (int64_t i = (int64_t)blockIdx.x * DORD_THREADS + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * DORD_THREADS) {
+        if (tiles[i] > 0)
+            atomicAdd(&counts[(__float_as_uint(depths[i]) - kmin) >> shift], 1u);
+    }
+}
+
+// ---- K2: counts -> bucket cursors (exclusive prefix, in place) + group starts --------------------------------------------
+// One CTA of 32 warps; warp w owns the 2048 consecutive buckets [2048 w, 2048 (w+1)) and walks them 32 at a time (lane l ->
+// bucket 2048 w + 32 j + l), so every load / store instruction of a warp covers one 128-byte line.
+#define DORD_SCAN_THREADS 1024
+#define DORD_ROWS (DORD_BUCKETS / DORD_SCAN_THREADS) // 32-bucket rows per warp
+__global__ void __launch_bounds__(DORD_SCAN_THREADS)
+rs_dord_scan_kernel(DordHeader *__restrict__ hdr, unsigned int *__restrict__ counts, unsigned int *__restrict__ group_start,
+                    int32_t *__restrict__ n_sorted_out) {
+    __shared__ unsigned int warp_tot[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned int *mine = counts + (size_t)warp * (32 * DORD_ROWS);
+    unsigned int c[DORD_ROWS];
+    unsigned int sum = 0;
+#pragma unroll
+    for (int j = 0; j < DORD_ROWS; ++j) {
+        c[j] = mine[j * 32 + lane];
+        sum += c[j];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0)
+        warp_tot[warp] = sum;
+    __syncthreads();
+    if (warp == 0) { // exclusive scan of the 32 warp totals
+        const unsigned int w = warp_tot[lane];
+        unsigned int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int n = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o)
+                wi += n;
+        }
+        warp_tot[lane] = wi - w;
+    }
+    __syncthreads();
+    const unsigned int V = hdr->n_visible;
+    if (threadIdx.x == 0) {
+        group_start[0] = 0u;
+        hdr->n_groups = V / DORD_TARGET + 1u;
+        group_start[V / DORD_TARGET + 1u] = V;
+        hdr->shift = dord_shift(~hdr->inv_min, hdr->max);
+        if (n_sorted_out != nullptr)
+            *n_sorted_out = (int32_t)V;
+    }
+    unsigned int carry = warp_tot[warp]; // elements in all buckets before this row
+#pragma unroll
+    for (int j = 0; j < DORD_ROWS; ++j) {
+        unsigned int incl = c[j];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o)
+                incl += n;
+        }
+        const unsigned int p = carry + incl - c[j], e = carry + incl;
+        mine[j * 32 + lane] = p; // the bucket's cursor for K3
+        if (c[j] != 0u) {
+            // every multiple g * TARGET inside (p, e]: group g starts at this bucket's END (first boundary at or after it)
+            for (unsigned int g = p / DORD_TARGET + 1u; g * DORD_TARGET <= e; ++g)
+                group_start[g] = e;
+        }
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
+// ---- K3 -----------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DORD_THREADS)
+rs_dord_scatter_kernel(int64_t n_elems, const float *__restrict__ depths, const int32_t *__restrict__ tiles,
+                       const DordHeader *__restrict__ hdr, unsigned int *__restrict__ cursors,
+                       unsigned long long *__restrict__ comp) {
+    const unsigned int kmin = ~hdr->inv_min, shift = hdr->shift;
+    for (int64_t i = (int64_t)blockIdx.x * DORD_THREADS + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * DORD_THREADS) {
+        if (tiles[i] > 0) {
+            const unsigned int k = __float_as_uint(depths[i]);
+            const unsigned int pos = atomicAdd(&cursors[(k - kmin) >> shift], 1u);
+            comp[pos] = ((unsigned long long)k << 32) | (unsigned long long)(unsigned int)i;
+        }
+    }
+}
+
+// ---- K4 -----------------------------------------------------------------------------------------------------------------
+// stable LSD radix sort of `n` composites by ONE warp, 8-bit digits over the bytes whose bits vary inside the group;
+// src / dst ping-pong in global memory, the result is left in `a` (copied back if needed).  Pathological inputs only.
+__device__ void dord_sort_big(unsigned long long *a, unsigned long long *b, unsigned int n, unsigned int *hist /*smem 256*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ unsigned long long vary_s;
+    if (threadIdx.x == 0)
+        vary_s = 0ull;
+    __syncthreads();
+    // which bits differ from the first composite
+    {
+        const unsigned long long first = a[0];
+        unsigned long long v = 0ull;
+        for (unsigned int i = threadIdx.x; i < n; i += DORD_THREADS)
+            v |= a[i] ^ first;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            v |= __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && v != 0ull)
+            atomicOr(&vary_s, v);
+    }
+    __syncthreads();
+    const unsigned long long vary = vary_s;
+    unsigned long long *src = a, *dst = b;
+    for (int byte = 0; byte < 8; ++byte) {
+        if (((vary >> (8 * byte)) & 0xffull) == 0ull)
+            continue;
+        const int sh = 8 * byte;
+        hist[threadIdx.x] = 0u;
+        __syncthreads();
+        for (unsigned int i = threadIdx.x; i < n; i += DORD_THREADS)
+            atomicAdd(&hist[(unsigned int)(src[i] >> sh) & 255u], 1u);
+        __syncthreads();
+        if (warp == 0) { // exclusive scan of the 256 counters by one warp (8 per lane)
+            unsigned int v[8], s = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                v[j] = hist[lane * 8 + j];
+                s += v[j];
+            }
+            unsigned int incl = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o)
+                    incl += t;
+            }
+            unsigned int run = incl - s;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                hist[lane * 8 + j] = run;
+                run += v[j];
+            }
+            __syncwarp();
+            // in-order scatter, 32 composites at a time: equal digits keep their order (rank = earlier lanes with my digit)
+            for (unsigned int i0 = 0; i0 < n; i0 += 32) {
+                const unsigned int i = i0 + lane;
+                const bool live = i < n;
+                const unsigned long long c = live ? src[i] : 0ull;
+                const unsigned int d = live ? ((unsigned int)(c >> sh) & 255u) : 256u + lane; // dead lanes: unique digits
+                const unsigned int peers = __match_any_sync(0xffffffffu, d);
+                const unsigned int rank = __popc(peers & rs_lanemask_lt());
+                unsigned int base = 0;
+                if (live && rank == 0)
+                    base = atomicAdd(&hist[d], (unsigned int)__popc(peers));
+                base = __shfl_sync(0xffffffffu, base, __ffs(peers) - 1);
+                if (live)
+                    dst[base + rank] = c;
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        unsigned long long *t = src;
+        src = dst;
+        dst = t;
+    }
+    if (src != a) {
+        for (unsigned int i = threadIdx.x; i < n; i += DORD_THREADS)
+            a[i] = src[i];
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(DORD_THREADS)
+rs_dord_sort_kernel(const DordHeader *__restrict__ hdr, const unsigned int *__restrict__ group_start,
+                    unsigned long long *__restrict__ comp, unsigned long long *__restrict__ comp_alt,
+                    int32_t *__restrict__ elems) {
+    __shared__ unsigned long long s[DORD_CAP];
+    __shared__ unsigned int hist[256];
+    const unsigned int n_groups = hdr->n_groups;
+    for (unsigned int g = blockIdx.x; g < n_groups; g += gridDim.x) {
+        const unsigned int lo = group_start[g], hi = group_start[g + 1];
+        if (hi <= lo)
+            continue;
+        const unsigned int n = hi - lo;
+        if (n > DORD_CAP) {
+            dord_sort_big(comp + lo, comp_alt + lo, n, hist);
+            for (unsigned int i = threadIdx.x; i < n; i += DORD_THREADS)
+                elems[lo + i] = (int32_t)(unsigned int)comp[lo + i];
+            continue;
+        }
+        unsigned int m = 32;
+        while (m < n)
+            m <<= 1;
+        for (unsigned int i = threadIdx.x; i < m; i += DORD_THREADS)
+            s[i] = i < n ? comp[lo + i] : ~0ull;
+        __syncthreads();
+        // bitonic network over m = 2^q composites (ascending); the composites are unique
+        for (unsigned int k = 2; k <= m; k <<= 1) {
+            for (unsigned int j = k >> 1; j > 0; j >>= 1) {
+                for (unsigned int t = threadIdx.x; t < (m >> 1); t += DORD_THREADS) {
+                    const unsigned int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)); // index with bit j clear
+                    const unsigned int p = i | j;
+                    const unsigned long long x = s[i], y = s[p];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) {
+                        s[i] = y;
+                        s[p] = x;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        for (unsigned int i = threadIdx.x; i < n; i += DORD_THREADS)
+            elems[lo + i] = (int32_t)(unsigned int)s[i];
+        __syncthreads();
+    }
+}
+
+// ---- host ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct DordLayout {
+    size_t hdr, counts, group_start, comp, comp_alt, total;
+};
+inline size_t dord_align(size_t x) { return (x + 255) & ~(size_t)255; }
+DordLayout dord_layout(int64_t n_elems) {
+    DordLayout L;
+    const size_t E = (size_t)(n_elems > 0 ? n_elems : 1);
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        size_t at = o;
+        o = dord_align(o + bytes);
+        return at;
+    };
+    L.hdr = take(sizeof(DordHeader));
+    L.counts = take((size_t)DORD_BUCKETS * 4);
+    L.group_start = take((E / DORD_TARGET + 3) * 4);
+    L.comp = take(E * 8);
+    L.comp_alt = take(E * 8);
+    L.total = o;
+    return L;
+}
+} // namespace
+
+uint64_t rs_depth_order_workspace_bytes(int64_t n_elems) { return dord_layout(n_elems).total; }
+
+// elems_out[0 .. V) = visible elements (tiles[e] > 0) in ascending (depth bits, index) order; *n_sorted_dev = V.
+int rs_depth_order(int64_t n_elems, const float *depths, const int32_t *tiles, int32_t *elems_out, int32_t *n_sorted_dev,
+                   void *workspace, uint64_t workspace_bytes, cudaStream_t s) {
+    RS_CHECK(n_elems >= 0 && n_elems < ((int64_t)1 << 31), "rs_depth_order: bad element count");
+    RS_CHECK(n_sorted_dev != nullptr, "rs_depth_order: n_sorted_dev is required");
+    if (n_elems == 0) {
+        RS_CUDA(cudaMemsetAsync(n_sorted_dev, 0, sizeof(int32_t), s));
+        return 0;
+    }
+    const DordLayout L = dord_layout(n_elems);
+    RS_CHECK(depths && tiles && elems_out && workspace && workspace_bytes >= L.total,
+             "rs_depth_order: null pointer or workspace too small (%llu < %llu)", (unsigned long long)workspace_bytes,
+             (unsigned long long)L.total);
+    char *w = reinterpret_cast<char *>(workspace);
+    DordHeader *hdr = reinterpret_cast<DordHeader *>(w + L.hdr);
+    unsigned int *counts = reinterpret_cast<unsigned int *>(w + L.counts);
+    unsigned int *group_start = reinterpret_cast<unsigned int *>(w + L.group_start);
+    unsigned long long *comp = reinterpret_cast<unsigned long long *>(w + L.comp);
+    unsigned long long *comp_alt = reinterpret_cast<unsigned long long *>(w + L.comp_alt);
+    // header + bucket counters in one clear (they are adjacent)
+    RS_CUDA(cudaMemsetAsync(w + L.hdr, 0, L.counts + (size_t)DORD_BUCKETS * 4 - L.hdr, s));
+    const int sms = rs_num_sms();
+    const int grid = (int)min((int64_t)sms * 8, (n_elems + DORD_THREADS - 1) / DORD_THREADS);
+    rs_dord_minmax_kernel<<<grid, DORD_THREADS, 0, s>>>(n_elems, depths, tiles, hdr);
+    RS_LAUNCH_CHECK("rs_dord_minmax_kernel");
+    rs_dord_count_kernel<<<grid, DORD_THREADS, 0, s>>>(n_elems, depths, tiles, hdr, counts);
+    RS_LAUNCH_CHECK("rs_dord_count_kernel");
+    rs_dord_scan_kernel<<<1, DORD_SCAN_THREADS, 0, s>>>(hdr, counts, group_start, n_sorted_dev);
+    RS_LAUNCH_CHECK("rs_dord_scan_kernel");
+    rs_dord_scatter_kernel<<<grid, DORD_THREADS, 0, s>>>(n_elems, depths, tiles, hdr, counts, comp);
+    RS_LAUNCH_CHECK("rs_dord_scatter_kernel");
+    const int sort_grid = (int)min((int64_t)sms * 8, n_elems / DORD_TARGET + 1);
+    rs_dord_sort_kernel<<<sort_grid, DORD_THREADS, 0, s>>>(hdr, group_start, comp, comp_alt, elems_out);
+    RS_LAUNCH_CHECK("rs_dord_sort_kernel");
+    return 0;
+}

@@ -18,7 +18,11 @@
 
 #include "common.cuh"
 
-#define RS_EXCHANGE_TIMEOUT_CYCLES (8ll * 1000 * 1000 * 1000) // ~4 s at 2 GHz
+// Spin limit of the flag waits: rs_exchange_args.timeout_ms, default RS_EXCHANGE_DEFAULT_TIMEOUT_MS (a rank may
+// legitimately lag by a checkpoint or a GC pause; NCCL's own watchdog default is minutes).  clock64() ticks at the SM
+// clock, taken as <= 2 GHz.
+#define RS_EXCHANGE_DEFAULT_TIMEOUT_MS 60000
+#define RS_EXCHANGE_CYCLES_PER_MS 2000000ll
 
 struct ExchangeCtl {
     unsigned int cnt_flag[2][RS_EXCHANGE_MAX_WORLD];  // epoch of the count vector of source s (double-buffered by parity)
@@ -26,6 +30,7 @@ struct ExchangeCtl {
     int counts[2][RS_EXCHANGE_MAX_WORLD][RS_EXCHANGE_MAX_WORLD]; // [parity][source][destination] rows
     unsigned int done_ctas;                           // local: CTAs of the running push kernel that finished
     unsigned int error;                               // local: 1 = spin timed out, 2 = a block did not fit
+    unsigned int fail_epoch[RS_EXCHANGE_MAX_WORLD];   // epoch in which source s gave up waiting (it then sent NO rows)
 };
 static_assert(sizeof(ExchangeCtl) <= RS_EXCHANGE_CTL_BYTES, "control block too large");
 
@@ -118,12 +123,13 @@ struct ExchangeLayout {
 };
 
 // waits until flag[s] has reached `epoch` for every s < world (one lane per source); returns false on timeout
-__device__ __forceinline__ bool wait_flags(const unsigned int *flags, int world, unsigned int epoch) {
+__device__ __forceinline__ bool wait_flags(const unsigned int *flags, int world, unsigned int epoch, int timeout_ms) {
     bool ok = true;
+    const long long limit = (long long)(timeout_ms > 0 ? timeout_ms : RS_EXCHANGE_DEFAULT_TIMEOUT_MS) * RS_EXCHANGE_CYCLES_PER_MS;
     if ((int)threadIdx.x < world) {
         const long long t0 = clock64();
         while ((int)(ld_sys(flags + threadIdx.x) - epoch) < 0) {
-            if (clock64() - t0 > RS_EXCHANGE_TIMEOUT_CYCLES) {
+            if (clock64() - t0 > limit) {
                 ok = false;
                 break;
             }
@@ -153,10 +159,15 @@ __global__ void __launch_bounds__(256) rs_exchange_push_kernel(const rs_exchange
             st_sys(&((ExchangeCtl *)peers[threadIdx.x])->cnt_flag[par][r], a.epoch);
     }
     // (B) all W vectors -> placement of my blocks
-    if (!wait_flags(mine->cnt_flag[par], W, a.epoch)) {
+    // A rank that gives up here must not place rows from a stale count matrix: it sends NOTHING this epoch (dst_base = -1
+    // below), tells every peer so (fail_epoch, read by rs_exchange_wait on every rank, so all ranks raise together), and
+    // still raises its data flag at the end so that no peer waits for it forever.
+    const bool counts_ok = wait_flags(mine->cnt_flag[par], W, a.epoch, a.timeout_ms);
+    if (!counts_ok) {
         if (threadIdx.x == 0)
             mine->error = 1u;
-        // fall through: the data flag below still goes up so that no peer waits for this rank forever
+        if (blockIdx.x == 0 && (int)threadIdx.x < W)
+            st_sys(&((ExchangeCtl *)peers[threadIdx.x])->fail_epoch[r], a.epoch);
     }
     if ((int)threadIdx.x <= W)
         src_lo[threadIdx.x] = a.indptr[min((int)threadIdx.x, W) * Cl];
@@ -173,7 +184,7 @@ __global__ void __launch_bounds__(256) rs_exchange_push_kernel(const rs_exchange
             base = -1;
             mine->error = 2u;
         }
-        dst_base[d] = base;
+        dst_base[d] = counts_ok ? base : -1;
     }
     __syncthreads();
 
@@ -253,8 +264,11 @@ __global__ void rs_exchange_wait_kernel(const rs_exchange_args a, long long *tot
     char *const *peers = (char *const *)a.peer_base;
     ExchangeCtl *mine = (ExchangeCtl *)peers[a.rank];
     const unsigned int par = a.epoch & 1u;
-    const bool ok = wait_flags(mine->data_flag, a.world, a.epoch);
+    bool ok = wait_flags(mine->data_flag, a.world, a.epoch, a.timeout_ms);
     if (threadIdx.x == 0) {
+        for (int s = 0; s < a.world; ++s) // a source that gave up on the counts sent no rows: the frame is invalid everywhere
+            if (ld_sys(&mine->fail_epoch[s]) == a.epoch)
+                ok = false;
         // diagnostics for a timed-out frame: which sources' flags are behind (bit s = data flag, bit 16 + s = count flag)
         long long behind = 0;
         for (int s = 0; s < a.world; ++s) {

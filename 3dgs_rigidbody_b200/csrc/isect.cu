@@ -324,13 +324,13 @@ extern "C" int rs_isect_offsets(const int64_t *isect_ids_sorted, int64_t n_isect
 // The reference sorts M 64-bit (image | tile | depth) keys with cub (csrc/IntersectTile.cu:296-339): ceil(46/8) = 6 LSD
 // passes over 12 B pairs for a 1080p frame.  The same order -- (image, tile, depth bits, flatten index), stable --
 // is produced here with far less traffic by sorting the two halves of the key separately:
-//   1. stable LSD sort of the E = I*N (depth bits, flatten index) pairs          4 passes over E 8-byte pairs
+//   1. the V visible elements in (depth bits, flatten index) order: bucket sort (depth_order.cu)   ~20 B per element
 //   2. count / scan / emit in that depth order: (image | tile) 32-bit keys, flatten-index values
 //   3. stable LSD sort of the M (image | tile, flatten index) pairs on the tile + image bits only
 //                                                                                 ceil(14/8) = 2 passes over M 8-byte pairs
 //   4. offsets from the sorted 32-bit keys; the 64-bit isect ids are rebuilt (tile key << 32 | depth bits of the
 //      flatten id) only when the caller asks for them.
-// Ties: equal depths keep ascending flatten index through 1 (stable), every Gaussian contributes at most one
+// Ties: equal depths are listed in ascending flatten index by 1, every Gaussian contributes at most one
 // intersection per tile, and 3 is stable, so equal (image, tile, depth) keys stay in ascending flatten-index order --
 // exactly the order the reference's stable sort of its emission order gives.
 // =====================================================================================================================
@@ -338,12 +338,17 @@ int rs_sort_pairs_u32_internal(int64_t n_bound, const int32_t *n_dev, int begin_
                                const int32_t *vals_in, uint32_t *kbuf0, int32_t *vbuf0, uint32_t *kbuf1, int32_t *vbuf1,
                                void *workspace, uint64_t workspace_bytes, int *passes, cudaStream_t s, bool hist_ready);
 int rs_sort_ws_prepare(void *workspace, cudaStream_t s);
+// depth_order.cu
+uint64_t rs_depth_order_workspace_bytes(int64_t n_elems);
+int rs_depth_order(int64_t n_elems, const float *depths, const int32_t *tiles, int32_t *elems_out, int32_t *n_sorted_dev,
+                   void *workspace, uint64_t workspace_bytes, cudaStream_t s);
 
 // block sums of the tile counts taken in depth order
 __global__ void __launch_bounds__(RS_ISECT_THREADS)
-rs_bin_count_kernel(int64_t n_elems, const int32_t *__restrict__ elems, const int32_t *__restrict__ tiles_per_gauss,
-                    int32_t *__restrict__ block_sums) {
+rs_bin_count_kernel(int64_t n_bound, const int32_t *__restrict__ n_sorted, const int32_t *__restrict__ elems,
+                    const int32_t *__restrict__ tiles_per_gauss, int32_t *__restrict__ block_sums) {
     __shared__ int sums[8];
+    const int64_t n_elems = min((int64_t)*n_sorted, n_bound); // visible elements, in depth order
     const int64_t base = (int64_t)blockIdx.x * RS_ISECT_BLOCK;
     int mine = 0;
 #pragma unroll
@@ -381,10 +386,11 @@ struct BinEmitSmem {
 };
 
 __global__ void __launch_bounds__(RS_ISECT_THREADS)
-rs_bin_emit_kernel(const rs_isect_args a, const int32_t *__restrict__ elems, uint32_t tile_n_bits,
-                   uint32_t *__restrict__ tile_keys, int32_t *__restrict__ vals, uint32_t *__restrict__ sort_ws,
-                   int sort_bits, int sort_nb_stride) {
+rs_bin_emit_kernel(const rs_isect_args a, const int32_t *__restrict__ elems, const int32_t *__restrict__ n_sorted,
+                   uint32_t tile_n_bits, uint32_t *__restrict__ tile_keys, int32_t *__restrict__ vals,
+                   uint32_t *__restrict__ sort_ws, int sort_bits, int sort_nb_stride) {
     __shared__ BinEmitSmem sm;
+    const int64_t n_live = min((int64_t)*n_sorted, (int64_t)a.n_elems); // visible elements, in depth order
     // digit histograms of the keys this CTA emits, for every pass of the tile sort that follows (saves that sort its own
     // read of all M keys)
     const int sort_passes = sort_num_passes(sort_bits), sort_width = sort_digit_width(sort_bits);
@@ -404,7 +410,7 @@ rs_bin_emit_kernel(const rs_isect_args a, const int32_t *__restrict__ elems, uin
         elem[k] = 0;
         x0[k] = y0[k] = hi[k] = 0;
         w[k] = 1;
-        if (i < a.n_elems) {
+        if (i < n_live) {
             const int32_t e = elems[i];
             c = a.tiles_per_gauss[e];
             if (c > 0) {
@@ -558,7 +564,7 @@ rs_bin_keys64_kernel(int64_t n_bound, const int32_t *__restrict__ n_dev, const u
 
 namespace {
 struct BinLayout {
-    size_t dkeys_a, dkeys_b, elems_a, elems_b, block_sums, tkeys_a, tkeys_b, vals_b, sort_ws, sort_ws_bytes, total;
+    size_t elems, n_sorted, dord_ws, dord_ws_bytes, block_sums, tkeys_a, tkeys_b, vals_b, sort_ws, sort_ws_bytes, total;
 };
 inline size_t bin_align(size_t x) { return (x + 255) & ~(size_t)255; }
 BinLayout bin_layout(int64_t n_elems, int64_t capacity) {
@@ -570,16 +576,15 @@ BinLayout bin_layout(int64_t n_elems, int64_t capacity) {
         return at;
     };
     const size_t E = (size_t)(n_elems > 0 ? n_elems : 1), M = (size_t)(capacity > 0 ? capacity : 1);
-    L.dkeys_a = take(E * 4);
-    L.dkeys_b = take(E * 4);
-    L.elems_a = take(E * 4);
-    L.elems_b = take(E * 4);
+    L.elems = take(E * 4);
+    L.n_sorted = take(4);
+    L.dord_ws_bytes = rs_depth_order_workspace_bytes((int64_t)E);
+    L.dord_ws = take(L.dord_ws_bytes);
     L.block_sums = take(((size_t)rs_isect_num_blocks((int64_t)E) + 1) * 4);
     L.tkeys_a = take(M * 4);
     L.tkeys_b = take(M * 4);
     L.vals_b = take(M * 4);
-    const uint64_t w1 = rs_radix_sort_workspace_bytes((int64_t)E), w2 = rs_radix_sort_workspace_bytes((int64_t)M);
-    L.sort_ws_bytes = w1 > w2 ? w1 : w2;
+    L.sort_ws_bytes = rs_radix_sort_workspace_bytes((int64_t)M);
     L.sort_ws = take(L.sort_ws_bytes);
     L.total = o;
     return L;
@@ -626,20 +631,15 @@ extern "C" int rs_isect_sorted(const rs_isect_sorted_args *b, rs_stream_t stream
     int32_t *tv_buf0 = final_is_buf0 ? tv_final : tv_other, *tv_buf1 = final_is_buf0 ? tv_other : tv_final;
     const uint32_t *tkeys = tk_final;
 
-    const int32_t *elems = nullptr;
+    const int32_t *elems = reinterpret_cast<const int32_t *>(w + L.elems);
+    const int32_t *n_sorted = reinterpret_cast<const int32_t *>(w + L.n_sorted);
     if (a->n_elems > 0) {
-        // 1. depth order: stable LSD sort of (depth bits, flatten index); the keys are read straight from `depths`, the
-        //    values of the first pass are the indices themselves
-        uint32_t *dk_a = reinterpret_cast<uint32_t *>(w + L.dkeys_a), *dk_b = reinterpret_cast<uint32_t *>(w + L.dkeys_b);
-        int32_t *el_a = reinterpret_cast<int32_t *>(w + L.elems_a), *el_b = reinterpret_cast<int32_t *>(w + L.elems_b);
-        int passes = 0;
-        if (int e = rs_sort_pairs_u32_internal(a->n_elems, nullptr, 0, 32, reinterpret_cast<const uint32_t *>(a->depths),
-                                               nullptr, dk_a, el_a, dk_b, el_b, w + L.sort_ws, L.sort_ws_bytes, &passes, s,
-                                               false))
+        // 1. depth order of the visible elements: bucket sort on the depth bits (depth_order.cu), ties by flatten index
+        if (int e = rs_depth_order(a->n_elems, a->depths, a->tiles_per_gauss, reinterpret_cast<int32_t *>(w + L.elems),
+                                   reinterpret_cast<int32_t *>(w + L.n_sorted), w + L.dord_ws, L.dord_ws_bytes, s))
             return e;
-        elems = ((passes - 1) & 1) ? el_b : el_a;
         // 2a. block sums of the tile counts in depth order
-        rs_bin_count_kernel<<<nb, RS_ISECT_THREADS, 0, s>>>(a->n_elems, elems, a->tiles_per_gauss, block_sums);
+        rs_bin_count_kernel<<<nb, RS_ISECT_THREADS, 0, s>>>(a->n_elems, n_sorted, elems, a->tiles_per_gauss, block_sums);
         RS_LAUNCH_CHECK("rs_bin_count_kernel");
     }
     // 2b. exclusive block offsets, device-side total and overflow flag
@@ -654,7 +654,7 @@ extern "C" int rs_isect_sorted(const rs_isect_sorted_args *b, rs_stream_t stream
         if (int err = rs_sort_ws_prepare(w + L.sort_ws, s)) // the emission kernel accumulates the sort's histograms
             return err;
         const int sort_nb_stride = (int)((a->capacity + SORT_TILE - 1) / SORT_TILE);
-        rs_bin_emit_kernel<<<nb, RS_ISECT_THREADS, 0, s>>>(e, elems, tile_n_bits, tk_buf1, tv_buf1,
+        rs_bin_emit_kernel<<<nb, RS_ISECT_THREADS, 0, s>>>(e, elems, n_sorted, tile_n_bits, tk_buf1, tv_buf1,
                                                            reinterpret_cast<uint32_t *>(w + L.sort_ws), tile_bits,
                                                            sort_nb_stride);
         RS_LAUNCH_CHECK("rs_bin_emit_kernel");

@@ -533,14 +533,14 @@ static int rs_project_launch(const rs_project_fwd_args *a, PackOut *po, cudaStre
         (!rigid || aligned16(a->rigid.cluster_ids)) && (a->B == 1 || a->N % 4 == 0) && (int64_t)a->B * a->C <= 65535) {
         const unsigned chunks_per_image = (unsigned)((a->N + PROJ_CHUNK - 1) / PROJ_CHUNK);
         if (rigid) {
-            static bool attr_set = false; // pose table + input stage can exceed the 48 KB default
-            if (!attr_set) {
+            static RsPerDevice attr_set; // pose table + input stage can exceed the 48 KB default
+            if (!rs_dev_done(attr_set)) {
                 const int bytes = RS_MAX_SMEM_BODIES * RS_BODY_FLOATS * (int)sizeof(float);
                 RS_CUDA(cudaFuncSetAttribute(rs_project_fwd_staged_kernel<true, false>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
                 RS_CUDA(cudaFuncSetAttribute(rs_project_fwd_staged_kernel<true, true>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-                attr_set = true;
+                rs_dev_mark(attr_set);
             }
         }
         if (packed) {

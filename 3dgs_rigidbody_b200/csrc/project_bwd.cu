@@ -1,7 +1,7 @@
 // rs_project_bwd: VJP of (rigid transform + fused EWA projection).
 // Replaces csrc/ProjectionEWA3DGSFused.cu:293-531 (host side csrc/Projection.cpp:191-281); VJP pieces follow
 // gsplat/cuda/include/Utils.cuh: inverse_vjp 373-378, add_blur_vjp 390-423, persp_proj_vjp 539-616, ortho 454-489,
-// fisheye 657-747, posW2C_VJP 30-48, covarW2C_VJP 59-80, quat_scale_to_covar_vjp 224-261, quat_to_rotmat_vjp 166-189.
+// fisheye 657-747 (own (s, w, k) formulation, see project_math.cuh), posW2C_VJP 30-48, covarW2C_VJP 59-80, quat_scale_to_covar_vjp 224-261, quat_to_rotmat_vjp 166-189.
 // The rigid transform is chained in: v_mean = R_k^T v_mean', v_quat = conj(q_k) (x) v_quat', v_Sigma = R_k^T v_Sigma' R_k.
 //
 // Same CTA shape as the forward kernel (1024 elements per CTA, pose table in shared memory).  Gradients are
@@ -88,67 +88,42 @@ __device__ __forceinline__ void ortho_vjp(const float cov3d[9], const RsCam &c, 
     v_mean3d[1] += c.fy * vm[1];
 }
 
-// Utils.cuh:657-747
+// VJP of the equidistant fisheye projection and of its Jacobian (replaces Utils.cuh:657-747), in the (s, w, k) form of
+// rs_fisheye_ray:  with g = dk/d(r^2) * 2 = -(2 z w^2 + 3 k) / r^2  (so dk/dx = x g, dk/dy = y g, dk/dz = 2 w^2)
+//   dJ00 = fx (x (3k + x^2 g),  y (k + x^2 g),  2 x^2 w^2 - w)        dJ01 = fx (y (k + x^2 g),  x (k + y^2 g),  2 x y w^2)
+//   dJ02 = fx (2 x^2 w^2 - w,   2 x y w^2,      2 x z w^2)            (rows of J10, J11, J12: x <-> y, fx -> fy)
+// each triple being the derivative with respect to (x, y, z).
 __device__ __forceinline__ void fisheye_vjp(const float p[3], const float cov3d[9], const RsCam &c, const float vc[4],
                                             const float vm[2], float v_mean3d[3], float v_cov3d[9]) {
-    float x = p[0], y = p[1], z = p[2];
-    const float fx = c.fx, fy = c.fy;
-    const float eps = 0.0000001f;
-    float x2 = x * x + eps;
-    float y2 = y * y;
-    float xy = x * y;
-    float x2y2 = x2 + y2;
-    float len_xy = sqrtf(x * x + y * y) + eps;
-    const float x2y2z2 = x2y2 + z * z;
-    float x2y2z2_inv = 1.f / x2y2z2;
-    float b = atan2f(len_xy, z) / len_xy / x2y2;
-    float a = z * x2y2z2_inv / (x2y2);
-    v_mean3d[0] += fx * (x2 * a + y2 * b) * vm[0] + fy * xy * (a - b) * vm[1];
-    v_mean3d[1] += fx * xy * (a - b) * vm[0] + fy * (y2 * a + x2 * b) * vm[1];
-    v_mean3d[2] += -fx * x * x2y2z2_inv * vm[0] - fy * y * x2y2z2_inv * vm[1];
-
-    const float theta = atan2f(len_xy, z);
-    const float J_b = theta / len_xy / x2y2;
-    const float J_a = z * x2y2z2_inv / (x2y2);
-    float J[6] = {fx * (x2 * J_a + y2 * J_b), fx * xy * (J_a - J_b), -fx * x * x2y2z2_inv,
-                  fy * xy * (J_a - J_b),      fy * (y2 * J_a + x2 * J_b), -fy * y * x2y2z2_inv};
+    const float x = p[0], y = p[1], z = p[2];
+    const RsFisheyeRay f = rs_fisheye_ray(x, y, z);
+    const float xx = x * x, yy = y * y, xy = x * y, w2 = f.w * f.w;
+    float J[6] = {c.fx * (f.s + xx * f.k), c.fx * xy * f.k, -c.fx * x * f.w,
+                  c.fy * xy * f.k,         c.fy * (f.s + yy * f.k), -c.fy * y * f.w};
+    // the 2D mean: v_p += J^T v_mean2d
+    v_mean3d[0] += J[0] * vm[0] + J[3] * vm[1];
+    v_mean3d[1] += J[1] * vm[0] + J[4] * vm[1];
+    v_mean3d[2] += J[2] * vm[0] + J[5] * vm[1];
     float v_J[6];
     proj_cov_vjp(J, cov3d, vc, v_cov3d, v_J);
-    float l4 = x2y2z2 * x2y2z2;
-    float E = -l4 * x2y2 * theta + x2y2z2 * x2y2 * len_xy * z;
-    float F = 3 * l4 * theta - 3 * x2y2z2 * len_xy * z - 2 * x2y2 * len_xy * z;
-    float A = x * (3 * E + x2 * F);
-    float B = y * (E + x2 * F);
-    float C = x * (E + y2 * F);
-    float D = y * (3 * E + y2 * F);
-    float S1 = x2 - y2 - z * z;
-    float S2 = y2 - x2 - z * z;
-    float inv1 = x2y2z2_inv * x2y2z2_inv;
-    float inv2 = inv1 / (x2y2 * x2y2 * len_xy);
-    float dJ_dx00 = fx * A * inv2;
-    float dJ_dx01 = fx * B * inv2;
-    float dJ_dx02 = fx * S1 * inv1;
-    float dJ_dx10 = fy * B * inv2;
-    float dJ_dx11 = fy * C * inv2;
-    float dJ_dx12 = 2.f * fy * xy * inv1;
-    float dJ_dy00 = dJ_dx01;
-    float dJ_dy01 = fx * C * inv2;
-    float dJ_dy02 = 2.f * fx * xy * inv1;
-    float dJ_dy10 = dJ_dx11;
-    float dJ_dy11 = fy * D * inv2;
-    float dJ_dy12 = fy * S2 * inv1;
-    float dJ_dz00 = dJ_dx02;
-    float dJ_dz01 = dJ_dy02;
-    float dJ_dz02 = 2.f * fx * x * z * inv1;
-    float dJ_dz10 = dJ_dx12;
-    float dJ_dz11 = dJ_dy12;
-    float dJ_dz12 = 2.f * fy * y * z * inv1;
-    v_mean3d[0] += dJ_dx00 * v_J[0] + dJ_dx01 * v_J[1] + dJ_dx02 * v_J[2] + dJ_dx10 * v_J[3] + dJ_dx11 * v_J[4] +
-                   dJ_dx12 * v_J[5];
-    v_mean3d[1] += dJ_dy00 * v_J[0] + dJ_dy01 * v_J[1] + dJ_dy02 * v_J[2] + dJ_dy10 * v_J[3] + dJ_dy11 * v_J[4] +
-                   dJ_dy12 * v_J[5];
-    v_mean3d[2] += dJ_dz00 * v_J[0] + dJ_dz01 * v_J[1] + dJ_dz02 * v_J[2] + dJ_dz10 * v_J[3] + dJ_dz11 * v_J[4] +
-                   dJ_dz12 * v_J[5];
+    // g: on the axis the series of k gives dk/d(r^2) = 0.8 / z^5 directly
+    float g;
+    if (z > 0.f && f.r2 < 1e-4f * z * z) {
+        const float iz = 1.f / z, iz2 = iz * iz;
+        g = 1.6f * iz2 * iz2 * iz;
+    } else {
+        g = -(2.f * z * w2 + 3.f * f.k) / f.r2;
+    }
+    const float kx = f.k + xx * g, ky = f.k + yy * g; // shared sub-expressions of the off-diagonal derivatives
+    // weights of the six Jacobian entries, focal lengths folded in
+    const float a0 = c.fx * v_J[0], a1 = c.fx * v_J[1], a2 = c.fx * v_J[2];
+    const float b0 = c.fy * v_J[3], b1 = c.fy * v_J[4], b2 = c.fy * v_J[5];
+    v_mean3d[0] += a0 * x * (3.f * f.k + xx * g) + (a1 + b0) * y * kx + a2 * (2.f * xx * w2 - f.w) + b1 * x * ky +
+                   b2 * 2.f * xy * w2;
+    v_mean3d[1] += a0 * y * kx + (a1 + b0) * x * ky + a2 * 2.f * xy * w2 + b1 * y * (3.f * f.k + yy * g) +
+                   b2 * (2.f * yy * w2 - f.w);
+    v_mean3d[2] += a0 * (2.f * xx * w2 - f.w) + (a1 + b0) * 2.f * xy * w2 + a2 * 2.f * x * z * w2 +
+                   b1 * (2.f * yy * w2 - f.w) + b2 * 2.f * y * z * w2;
 }
 
 template <bool HAS_RIGID>

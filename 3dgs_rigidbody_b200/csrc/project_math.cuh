@@ -4,7 +4,7 @@
 //   rigid transform     main.py:173-228, gsplat/utils.py:109-134
 //   quat/scale -> covar gsplat/cuda/include/Utils.cuh:142-164, 191-205
 //   world -> camera     Utils.cuh:18-57
-//   pinhole/ortho/fisheye EWA  Utils.cuh:428-452, 498-537, 618-655
+//   pinhole / ortho EWA  Utils.cuh:428-452, 498-537; fisheye: own formulation (rs_fisheye_ray), same mathematics as 618-655
 //   blur + conic + radius + culls  csrc/ProjectionEWA3DGSFused.cu:69-212, Utils.cuh:380-388
 // Matrices are row-major float[9]: m[3*r + c].  Sums run k = 0,1,2 left to right (glm's order).
 #pragma once
@@ -25,9 +25,11 @@ struct RsBody { // one row of the pose table held in shared memory (20 floats)
 __device__ __forceinline__ void rs_make_body(const rs_rigid_t &rg, int k, float *out /*20 floats*/) {
     float w = rg.body_quats[4 * k + 0], x = rg.body_quats[4 * k + 1], y = rg.body_quats[4 * k + 2],
           z = rg.body_quats[4 * k + 3];
-    // main.py:207 torch.linalg.norm
-    float n = __fsqrt_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(w, w), __fmul_rn(x, x)), __fmul_rn(y, y)),
-                                   __fmul_rn(z, z)));
+    // main.py:207 torch.linalg.norm of a 4-vector on CUDA: four threads square one component each and combine by a
+    // shuffle tree, i.e. sqrt((w^2 + y^2) + (x^2 + z^2)) with rounded squares -- measured bit-exact on 512 random
+    // quaternions by tools/rigid_association_experiment.py (profiles/r02_rigid_association.json); the sequential order
+    // ((w^2 + x^2) + y^2) + z^2 matches only 85 % of them
+    float n = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(w, w), __fmul_rn(y, y)), __fadd_rn(__fmul_rn(x, x), __fmul_rn(z, z))));
     w = __fdiv_rn(w, n);
     x = __fdiv_rn(x, n);
     y = __fdiv_rn(y, n);
@@ -250,27 +252,43 @@ __device__ __forceinline__ void rs_ortho_J(const float p[3], const RsCam &c, RsP
     o.mx = c.fx * p[0] + c.cx;
     o.my = c.fy * p[1] + c.cy;
 }
-// Utils.cuh:618-655
+// Equidistant fisheye (replaces Utils.cuh:618-655): (u, v) = (fx s x + cx, fy s y + cy) with r = |(x, y)|, theta = atan2(r, z)
+// and s = theta / r.  Everything the Jacobian and its derivatives need is expressed through three scalars of the ray:
+//     s = theta / r,    w = 1 / (r^2 + z^2),    k = (z w - s) / r^2        (ds/dx = x k, ds/dy = y k, ds/dz = -w)
+// so that J = [[fx (s + x^2 k), fx x y k, -fx x w], [fy x y k, fy (s + y^2 k), -fy y w]].  Near the optical axis z w - s is a
+// difference of two numbers that agree to O(r^2): there the Taylor expansions in (r/z)^2 are used instead (the reference
+// keeps the cancellation and adds 1e-7 to r and x^2).
+struct RsFisheyeRay {
+    float s, w, k, r2;
+};
+__device__ __forceinline__ RsFisheyeRay rs_fisheye_ray(float x, float y, float z) {
+    RsFisheyeRay f;
+    f.r2 = x * x + y * y;
+    const float rho2 = f.r2 + z * z;
+    f.w = 1.f / rho2;
+    if (z > 0.f && f.r2 < 1e-4f * z * z) { // |r/z| < 0.01: series, relative error below 1e-9
+        const float iz = 1.f / z, q = f.r2 * iz * iz;
+        f.s = iz * (1.f - q * (1.f / 3.f - q * 0.2f));
+        f.k = -iz * iz * iz * (2.f / 3.f - q * 0.8f);
+    } else {
+        const float r = sqrtf(f.r2);
+        f.s = atan2f(r, z) / r;
+        f.k = (z * f.w - f.s) / f.r2;
+    }
+    return f;
+}
 __device__ __forceinline__ void rs_fisheye_J(const float p[3], const RsCam &c, RsProj &o) {
-    float x = p[0], y = p[1], z = p[2];
-    float eps = 0.0000001f;
-    float xy_len = sqrtf(x * x + y * y) + eps;
-    float theta = atan2f(xy_len, z + eps);
-    o.mx = x * c.fx * theta / xy_len + c.cx;
-    o.my = y * c.fy * theta / xy_len + c.cy;
-    float x2 = x * x + eps;
-    float y2 = y * y;
-    float xy = x * y;
-    float x2y2 = x2 + y2;
-    float x2y2z2_inv = 1.f / (x2y2 + z * z);
-    float b = atan2f(xy_len, z) / xy_len / x2y2;
-    float a = z * x2y2z2_inv / (x2y2);
-    o.J[0] = c.fx * (x2 * a + y2 * b);
-    o.J[3] = c.fy * xy * (a - b);
-    o.J[1] = c.fx * xy * (a - b);
-    o.J[4] = c.fy * (y2 * a + x2 * b);
-    o.J[2] = -c.fx * x * x2y2z2_inv;
-    o.J[5] = -c.fy * y * x2y2z2_inv;
+    const float x = p[0], y = p[1];
+    const RsFisheyeRay f = rs_fisheye_ray(x, y, p[2]);
+    o.mx = c.fx * f.s * x + c.cx;
+    o.my = c.fy * f.s * y + c.cy;
+    const float xyk = x * y * f.k;
+    o.J[0] = c.fx * (f.s + x * x * f.k);
+    o.J[1] = c.fx * xyk;
+    o.J[2] = -c.fx * x * f.w;
+    o.J[3] = c.fy * xyk;
+    o.J[4] = c.fy * (f.s + y * y * f.k);
+    o.J[5] = -c.fy * y * f.w;
 }
 
 // cov2d = J * cov3d * J^T, all four entries computed separately like glm (mat3x2 * mat3 * mat2x3).

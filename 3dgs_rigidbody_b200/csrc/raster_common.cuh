@@ -10,6 +10,9 @@ __device__ __forceinline__ void rs_cp_async4(void *smem, const void *gmem) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem) : "memory");
 }
+// waits for ALL of this thread's cp.async copies, committed to a group or not (the ring tracks its copies through
+// cp.async.mbarrier.arrive and never commits groups, so wait_group would not cover them)
+__device__ __forceinline__ void rs_cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 __device__ __forceinline__ void rs_cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void rs_cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");

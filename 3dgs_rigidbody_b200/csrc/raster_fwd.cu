@@ -193,7 +193,7 @@ rs_raster_fwd_kernel(const rs_raster_fwd_args a, const int ch_off, const int ch_
                 gnx[k] = (idx < range_end) ? a.flatten_ids[idx] : -1;
             }
         }
-        rs_cp_async_wait<0>(); // nothing may still be landing in shared memory when the CTA retires
+        rs_cp_async_wait_all(); // nothing may still be landing in shared memory when the CTA retires
         return;
     }
 
@@ -342,19 +342,19 @@ static int launch_raster_fwd(const rs_raster_fwd_args &a, int ch_off, int ch_cnt
     // 16-byte colour copies need aligned rows that fill the shared-memory pitch exactly
     const bool vec = (ch_cnt == Cfg::CP) && (a.channels % 4 == 0) && (ch_off % 4 == 0) &&
                      ((reinterpret_cast<uintptr_t>(a.colors) & 15) == 0);
-    static bool attr_done[2] = {false, false};
+    static RsPerDevice attr_done[2];
     if (vec) {
-        if (!attr_done[1]) {
+        if (!rs_dev_done(attr_done[1])) {
             RS_CUDA(cudaFuncSetAttribute(rs_raster_fwd_kernel<CDIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg::SMEM));
-            attr_done[1] = true;
+            rs_dev_mark(attr_done[1]);
         }
         rs_raster_fwd_kernel<CDIM, true><<<(unsigned)grid, RAST_THREADS, Cfg::SMEM, s>>>(a, ch_off, ch_cnt);
     } else {
-        if (!attr_done[0]) {
+        if (!rs_dev_done(attr_done[0])) {
             RS_CUDA(cudaFuncSetAttribute(rs_raster_fwd_kernel<CDIM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)Cfg::SMEM));
-            attr_done[0] = true;
+            rs_dev_mark(attr_done[0]);
         }
         rs_raster_fwd_kernel<CDIM, false><<<(unsigned)grid, RAST_THREADS, Cfg::SMEM, s>>>(a, ch_off, ch_cnt);
     }

@@ -372,12 +372,12 @@ static int radix_sort_impl(int64_t n_bound, const int32_t *n_dev, int begin_bit,
     RS_CHECK(n_bound < (int64_t)LB_VALUE, "rs_radix_sort_pairs: n must be below 2^30");
     const int nb = sort_nblocks(n_bound);
     uint32_t *ws = reinterpret_cast<uint32_t *>(workspace);
-    static bool attr_set[2] = {false, false};
+    static RsPerDevice attr_set[2];
     const int which = sizeof(KeyT) == 8 ? 1 : 0;
     const size_t smem = sizeof(SortSmem<KeyT>);
-    if (!attr_set[which]) {
+    if (!rs_dev_done(attr_set[which])) {
         RS_CUDA(cudaFuncSetAttribute(sort_pass_kernel<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[which] = true;
+        rs_dev_mark(attr_set[which]);
     }
     const int sms = rs_num_sms();
     if (!hist_ready) { // else: the producer of the keys already filled ws (rs_sort_ws_prepare + its own histogramming)

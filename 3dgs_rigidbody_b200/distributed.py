@@ -20,6 +20,8 @@ where autograd needs the transposed exchange.
 from __future__ import annotations
 
 import ctypes
+import os
+import socket
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -191,8 +193,32 @@ class PeerSplatExchange:
     All ranks of the group must call exchange() the same number of times (it is a collective)."""
 
     _instances: Dict[Tuple, "PeerSplatExchange"] = {}
+    _usable: Dict = {}  # process group -> bool (probed once, collectively)
     enabled: bool = True  # False routes no-grad packed calls through the NCCL all-to-all too (A/B measurements)
     initial_capacity: Optional[int] = None  # rows; None = this rank's row count of the first call (regrown on demand)
+    timeout_ms: int = int(os.environ.get("RS_EXCHANGE_TIMEOUT_MS", "0"))  # 0 = the library default (60 s)
+
+    @classmethod
+    def usable(cls, group, device: torch.device) -> bool:
+        """Collective probe, cached per group: the peer-memory route needs every rank on ONE host (CUDA IPC), peer access
+        between every pair of devices and at most RS_EXCHANGE_MAX_WORLD ranks.  Anything else (multi-node jobs, more than
+        16 ranks, GPUs without P2P) takes the NCCL all-to-all of GaussianShardExchange, as the reference does."""
+        key = id(group) if group is not None else None
+        if key in cls._usable:
+            return cls._usable[key]
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        ok = cls.enabled and world <= 16 and device.type == "cuda"
+        cards: List = [None] * world
+        dist.all_gather_object(cards, (socket.gethostname(), device.index if device.type == "cuda" else -1), group=group)
+        ok = ok and len({c[0] for c in cards}) == 1 and all(c[1] >= 0 for c in cards)
+        if ok:
+            for s, (_, idx) in enumerate(cards):
+                if s != rank and idx != device.index and not torch.cuda.can_device_access_peer(device.index, idx):
+                    ok = False
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        cls._usable[key] = bool(flag.item())
+        return cls._usable[key]
 
     @classmethod
     def get(cls, group, device: torch.device, channels: int) -> "PeerSplatExchange":
@@ -238,6 +264,7 @@ class PeerSplatExchange:
             a.world, a.rank, a.cameras_per_rank, a.channels = self.world, self.rank, cameras_per_rank, self.channels
             a.capacity, a.epoch = self.buffers.capacity, self.epoch
             a.colors_per_row, a.opacities_per_row = int(colors_per_row), int(opacities_per_row)
+            a.timeout_ms = int(self.timeout_ms)
             a.peer_base = self.buffers.table.data_ptr()
             (a.indptr, a.camera_ids, a.gaussian_ids, a.radii, a.means2d, a.depths, a.conics, a.opacities,
              a.colors) = [t.data_ptr() for t in keep]
@@ -248,10 +275,10 @@ class PeerSplatExchange:
                 _lib.check(self.lib.rs_exchange_push(ctypes.byref(a), stream))
                 _lib.check(self.lib.rs_exchange_wait(ctypes.byref(a), self.totals.data_ptr(), stream))
             got, worst, err, behind = self.totals.tolist()  # the one host sync of the exchange (sizes of the views)
-            if err == 1:
+            if err == 1:  # raised on EVERY rank of the group for this epoch (a rank that gave up sent no rows at all)
                 raise RuntimeError(f"PeerSplatExchange rank {self.rank} epoch {self.epoch}: a peer did not arrive within "
                                    f"the spin limit (data flags behind: {behind & 0xffff:#x}, count flags behind: "
-                                   f"{behind >> 16:#x})")
+                                   f"{behind >> 16:#x}); set RS_EXCHANGE_TIMEOUT_MS to wait longer")
             if err == 0:
                 break
             self._regrow(int(worst * 1.25) + 1024)  # identical decision on every rank: `worst` comes from the full matrix

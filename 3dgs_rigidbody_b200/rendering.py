@@ -8,7 +8,8 @@ the reference's:
     cluster_ids  int32 [N]   body index of every Gaussian (< 0: static background)
     body_quats   [K, 4]      per-body rotation, wxyz, normalised inside the kernel (main.py:207)
     body_trans   [K, 3]      per-body translation
-    body_centers [K, 3]      per-body pivot (apply_transform() rotates about the body's mean centre, main.py:210)
+    body_centers [K, 3]      per-body pivot; None = the mean of the body's Gaussian centres, as apply_transform() uses
+                             (main.py:210) -- computed per call, so an animation loop should pass it precomputed
 
 They replace the animation loop's per-body `apply_transform()` calls (main.py:366-400): the pose table is consumed inside
 the projection kernel, so no splat tensor is cloned and no extra pass over HBM is made.
@@ -165,6 +166,11 @@ def rasterization(
     Returns (render_colors [..., C, H, W, X], render_alphas [..., C, H, W, 1], meta); `meta` carries the reference's keys
     (rendering.py:455-468, 651-665) and `meta["means2d"]` is a grad-tracking non-leaf ([..., C, N, 2], or [nnz, 2] when
     packed) so that `retain_grad()` / `.absgrad` work as in the reference's training loop.
+
+    Lifetime note (distributed=True, packed=True, no gradients): the per-splat `meta` tensors (means2d, radii, depths,
+    conics, opacities, camera_ids, gaussian_ids) are then views of this rank's persistent peer-memory receive arrays
+    (distributed.PeerSplatExchange) and are overwritten by the NEXT distributed rasterization() call on this process
+    group; clone what must outlive it.
     """
     # ---- 0. validation -------------------------------------------------------------------------------------------------
     d = _Dims(means, viewmats)
@@ -186,7 +192,7 @@ def rasterization(
                   rolling_shutter, viewmats_rs)
     per_camera_colors = _check_colors(d, colors, sh_degree, distributed)
     assert not (absgrad and distributed), "AbsGrad is not supported in distributed mode."
-    rigid = make_rigid(cluster_ids, body_quats, body_trans, body_centers)
+    rigid = make_rigid(cluster_ids, body_quats, body_trans, body_centers, means)
     if rigid is not None:
         assert tuple(cluster_ids.shape) == (d.N,), cluster_ids.shape
     device = means.device
@@ -211,19 +217,35 @@ def rasterization(
     if peer_path:
         from .distributed import PeerSplatExchange
 
-        peer_path = PeerSplatExchange.enabled
+        # same host, peer access between all devices, <= 16 ranks -- else the NCCL route below (probed once per group)
+        peer_path = PeerSplatExchange.enabled and PeerSplatExchange.usable(shard.group, device)
 
-    # ---- 1. project (rigid transform fused in) ---------------------------------------------------------------------------
-    if peer_path:
-        from . import _C
-        from .wrapper import _CAMERA_MODELS
+    # ---- 1. project (rigid transform fused in; without gradients also the SH colours) -------------------------------------
+    from . import _C
+    from .wrapper import _CAMERA_MODELS
 
-        indptr, batch_ids, camera_ids, gaussian_ids, radii, means2d, depths, conics, compensations = (
-            _C.projection_ewa_3dgs_packed_fwd(
-                means.contiguous(), None if covars is None else covars.contiguous(),
-                None if quats is None else quats.contiguous(), None if scales is None else scales.contiguous(),
-                opacities.contiguous(), viewmats.contiguous(), Ks.contiguous(), width, height, eps2d, near_plane,
-                far_plane, radius_clip, rasterize_mode == "antialiased", _CAMERA_MODELS[camera_model], rigid))
+    # No gradient to carry: the view-dependent colours are evaluated INSIDE the projection kernel for the moved means (no
+    # eager-torch rigid transform, no torch.linalg.inv, no [C,N,3] dirs tensor, no separate SH pass) -- what main.py:328-339
+    # renders with (sh_degree=3).  Training keeps the differentiable spherical_harmonics() operator below.
+    fused_sh = (sh_degree is not None and not needs_grad and not per_camera_colors and means.is_cuda
+                and colors.dtype == torch.float32)
+    sh_arg = (colors.contiguous(), int(sh_degree)) if fused_sh else None
+    sh_rgb = None
+    if peer_path or (fused_sh and packed):
+        out = _C.projection_ewa_3dgs_packed_fwd(
+            means.contiguous(), None if covars is None else covars.contiguous(),
+            None if quats is None else quats.contiguous(), None if scales is None else scales.contiguous(),
+            opacities.contiguous(), viewmats.contiguous(), Ks.contiguous(), width, height, eps2d, near_plane,
+            far_plane, radius_clip, rasterize_mode == "antialiased", _CAMERA_MODELS[camera_model], rigid, None, sh_arg)
+        indptr, batch_ids, camera_ids, gaussian_ids, radii, means2d, depths, conics, compensations = out[:9]
+        sh_rgb = out[9] if fused_sh else None
+        projected = None
+    elif fused_sh:
+        radii, means2d, depths, conics, compensations, sh_rgb = _C.projection_ewa_3dgs_fused_fwd(
+            means.contiguous(), None if covars is None else covars.contiguous(),
+            None if quats is None else quats.contiguous(), None if scales is None else scales.contiguous(),
+            opacities.contiguous(), viewmats.contiguous(), Ks.contiguous(), width, height, eps2d, near_plane, far_plane,
+            radius_clip, rasterize_mode == "antialiased", _CAMERA_MODELS[camera_model], rigid, None, sh_arg)
         projected = None
     else:
         projected = fully_fused_projection(
@@ -236,18 +258,22 @@ def rasterization(
         alpha_in = None  # opacity x compensation is formed inside the exchange kernel
         image_ids = camera_ids
     elif packed:
-        batch_ids, camera_ids, gaussian_ids, radii, means2d, depths, conics, compensations = projected
+        if projected is not None:
+            batch_ids, camera_ids, gaussian_ids, radii, means2d, depths, conics, compensations = projected
         rows = (batch_ids, camera_ids, gaussian_ids)
         alpha_in = opacities.reshape(d.B, d.N)[batch_ids, gaussian_ids]  # [nnz]
         image_ids = batch_ids * d.C + camera_ids
     else:
-        radii, means2d, depths, conics, compensations = projected
+        if projected is not None:
+            radii, means2d, depths, conics, compensations = projected
         batch_ids = camera_ids = gaussian_ids = image_ids = rows = None
         alpha_in = opacities.unsqueeze(-2).expand(d.batch + (d.C, d.N))  # stride-0 view, consumed without a copy
     if compensations is not None and not peer_path:
         alpha_in = alpha_in * compensations
     # ---- 2. shade ----------------------------------------------------------------------------------------------------------
-    if peer_path and sh_degree is None and not per_camera_colors:
+    if sh_rgb is not None:
+        shaded = sh_rgb
+    elif peer_path and sh_degree is None and not per_camera_colors:
         shaded = None  # the exchange kernel gathers the colour row of each splat itself
     elif sh_degree is None:
         shaded = _plain_colors(d, colors, per_camera_colors, packed, rows)

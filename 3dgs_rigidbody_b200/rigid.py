@@ -37,23 +37,41 @@ def cluster_ids_from_groups(groups: Mapping[str, Sequence[int]], num_gaussians: 
 
 
 def body_centers(means: Tensor, cluster_ids: Tensor, K: int) -> Tensor:
-    """Per-body mean of the Gaussian centres: the pivot apply_transform() rotates about (main.py:210)."""
-    valid = cluster_ids >= 0
-    idx = cluster_ids[valid].long()
-    sums = torch.zeros(K, 3, dtype=means.dtype, device=means.device).index_add_(0, idx, means[valid])
-    cnt = torch.zeros(K, dtype=means.dtype, device=means.device).index_add_(
-        0, idx, torch.ones_like(idx, dtype=means.dtype))
-    return sums / cnt.clamp_min(1.0)[:, None]
+    """Per-body mean of the Gaussian centres: the pivot apply_transform() rotates about (main.py:210).
+
+    Evaluated exactly as the reference does for each body -- `means[body].mean(dim=0)` on the body's Gaussians in index
+    order -- so the pivots (and therefore the moved means) are bit-identical to the per-body apply_transform() chain; it is
+    a per-scene precomputation (K small reductions), not a per-frame step."""
+    out = torch.zeros(K, 3, dtype=means.dtype, device=means.device)
+    for k in range(K):
+        idx = torch.nonzero(cluster_ids == k).squeeze(-1)
+        if idx.numel() > 0:
+            out[k] = means[idx].mean(dim=0)
+    return out
+
+
+_mean_centers = body_centers  # make_rigid() has a parameter of the same name
 
 
 def make_rigid(cluster_ids: Optional[Tensor], body_quats: Optional[Tensor], body_trans: Optional[Tensor],
-               body_centers: Optional[Tensor] = None) -> Optional[RigidPoses]:
-    """Build the RigidPoses argument of the projection (None when no cluster ids are given)."""
+               body_centers: Optional[Tensor] = None, means: Optional[Tensor] = None) -> Optional[RigidPoses]:
+    """Build the RigidPoses argument of the projection (None when no cluster ids are given).
+
+    Without `body_centers` the pivot of every body is the mean of its Gaussian centres, as apply_transform() does
+    (main.py:210), computed here from `means` ([N,3]; one extra pass over the means per call -- an animation loop should
+    compute `body_centers(...)` once and pass it).  The poses are not differentiable: the kernels chain the gradients of
+    the means / quats through the pose but produce none for the pose itself, so a pose that requires grad is rejected
+    instead of silently getting no gradient."""
     if cluster_ids is None:
         assert body_quats is None and body_trans is None, "body poses given without cluster_ids"
         return None
     assert body_quats is not None and body_trans is not None, "cluster_ids requires body_quats and body_trans"
+    if torch.is_grad_enabled() and (body_quats.requires_grad or body_trans.requires_grad):
+        raise RuntimeError("body_quats / body_trans require grad, but the fused rigid transform has no pose gradient; "
+                           "detach them (gradients still flow to means / quats through the pose)")
     dev = cluster_ids.device
+    if body_centers is None and means is not None and means.dim() == 2:
+        body_centers = _mean_centers(means.detach(), cluster_ids.to(means.device), body_quats.shape[0])
     return RigidPoses(
         cluster_ids.to(torch.int32).contiguous(),
         body_quats.to(device=dev, dtype=torch.float32).contiguous(),

@@ -10,21 +10,28 @@ Workload (BASELINE.json configs[1]): synthetic domino scen
 tile-intersect + radix sort -> front-to-back compositing (the commented-out loop of the reference, main.py:357-409:
 apply_transform() per body + rasterization()).
 
-  value     frames/s over all ranks, everything resident in HBM (poses [240,K,.] pre-generated on the device),
-            K frames enqueued back to back through FramePipeline (`--in-flight` frames per GPU, one stream + workspace
-            each, so the latency-bound binning of one frame overlaps the compositing of another), CUDA events on the
-            launching stream, max over ranks.
-  e2e       frames/s through the public per-frame API (FrameRenderer.render -> C ABI rs_render_frame) with HOST inputs
-            and HOST results: per step the frame's poses + camera are copied from pinned host memory and the rendered
-            float32 image [H,W,3] is copied back to pinned host memory (what the reference's loop keeps,
-            main.py:387-400); copies are inside the timed region.  At ~25 MB per frame this leg is PCIe-bound.
-  roofline  the dominant HBM-bound kernel of the step (radix-sort scatter pass), timed live with CUDA events.
-  stages    per-stage CUDA-event times of one frame through the separate C-ABI entry points, with achieved GB/s against
-            the algorithmic bytes of SURVEY.md section 8(d) -- explains `value`.
+  value     frames/s over all ranks, everything resident in HBM (poses [240,K,.] pre-generated on the device), K frames
+            enqueued back to back through FramePipeline (`--in-flight` frames per GPU, one stream + workspace each, so the
+            latency-bound binning of one frame overlaps the compositing of another), CUDA events, max over ranks.
+  e2e       frames/s through the public per-frame API (FrameRenderer.render -> C ABI rs_render_frame) with HOST inputs and
+            HOST results: per step the frame's poses + camera are copied from pinned host memory and the rendered frame is
+            copied back to pinned host memory as the 8-bit RGB image the reference's loop stores (main.py:140-171
+            save_rendered_image -> torchvision save_image quantisation, done here by the compositing epilogue); copies are
+            inside the timed region.  `e2e_f32` is the same loop reading back the float32 image.  Both are reported against
+            the box's pinned device->host copy ceiling measured in the same run at the same rank count (`d2h_ceiling`).
+  roofline  the kernel with the largest share of the step (compositing), timed live per kernel with CUDA events behind every
+            launch (rs_profile_begin/_end); `kernels` lists EVERY kernel of the frame with the bytes it actually moves.
+  ref_cuda  the reference's own python + CUDA kernels (baseline/_ref + oracle/_ref, unmodified) on the same B200 and the
+            same frames: apply_transform() per body + rasterization() -- "the number to beat" (SURVEY.md 8d).
   cpu_baseline  the CPU port of the reference path (oracle/, OpenMP, all host threads) on a bounded sample of frames.
+  other_configs  c3 (16 identity channels fwd+bwd), the drop-in rasterization() API on c2 (incl. main.py's sh_degree=3 /
+            RGB+ED call), c4 (6 M Gaussians / 500 bodies / 8 cameras at 4K, cameras sharded over the ranks) and c5
+            (20 M Gaussians sharded over the ranks, projected splats exchanged over NVLink peer memory and over NCCL, with a
+            sharded == single-GPU image check) -- the multi-GPU configs run at every --gpus N.
 
-Multi-GPU: frames shard across ranks (rank r renders frames r, r+P, ...), Gaussians replicated, no collective on the
-data path ("weak" scaling: every rank renders K frames).  `--impl reference` times the oracle port on the host cores.
+Multi-GPU (c2): frames shard across ranks with no collective on the data path.  Every rank renders the SAME set of K
+animation frames (rotated by rank), so per-rank work does not depend on N ("weak" scaling: N x K frames in total).
+`--impl reference` times the oracle port on the host cores (rank 0 only).
 """
 from __future__ import annotations
 
@@ -138,8 +145,21 @@ def domino_poses_np(n_bodies=N_BODIES, frames=None, centers=None):
 
 
 def frames_of_rank(rank, world, count, start=0):
-    """Animation frames rendered by `rank`: start + rank, start + rank + world, ... (`count` of them, modulo 240)."""
+    """A 240-frame job sharded over `world` ranks: rank r owns frames start + r, start + r + world, ... (FrameRenderer
+    multi-GPU mode; every frame exactly once)."""
     return [(start + rank + world * i) % N_FRAMES for i in range(count)]
+
+
+BENCH_FRAME_STRIDE = 7  # the K timed frames are spread over the animation (frame 5, 12, 19, ...)
+
+
+def bench_frames(rank, count, start=5):
+    """The frames bench.py times: the SAME set of `count` animation frames on every rank and for every --gpus N (so the
+    per-rank work is identical at 1, 2, 4 and 8 GPUs and the driver's scaling efficiency compares like with like), rotated
+    by rank so that the ranks are not in lock step."""
+    base = [(start + BENCH_FRAME_STRIDE * i) % N_FRAMES for i in range(count)]
+    r = rank % max(count, 1)
+    return base[r:] + base[:r]
 
 
 def make_domino_scene(n_gauss=N_GAUSS, n_bodies=N_BODIES, device="cuda:0", **kw):
@@ -237,12 +257,23 @@ def run_cpu_port(sc, frames, budget_s=None):
     return times, oracle.num_threads()
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# shared by both arms: the identity of the workload (identical `config` dicts => the driver's same_config check holds)
+# ----------------------------------------------------------------------------------------------------------------------
+def base_config():
+    return {"workload": WORKLOAD, "gaussians": N_GAUSS, "bodies": N_BODIES, "width": WIDTH, "height": HEIGHT, "channels": 3,
+            "frames": f"the same K animation frames on every rank: 5, {5 + BENCH_FRAME_STRIDE}, {5 + 2 * BENCH_FRAME_STRIDE}, ... "
+                      "(stride 7, modulo 240), rotated by rank",
+            "l2": "per-frame working set (Gaussians 60 MB + projected 68 MB + keys/values >= 120 MB + images 41 MB) exceeds "
+                  "the 126 MB L2 and every frame has new poses; no explicit flush"}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     sc = make_domino_scene_np()
-    frames = [(60 + 7 * i) % N_FRAMES for i in range(args.warmup + args.steps)]
+    frames = bench_frames(0, args.warmup + args.steps)
     times, threads = run_cpu_port(sc, frames)
     timed = times[args.warmup:]
     fps = len(timed) / sum(timed)
@@ -251,10 +282,9 @@ def reference_arm(args):
         "impl": "reference", "metric": "frames/sec (1M Gaussians, 1080p, rigid-animated)", "value": fps,
         "unit": "frames/s", "n_gpus": args.gpus, "steps": len(timed), "warmup": args.warmup,
         "ms_per_step": 1e3 * sum(timed) / len(timed), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "gaussians": N_GAUSS, "bodies": N_BODIES, "width": WIDTH, "height": HEIGHT,
-                   "arm": "CPU port of the reference path (oracle/oracle.c, OpenMP); the reference's own python CPU "
-                          "path cannot travel to the GPU box and cannot composite without its CUDA extension"},
+        "dtype": "f32", "data": "synthetic", "config": base_config(),
+        "arm": "CPU port of the reference path (oracle/oracle.c, OpenMP, all host threads); the reference's own python CPU "
+               "path cannot composite without its CUDA extension (SURVEY.md 8c)",
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -266,84 +296,229 @@ def reference_arm(args):
 # ----------------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------------
-def stage_breakdown(fr, sc, q_all, t_all, frames, peak_gbs, peak_src, n_tiles):
-    """Per-stage CUDA-event times of the SAME frames through the frame path itself (rs_render_frame_timed records events
-    between the stages of rs_render_frame).  Returns (stages, roofline): `stages` lists every stage with its algorithmic
-    bytes (SURVEY.md section 8d formulas, with this scene's measured M) and achieved GB/s; `roofline` is the dominant
-    kernel of the step (compositing: one launch of rs_raster_fwd_kernel per frame)."""
-    ms = np.array([fr.render_timed(sc["viewmats"], sc["Ks"], q_all[f], t_all[f]) for f in frames], np.float64)
-    mean = ms.mean(0)
+def _timed_ms(torch, fn, steps, warm=3):
+    """ms per call of fn(i): `warm` untimed calls, then `steps` calls between two CUDA events on the current stream."""
+    for i in range(warm):
+        fn(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        fn(warm + i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def kernel_rooflines(rs, _lib, fr, sc, q_all, t_all, frames, peak_gbs, peak_src, n_tiles):
+    """Per-KERNEL times of the frames through rs_render_frame itself, measured live: one CUDA event behind every kernel
+    launch (rs_profile_begin / rs_profile_end).  Every kernel gets the bytes it actually has to move
+    and its achieved GB/s against the measured HBM peak.  Returns (kernels, stages, roofline, frame_ms, M)."""
+    import torch
+
+    stream = torch.cuda.current_stream().cuda_stream
+    per_frame = []
+    for f in frames:
+        rows = _lib.profile_kernels(lambda: fr.render(sc["viewmats"], sc["Ks"], q_all[f], t_all[f]), stream)
+        per_frame.append(rows)
+    M = fr.n_isects()
     N, D, C = fr.N, fr.D, fr.C
     E, P = C * N, C * fr.W * fr.H
-    M = fr.n_isects()
-    key_bits = 32 + int(n_tiles).bit_length() + int(C).bit_length()
-    ref_passes = (key_bits + 7) // 8
-    tile_passes = (key_bits - 32 + 7) // 8
-    alg = {
-        "rigid+project": N * 48 + E * 32,
-        # what the reference's count + cumsum + emission + 64-bit cub sort + offsets move (SURVEY 8d)
-        "binning": E * 32 + (E * 20 + M * 12) + (M * 8 + ref_passes * 2 * M * 12) + (M * 8 + n_tiles * C * 4),
-        "composite": M * (4 + 28 + 4 * D) + P * (D + 2) * 4,
-    }
-    # what the depth-ordered scheme actually has to move: depth sort (hist + 4 passes of 8-byte pairs), ordered count
-    # and emission, tile sort (hist + passes of 8-byte pairs), offsets
-    moved_binning = E * 4 + 4 * E * 16 + E * 8 + (E * 24 + M * 8) + M * 4 + tile_passes * M * 16 + M * 4
+    names = [n for n, _ in per_frame[0]]
+    assert all([n for n, _ in rows] == names for rows in per_frame), "kernel sequence differs between frames"
+    mean_ms = np.mean([[ms for _, ms in rows] for rows in per_frame], axis=0)
+    tile_bits = int(n_tiles).bit_length() + int(C).bit_length()
+    # bytes each launch has to move, keyed by (kernel name, occurrence index of that name inside the frame)
+    n_tile_passes = (tile_bits + 7) // 8
+    V = min(E, M)  # visible elements (an upper bound is enough for the byte counts: every visible element has >= 1 tile)
+    seen = {}
+    kernels = []
+    for name, ms in zip(names, mean_ms):
+        k = seen.get(name, 0)
+        seen[name] = k + 1
+        what, nbytes = name, None
+        if name.startswith("rs_project_fwd"):
+            what, nbytes = "rigid transform + EWA projection + tile count + compositing records", N * 48 + E * 68
+        elif name == "rs_dord_minmax_kernel":
+            what, nbytes = "depth order 1/5: min / max of the visible depth bits", E * 8
+        elif name == "rs_dord_count_kernel":
+            what, nbytes = "depth order 2/5: histogram over 65536 range-adapted depth buckets", E * 8 + V * 4
+        elif name == "rs_dord_scan_kernel":
+            what, nbytes = "depth order 3/5: scan of the bucket counts, sort-group boundaries (1 CTA)", 65536 * 8
+        elif name == "rs_dord_scatter_kernel":
+            what, nbytes = "depth order 4/5: scatter of (depth bits, id) composites into their buckets", E * 8 + V * 12
+        elif name == "rs_dord_sort_kernel":
+            what, nbytes = "depth order 5/5: per-group bitonic sort in shared memory -> ids in depth order", V * 12
+        elif name == "sort_pass_kernel":
+            what = f"tile-key radix pass {k + 1}/{n_tile_passes} ((image|tile, id) pairs)"
+            nbytes = M * 16
+        elif name == "rs_bin_count_kernel":
+            what, nbytes = "tile counts gathered in depth order -> block sums", E * 8
+        elif name == "rs_isect_scan_kernel":
+            what, nbytes = "exclusive scan of the block sums (1 CTA)", (E // 1024 + 1) * 8
+        elif name == "rs_bin_emit_kernel":
+            what, nbytes = "emission of (image|tile, id) pairs in depth order + tile-key histograms", E * 24 + M * 8
+        elif name == "rs_isect_offsets_kernel":
+            what, nbytes = "per-tile offsets from the sorted tile keys", M * 4 + n_tiles * C * 4
+        elif name == "rs_raster_fwd_kernel":
+            what, nbytes = "front-to-back compositing (SURVEY 8d algorithmic bytes)", M * (4 + 28 + 4 * D) + P * (D + 2) * 4
+        row = {"kernel": name, "what": what, "ms": round(float(ms), 4)}
+        if nbytes is not None:
+            gbs = nbytes / (float(ms) * 1e-3) / 1e9
+            row.update(bytes=int(nbytes), GBps=round(gbs, 1), frac_of_hbm_peak=round(gbs / peak_gbs, 4))
+        kernels.append(row)
+    total = float(mean_ms.sum())
+    for row in kernels:
+        row["share_of_frame"] = round(row["ms"] / total, 4)
+    stage_of = lambda n: ("rigid+project" if n.startswith("rs_project") else "composite" if n.startswith("rs_raster") else "binning")
     stages = []
-    for k, name in enumerate(("rigid+project", "binning", "composite")):
-        t = float(mean[k]) * 1e-3
-        st = {"stage": name, "ms": round(float(mean[k]), 4), "algorithmic_MB": round(alg[name] / 1e6, 1),
-              "GBps": round(alg[name] / t / 1e9, 1), "frac_of_hbm_peak": round(alg[name] / t / 1e9 / peak_gbs, 4)}
-        if name == "binning":
-            st["bytes_actually_moved_MB"] = round(moved_binning / 1e6, 1)
-            st["GBps_actually_moved"] = round(moved_binning / t / 1e9, 1)
-            st["note"] = ("algorithmic bytes = the reference's 64-bit LSD sort accounting (SURVEY 8d); the depth-ordered "
-                          "scheme moves far fewer bytes, so the first fraction may exceed what the kernels stream")
-        stages.append(st)
-    t_c = float(mean[2]) * 1e-3
-    achieved = alg["composite"] / t_c / 1e9
+    for st in ("rigid+project", "binning", "composite"):
+        rows = [r for r in kernels if stage_of(r["kernel"]) == st]
+        ms = sum(r["ms"] for r in rows)
+        nb = sum(r.get("bytes", 0) for r in rows)
+        stages.append({"stage": st, "ms": round(ms, 4), "kernels": len(rows), "bytes_moved_MB": round(nb / 1e6, 1),
+                       "GBps": round(nb / (ms * 1e-3) / 1e9, 1), "frac_of_hbm_peak": round(nb / (ms * 1e-3) / 1e9 / peak_gbs, 4)})
+    top = max(kernels, key=lambda r: r["ms"])
+    traffic, traffic_src = None, "no ncu capture of this build under profiles/ (profiles/r02_kernel_traffic.json)"
+    tpath = os.path.join(ROOT, "profiles", "r02_kernel_traffic.json")
+    if os.path.exists(tpath):  # dram__bytes_read.sum + dram__bytes_write.sum per launch from one `ncu --set full` capture
+        try:
+            tj = json.load(open(tpath))
+            if top["kernel"] in tj.get("kernels", {}):
+                traffic = tj["kernels"][top["kernel"]]["dram_bytes_per_launch"]
+                traffic_src = f"profiles/r02_kernel_traffic.json ({tj.get('source', 'ncu --set full')}); static profile data, not measured in this run"
+        except (OSError, ValueError, KeyError):
+            pass
     roofline = {
-        "bound": "hbm", "kernel": "rs_raster_fwd_kernel (compositing, 1 launch/frame: the largest share of the step)",
-        "achieved": round(achieved, 1), "peak": peak_gbs, "unit": "GB/s", "frac": round(achieved / peak_gbs, 4),
-        "traffic": 61.26e6, "traffic_source": "ncu --set full r01 (profiles/r01_frame_kernels_ncu_full.txt): dram read 48.80 MB + write 12.46 MB per launch",
-        "peak_source": peak_src, "algorithmic_bytes_per_launch": alg["composite"], "ms_per_launch": round(float(mean[2]), 4),
-        "frames_timed": int(len(frames)),
-        "note": "this kernel is bound by SM issue (FP32 FMA + MUFU.EX2 + LDS), not by HBM: 66 % issue-slot utilisation, "
-                "1.09e8 warp instructions per launch, 4 % DRAM throughput (profiles/r01_frame_kernels_ncu_full.txt); the gathers "
-                "hit in L2, so DRAM traffic is far BELOW the algorithmic bytes; the other stages are in `stages`",
-        "issue_slot_utilisation": 0.662,
+        "bound": "hbm", "kernel": f"{top['kernel']} ({top['what']}; 1 launch/frame, {top['share_of_frame']:.0%} of the frame's kernel time)",
+        "achieved": top.get("GBps"), "peak": peak_gbs, "unit": "GB/s", "frac": top.get("frac_of_hbm_peak"),
+        "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": top.get("bytes"), "ms_per_launch": top["ms"], "frames_timed": int(len(frames)),
+        "timing": "CUDA events behind every kernel launch on the launching stream (rs_profile_begin/_end), mean over the timed frames",
+        "limiter": "SM issue (FP32 FMA + MUFU.EX2 + LDS) and per-tile latency, not HBM: the roofline fraction of this kernel says how "
+                   "far it is from being bandwidth-bound; the HBM-bound kernels of the frame are listed in `kernels`",
     }
-    return stages, roofline, float(mean[3]), M
+    return kernels, stages, roofline, total, M
 
 
-def other_configs(rs, sc, q_all, t_all, steps=10):
-    """Extra information next to the c2 headline (not the metric): the same scene through the drop-in `rasterization()` call
-    (operator path, with the host reads the reference API implies), and BASELINE configs[2] (c3): 16 identity-feature
-    channels, forward + backward, plus the contrastive clustering loss on the rendered map.  CUDA events, ms per step."""
+def d2h_ceiling(torch, dist, dev, nbytes=64 << 20, reps=8):
+    """Aggregate pinned device->host copy bandwidth of this box with all ranks copying at once (GB/s): the roof of `e2e`."""
+    src = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    dst = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    for _ in range(2):
+        dst.copy_(src, non_blocking=True)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        dst.copy_(src, non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    world = dist.get_world_size() if dist is not None else 1
+    return world * nbytes * reps / (float(t[0]) * 1e-3) / 1e9
+
+
+def ref_cuda_leg(sc, q_all, t_all, frames, steps=10):
+    """The reference's OWN python and CUDA kernels on this GPU and these frames ("that, not the CPU, is the
+    number to beat"): per frame, apply_transform() (main.py:183-228) once per body on that body's Gaussians, then
+    gsplat.rendering.rasterization(packed=False) (rendering.py:33-770) on its compiled extension.  Unmodified reference
+    code from baseline/_ref + oracle/_ref; measurement infrastructure only."""
+    import importlib.util
+
+    import torch
+
+    so = os.path.join(ROOT, "oracle", "_ref", "gsplat_ref_cuda.so")
+    inst = os.path.join(ROOT, "baseline", "install_ref.py")
+    if not os.path.exists(so):
+        return {"unavailable": "oracle/_ref/gsplat_ref_cuda.so not built (needs /root/reference at build time)"}
+    spec = importlib.util.spec_from_file_location("install_ref", inst)
+    refpy = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(refpy)
+    if not refpy.available():
+        return {"unavailable": "baseline/_ref not installed (needs /root/reference at build time)"}
+    spec = importlib.util.spec_from_file_location("gsplat_ref_cuda", so)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    gs = refpy.load_reference(ref)
+    fns = refpy.reference_functions("main.py", ["apply_transform", "quat_multiply"])
+    K = q_all.shape[1]
+    body_idx = [torch.nonzero(sc["cluster_ids"] == k).squeeze(-1) for k in range(K)]
+    splats = {"means": sc["means"], "quats": sc["quats"]}
+
+    def animate(f):
+        means, quats = sc["means"].clone(), sc["quats"].clone()
+        for k in range(K):
+            part = {n: v[body_idx[k]] for n, v in splats.items()}
+            moved = fns["apply_transform"](part, t_all[f, k], q_all[f, k])
+            means[body_idx[k]] = moved["means"]
+            quats[body_idx[k]] = moved["quats"]
+        return means, quats
+
+    def render(m, q):
+        return gs.rendering.rasterization(m, q, sc["scales"], sc["opacities"], sc["colors"], sc["viewmats"], sc["Ks"], WIDTH,
+                                          HEIGHT, packed=False)
+
+    fl = list(frames)
+    with torch.no_grad():
+        t_anim = _timed_ms(torch, lambda i: animate(fl[i % len(fl)]), steps)
+        m, q = animate(fl[0])
+        t_render = _timed_ms(torch, lambda i: render(m, q), steps)
+        t_frame = _timed_ms(torch, lambda i: render(*animate(fl[i % len(fl)])), steps)
+        # per operator, on the moved splats of one frame
+        C_ = ref
+        tw, th = (WIDTH + 15) // 16, (HEIGHT + 15) // 16
+        pa = (m, None, q, sc["scales"], sc["opacities"], sc["viewmats"], sc["Ks"], WIDTH, HEIGHT, 0.3, 0.01, 1e10, 0.0, False)
+        radii, means2d, depths, conics, _ = C_.projection_ewa_3dgs_fused_fwd(*pa, C_.PINHOLE)
+        tpg, ids, flat = C_.intersect_tile(means2d, radii, depths, None, None, 1, 16, tw, th, True, False)
+        off = C_.intersect_offset(ids, 1, tw, th)
+        colors, opac = sc["colors"][None].contiguous(), sc["opacities"][None].contiguous()
+        ops = {
+            "projection_ewa_3dgs_fused_fwd": _timed_ms(torch, lambda i: C_.projection_ewa_3dgs_fused_fwd(*pa, C_.PINHOLE), steps),
+            "intersect_tile (count + cumsum + emit + cub 64-bit sort, 1 host sync)": _timed_ms(
+                torch, lambda i: C_.intersect_tile(means2d, radii, depths, None, None, 1, 16, tw, th, True, False), steps),
+            "intersect_offset": _timed_ms(torch, lambda i: C_.intersect_offset(ids, 1, tw, th), steps),
+            "rasterize_to_pixels_3dgs_fwd": _timed_ms(torch, lambda i: C_.rasterize_to_pixels_3dgs_fwd(
+                means2d, conics, colors, opac, None, None, WIDTH, HEIGHT, 16, off, flat), steps),
+        }
+    return {
+        "what": "UNMODIFIED reference python (baseline/_ref: main.py apply_transform per body + gsplat.rendering.rasterization, "
+                "packed=False) on the reference's own CUDA extension (oracle/_ref), same GPU, same frames; ms per frame, CUDA events",
+        "frame_ms": round(t_frame, 4), "frames_per_s": round(1e3 / t_frame, 2),
+        "apply_transform_per_body_ms": round(t_anim, 4), "rasterization_ms": round(t_render, 4),
+        "operators_ms": {k: round(v, 4) for k, v in ops.items()}, "kernels_only_ms": round(sum(ops.values()), 4),
+        "n_isects": int(ids.numel()), "steps": steps,
+    }
+
+
+def c2_api_configs(rs, sc, q_all, t_all, frames, steps=10):
+    """The c2 scene through the drop-in `rasterization()` signature (operator path, with the host reads the reference API
+    implies), including main.py:328-339's own configuration (sh_degree=3, render_mode="RGB+ED", packed=False), and
+    BASELINE configs[2] (c3): 16 identity-feature channels, forward + backward, plus the contrastive clustering loss and the
+    segmentation-head MLP of the identity step.  CUDA events, ms per step."""
     import torch
 
     dev = sc["means"].device
-
-    def timed(fn):
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(steps):
-            fn(i)
-        e1.record()
-        torch.cuda.synchronize()
-        return round(e0.elapsed_time(e1) / steps, 4)
-
-    rigid = lambda f: dict(cluster_ids=sc["cluster_ids"], body_quats=q_all[f], body_trans=t_all[f],
+    fl = list(frames)
+    rigid = lambda i: dict(cluster_ids=sc["cluster_ids"], body_quats=q_all[fl[i % len(fl)]], body_trans=t_all[fl[i % len(fl)]],
                            body_centers=sc["body_centers"])
     base = (sc["means"], sc["quats"], sc["scales"], sc["opacities"])
     out = {}
     with torch.no_grad():
-        out["c2_rasterization_api_ms"] = timed(lambda i=0: rs.rasterization(
-            *base, sc["colors"], sc["viewmats"], sc["Ks"], WIDTH, HEIGHT, packed=False, **rigid(60 + i)))
-        out["c2_rasterization_api_packed_ms"] = timed(lambda i=0: rs.rasterization(
-            *base, sc["colors"], sc["viewmats"], sc["Ks"], WIDTH, HEIGHT, packed=True, **rigid(60 + i)))
+        out["c2_rasterization_api_ms"] = round(_timed_ms(torch, lambda i: rs.rasterization(
+            *base, sc["colors"], sc["viewmats"], sc["Ks"], WIDTH, HEIGHT, packed=False, **rigid(i)), steps), 4)
+        out["c2_rasterization_api_packed_ms"] = round(_timed_ms(torch, lambda i: rs.rasterization(
+            *base, sc["colors"], sc["viewmats"], sc["Ks"], WIDTH, HEIGHT, packed=True, **rigid(i)), steps), 4)
+        g = torch.Generator(device=dev).manual_seed(7)
+        sh = torch.randn(sc["means"].shape[0], 16, 3, device=dev, generator=g) * 0.2
+        out["c2_main_py_call_sh3_rgb_ed_ms"] = round(_timed_ms(torch, lambda i: rs.rasterization(
+            *base, sh, sc["viewmats"], sc["Ks"], WIDTH, HEIGHT, packed=False, sh_degree=3, render_mode="RGB+ED",
+            near_plane=0.01, far_plane=1e10, **rigid(i)), steps), 4)
+        del sh
     g = torch.Generator(device=dev).manual_seed(42)
     feats = torch.randn(sc["means"].shape[0], 16, device=dev, generator=g).requires_grad_()
     w = torch.rand(1, HEIGHT, WIDTH, 16, device=dev, generator=g)
@@ -352,10 +527,10 @@ def other_configs(rs, sc, q_all, t_all, steps=10):
     def c3_step(i=0):
         for t in leaves + [feats]:
             t.grad = None
-        img, _, _ = rs.rasterization(*leaves, feats, sc["viewmats"], sc["Ks"], WIDTH, HEIGHT, packed=False, **rigid(60 + i))
+        img, _, _ = rs.rasterization(*leaves, feats, sc["viewmats"], sc["Ks"], WIDTH, HEIGHT, packed=False, **rigid(i))
         (img * w).sum().backward()
 
-    out["c3_fwd_bwd_16ch_ms"] = timed(c3_step)
+    out["c3_fwd_bwd_16ch_ms"] = round(_timed_ms(torch, c3_step, steps), 4)
     # instance mask: one box per domino in screen space is not available here; a 6 x 4 grid of instances stands in
     mask = torch.zeros(HEIGHT, WIDTH, dtype=torch.long, device=dev)
     for a in range(4):
@@ -368,7 +543,172 @@ def other_configs(rs, sc, q_all, t_all, steps=10):
         fmap.grad = None
         rs.cgc_contrastive_clustering_loss(fmap, mask, tables=tables).backward()
 
-    out["c3_contrastive_loss_fwd_bwd_ms"] = timed(cgc_step)
+    out["c3_contrastive_loss_fwd_bwd_ms"] = round(_timed_ms(torch, cgc_step, steps), 4)
+    return out
+
+
+def bench_c4(rs, torch, dist, dev, rank, world, frames=6, warmup=1, in_flight=3):
+    """c4 (BASELINE configs[3]): 6 M Gaussians, 500 rigid bodies, 8 ring cameras at 3840x2160.  The 8 cameras of every
+    animation frame are sharded over the ranks (camera c of frame f -> rank (c + f) % world: every rank sees every viewpoint,
+    so the busiest one does not pin a rank), Gaussians replicated, NO collective on the data path.  camera-frames/s over all
+    ranks (CUDA events, max over ranks); at world 1 one GPU renders all 8 cameras."""
+    W, H, N, K, C = 3840, 2160, 6_000_000, 500, 8
+    sc = make_domino_scene(N, K, device=dev, width=W, height=H, n_cameras=C)
+    q_np, t_np = domino_poses_np(K, None, sc["body_centers"].cpu().numpy())
+    q_all, t_all = torch.from_numpy(q_np).to(dev), torch.from_numpy(t_np).to(dev)
+    cams_of = lambda f: [c for c in range(C) if (c + f) % world == rank]
+    pipe = rs.FramePipeline(in_flight, sc["means"], sc["quats"], sc["scales"], sc["opacities"], sc["colors"], W, H,
+                            cluster_ids=sc["cluster_ids"], body_centers=sc["body_centers"], max_isects=96_000_000)
+
+    def run(fs):
+        for f in fs:
+            for c in cams_of(f):
+                pipe.submit(sc["viewmats"][c:c + 1], sc["Ks"][c:c + 1], q_all[f % N_FRAMES], t_all[f % N_FRAMES])
+        pipe.join()
+
+    run(range(60, 60 + warmup))
+    torch.cuda.synchronize()
+    ok = not pipe.overflowed()
+    # replicas must agree: every rank renders camera 0 of frame 60 and the checksums are compared
+    img, _, done = pipe.submit(sc["viewmats"][0:1], sc["Ks"][0:1], q_all[60], t_all[60])
+    pipe.join()
+    torch.cuda.synchronize()
+    chk = torch.stack([img.double().sum(), img.double().abs().max()])
+    if dist is not None:
+        allc = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        replicas_equal = all(bool(torch.equal(allc[0], c)) for c in allc)
+        dist.barrier()
+    else:
+        replicas_equal = True
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run(range(60 + warmup, 60 + warmup + frames))
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    n_is = torch.tensor([float(pipe.renderers[0].n_isects())], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.barrier()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n_is, op=dist.ReduceOp.SUM)
+    ms = float(t[0])
+    del pipe, sc
+    torch.cuda.empty_cache()
+    return {"workload": "c4: 6M Gaussians, 500 bodies, 8 ring cameras 3840x2160; the cameras of each animation frame sharded over the ranks, no collective",
+            "n_gpus": world, "animation_frames": frames, "camera_frames": frames * C,
+            "ms_per_animation_frame": round(ms / frames, 3), "camera_frames_per_s": round(frames * C / (ms * 1e-3), 2),
+            "n_isects_sample_camera_mean": int(float(n_is[0]) / world), "workspace_ok": bool(ok),
+            "replica_checksums_equal_across_ranks": bool(replicas_equal)}
+
+
+def _c5_scene(torch, dev, n_total, lo, hi, seed=1234):
+    """Gaussians [lo, hi) of the c5 scene: uniform in a 40 x 40 x 4 slab.  Generated in fixed blocks of 1 M
+    with a per-block seed, so any shard of any world size sees exactly the values of the single-GPU scene."""
+    BLOCK = 1_000_000
+    parts = {k: [] for k in ("means", "quats", "scales", "opac", "colors")}
+    for b in range(lo // BLOCK, (max(hi, lo + 1) - 1) // BLOCK + 1):
+        g = torch.Generator(device=dev).manual_seed(seed + b)
+        n = min(BLOCK, n_total - b * BLOCK)
+        blk = {
+            "means": (torch.rand(n, 3, device=dev, generator=g) - 0.5) * torch.tensor([40.0, 40.0, 4.0], device=dev),
+            "quats": torch.nn.functional.normalize(torch.randn(n, 4, device=dev, generator=g), dim=-1),
+            "scales": torch.rand(n, 3, device=dev, generator=g) * 0.02,
+            "opac": torch.rand(n, device=dev, generator=g),
+            "colors": torch.rand(n, 3, device=dev, generator=g),
+        }
+        a, z = max(lo - b * BLOCK, 0), min(hi - b * BLOCK, n)
+        for k in parts:
+            parts[k].append(blk[k][a:z])
+    return {k: torch.cat(v).contiguous() for k, v in parts.items()}
+
+
+def _c5_cameras(torch, dev, n_cams, W, H):
+    vms = np.stack([look_at((30 * math.cos(2 * math.pi * c / n_cams), 30 * math.sin(2 * math.pi * c / n_cams), 12.0), (0, 0, 0))
+                    for c in range(n_cams)])
+    f = 0.5 * W / math.tan(math.radians(30.0))
+    Ks = np.tile(np.array([[[f, 0, W / 2], [0, f, H / 2], [0, 0, 1]]], np.float32), (n_cams, 1, 1))
+    return torch.from_numpy(vms).to(dev), torch.from_numpy(Ks).to(dev)
+
+
+def bench_c5(rs, torch, dist, dev, rank, world, n_total=20_000_000, steps=5, warmup=2, n_cams=8):
+    """c5 (BASELINE configs[4]): 20 M Gaussians sharded over the ranks (contiguous blocks), 8 ring cameras at 1080p owned
+    8 / world per rank; every rank projects ITS Gaussians to ALL cameras and the projected splats travel to the rank owning the
+    camera (rendering.py:527-611) -- over NVLink peer memory (rs_exchange_push, one kernel per rank) and, for comparison,
+    over the NCCL all-to-all route.  Total work is fixed (strong scaling).  Includes a correctness flag: a reduced scene
+    (400 k Gaussians, the same 8 cameras at 480x270) rendered sharded on all ranks == rendered whole on one GPU."""
+    dmod = importlib.import_module("3dgs_rigidbody_b200.distributed")
+    W, H = WIDTH, HEIGHT
+    assert n_cams % world == 0
+    cl = n_cams // world
+    mine = slice(rank * cl, (rank + 1) * cl)
+    out = {"workload": f"c5: {n_total // 1_000_000}M Gaussians sharded over the ranks, {n_cams} ring cameras 1920x1080 ({cl} per rank), "
+                       "projected splats exchanged to the camera owners", "n_gpus": world}
+
+    def render(sc, vm, Ks, w, h):
+        with torch.no_grad():
+            return rs.rasterization(sc["means"], sc["quats"], sc["scales"], sc["opac"], sc["colors"], vm, Ks, w, h, packed=True,
+                                    distributed=dist is not None)
+
+    # ---- correctness: sharded == single GPU on a reduced scene ---------------------------------------------------------
+    n_small, ws, hs = 400_000, 480, 270
+    vm_s, Ks_s = _c5_cameras(torch, dev, n_cams, ws, hs)
+    lo, hi = rank * n_small // world, (rank + 1) * n_small // world
+    small = _c5_scene(torch, dev, n_small, lo, hi, seed=99)
+    for route in (("peer", "nccl") if dist is not None else ("single",)):
+        dmod.PeerSplatExchange.enabled = route == "peer"
+        dmod.PeerSplatExchange._usable.clear()
+        img_sh, alpha_sh, _ = render(small, vm_s[mine], Ks_s[mine], ws, hs)
+        if dist is not None:
+            parts = [torch.empty_like(img_sh) for _ in range(world)]
+            dist.all_gather(parts, img_sh.contiguous())
+            img_all = torch.cat(parts, 0)
+        else:
+            img_all = img_sh
+        if rank == 0:
+            whole = _c5_scene(torch, dev, n_small, 0, n_small, seed=99)
+            with torch.no_grad():
+                img_one, _, _ = rs.rasterization(whole["means"], whole["quats"], whole["scales"], whole["opac"], whole["colors"],
+                                                 vm_s, Ks_s, ws, hs, packed=True)
+            out[f"sharded_equals_single_gpu_{route}"] = {
+                "checksum_equal_to_single_gpu": bool(torch.equal(img_all, img_one)),
+                "max_abs_diff": float((img_all - img_one).abs().max()), "mean_alpha_gt_0": bool(float(img_one.mean()) > 0),
+                "scene": f"{n_small} Gaussians, {n_cams} cameras {ws}x{hs}"}
+            del whole, img_one
+    del small
+    torch.cuda.empty_cache()
+
+    # ---- timing at full size ----------------------------------------------------------------------------------------------
+    lo, hi = rank * n_total // world, (rank + 1) * n_total // world
+    sc = _c5_scene(torch, dev, n_total, lo, hi)
+    vm, Ks = _c5_cameras(torch, dev, n_cams, W, H)
+    for route in (("peer", "nccl") if dist is not None else ("single",)):
+        dmod.PeerSplatExchange.enabled = route == "peer"
+        dmod.PeerSplatExchange._usable.clear()
+        for _ in range(warmup):
+            img, alpha, meta = render(sc, vm[mine], Ks[mine], W, H)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            img, alpha, meta = render(sc, vm[mine], Ks[mine], W, H)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        st = torch.tensor([float(meta["flatten_ids"].numel()), float(meta["gaussian_ids"].numel())], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.barrier()
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(st, op=dist.ReduceOp.SUM)
+        ms = float(t[0]) / steps
+        out[f"{route}_exchange"] = {"ms_per_step": round(ms, 3), "camera_frames_per_s": round(n_cams / (ms * 1e-3), 2),
+                                    "n_isects_total": int(st[0]), "visible_rows_total": int(st[1])}
+    dmod.PeerSplatExchange.enabled = True
+    dmod.PeerSplatExchange._usable.clear()
+    del sc
+    torch.cuda.empty_cache()
     return out
 
 
@@ -393,7 +733,8 @@ def ours_arm(args):
     if dist is not None:
         dist.barrier()
     rs = importlib.import_module("3dgs_rigidbody_b200")
-    lib = importlib.import_module("3dgs_rigidbody_b200._lib").load()
+    _lib = importlib.import_module("3dgs_rigidbody_b200._lib")
+    lib = _lib.load()
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -407,7 +748,8 @@ def ours_arm(args):
     q_all, t_all = torch.from_numpy(q_np).to(dev), torch.from_numpy(t_np).to(dev)  # [240,K,4], [240,K,3]
     fr = rs.FrameRenderer(sc["means"], sc["quats"], sc["scales"], sc["opacities"], sc["colors"], WIDTH, HEIGHT,
                           cluster_ids=sc["cluster_ids"], body_centers=sc["body_centers"], max_isects=args.max_isects)
-    frames = frames_of_rank(rank, world, args.warmup + args.steps)
+    frames = bench_frames(rank, args.warmup + args.steps)
+    warm_frames, timed_frames = frames[:args.warmup], frames[args.warmup:]
 
     def barrier():
         if dist is not None:
@@ -418,7 +760,7 @@ def ours_arm(args):
     pipe = rs.FramePipeline(args.in_flight, sc["means"], sc["quats"], sc["scales"], sc["opacities"], sc["colors"], WIDTH,
                             HEIGHT, cluster_ids=sc["cluster_ids"], body_centers=sc["body_centers"],
                             max_isects=args.max_isects, split=not args.no_split, rgb8=True)
-    for f in frames[:args.warmup]:
+    for f in warm_frames:
         fr.render(sc["viewmats"], sc["Ks"], q_all[f], t_all[f])
         pipe.submit(sc["viewmats"], sc["Ks"], q_all[f], t_all[f])
     pipe.join()
@@ -428,19 +770,19 @@ def ours_arm(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
-    n0 = lib.rs_launch_count() if hasattr(lib, "rs_launch_count") else None
+    n0 = lib.rs_launch_count()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
     e0.record()
-    for f in frames[args.warmup:]:
+    for f in timed_frames:
         pipe.submit(sc["viewmats"], sc["Ks"], q_all[f], t_all[f])
     pipe.join()
     e1.record()
     barrier()
     t_wall1 = time.time()
     ms = e0.elapsed_time(e1)
-    launches = (lib.rs_launch_count() - n0) if n0 is not None else None
+    launches = lib.rs_launch_count() - n0
     assert not pipe.overflowed()
     n_isects_last = pipe.renderers[(pipe.count - 1) % args.in_flight].n_isects()
 
@@ -454,7 +796,6 @@ def ours_arm(args):
     vm_np, Ks_np = sc_np["viewmats"].reshape(-1), sc_np["Ks"].reshape(-1)
     slot_done = [None] * depth
     h2d_bytes = (K * 7 + 25) * 4
-    d2h_bytes = HEIGHT * WIDTH * 3 * 4  # the rendered image; the reference's loop discards the alphas (main.py:387-400)
 
     def e2e_frame(i, f, as_rgb8):
         k = i % depth
@@ -482,75 +823,107 @@ def ours_arm(args):
             slot_done[k] = ev
 
     def e2e_run(as_rgb8):
-        for i, f in enumerate(frames[:args.warmup]):
+        for i, f in enumerate(warm_frames):
             e2e_frame(i, f, as_rgb8)
         torch.cuda.synchronize()
         barrier()
         t0 = time.perf_counter()
-        for i, f in enumerate(frames[args.warmup:]):
+        for i, f in enumerate(timed_frames):
             e2e_frame(i, f, as_rgb8)
         torch.cuda.synchronize()
         return time.perf_counter() - t0
 
-    e2e_s = e2e_run(False)
+    e2e32_s = e2e_run(False)
     e2e_checksum = float(h_img[(args.steps - 1) % depth].sum())
-    # the same loop reading back the 8-bit frame the reference's animation loop would store (main.py:140-171
-    # save_rendered_image -> torchvision save_image quantisation), produced by the compositing epilogue: 4x fewer PCIe bytes
     e2e8_s = e2e_run(True)
     last8 = h_img8[(args.steps - 1) % depth]
     ref8 = (h_img[(args.steps - 1) % depth] * 255).add_(0.5).clamp_(0, 255).to(torch.uint8)
     rgb8_matches = bool(torch.equal(last8, ref8))
+    ceiling_gbs = d2h_ceiling(torch, dist, dev)
 
-    t_ms = torch.tensor([ms, e2e_s * 1e3, e2e8_s * 1e3], dtype=torch.float64, device=dev)
+    t_ms = torch.tensor([ms, e2e32_s * 1e3, e2e8_s * 1e3], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms_max, e2e_ms_max, e2e8_ms_max = float(t_ms[0]), float(t_ms[1]), float(t_ms[2])
+    ms_max, e2e32_ms_max, e2e8_ms_max = float(t_ms[0]), float(t_ms[1]), float(t_ms[2])
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
 
+    total_frames = args.steps * world
+    value = total_frames / (ms_max * 1e-3)
+    e2e8_fps, e2e32_fps = total_frames / (e2e8_ms_max * 1e-3), total_frames / (e2e32_ms_max * 1e-3)
+    d2h8, d2h32 = HEIGHT * WIDTH * 3, HEIGHT * WIDTH * 3 * 4
+    api = ("FrameRenderer.render -> rs_render_frame (C ABI); pinned host poses+camera in, pinned host frame out, one stream per "
+           "in-flight frame (H2D, render, D2H in stream order)")
+    line = {
+        "metric": "frames/sec (1M Gaussians, 1080p, rigid-animated)", "value": round(value, 2), "unit": "frames/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_max / args.steps, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": base_config(),
+        "run": {"n_isects_last_frame": n_isects_last, "frames_in_flight_per_gpu": args.in_flight,
+                "sharding": f"{world} rank(s) x the same {args.steps} frames, no collective on the data path"},
+        "e2e": {"value": round(e2e8_fps, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h8,
+                "api": api, "result": "uint8 [H,W,3] frame, quantised as the reference's loop stores it (main.py:140-171 "
+                                      "save_rendered_image -> torchvision save_image: x*255+0.5, clamp, truncate) by the compositing epilogue",
+                "equals_quantised_float_image": rgb8_matches,
+                "d2h_GBps": round(e2e8_fps * d2h8 / 1e9, 2), "d2h_ceiling_GBps": round(ceiling_gbs, 2),
+                "frac_of_d2h_ceiling": round(e2e8_fps * d2h8 / 1e9 / ceiling_gbs, 4)},
+        "e2e_f32": {"value": round(e2e32_fps, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h32,
+                    "result": "float32 [H,W,3] image", "checksum_last_image": e2e_checksum,
+                    "d2h_GBps": round(e2e32_fps * d2h32 / 1e9, 2), "d2h_ceiling_GBps": round(ceiling_gbs, 2),
+                    "frac_of_d2h_ceiling": round(e2e32_fps * d2h32 / 1e9 / ceiling_gbs, 4)},
+        "d2h_ceiling": {"GBps": round(ceiling_gbs, 2), "how": f"{world} rank(s) copying 64 MiB device -> pinned host at once, 8 copies each, "
+                                                              "CUDA events, max over ranks, in this run"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+    extras = not args.no_extras
+    if extras and world == 1 and rank == 0:
+        n_tiles = ((WIDTH + 15) // 16) * ((HEIGHT + 15) // 16)
+        kernels, stages, roofline, frame_ms, M = kernel_rooflines(rs, _lib, fr, sc, q_all, t_all, timed_frames, peak_gbs,
+                                                                  peak_src, n_tiles)
+        line["kernels"] = kernels
+        line["stages"] = stages
+        line["roofline"] = roofline
+        line["run"]["frame_ms_one_frame_in_flight_with_kernel_events"] = round(frame_ms, 4)
+    del pipe
+    torch.cuda.empty_cache()
+    other = {}
+    if extras:
+        if world == 1:
+            for name, fn in (("api", lambda: c2_api_configs(rs, sc, q_all, t_all, timed_frames)),
+                             ("ref_cuda", lambda: ref_cuda_leg(sc, q_all, t_all, timed_frames))):
+                try:
+                    res = fn()
+                except Exception as e:  # extra information only: never let it take the headline line down
+                    res = {"error": f"{type(e).__name__}: {e}"[:300]}
+                if name == "api":
+                    other.update(res)
+                else:
+                    line["ref_cuda"] = res
+                torch.cuda.empty_cache()
+        del fr
+        sc = None
+        torch.cuda.empty_cache()
+        for name, fn in (("c4", lambda: bench_c4(rs, torch, dist, dev, rank, world)),
+                         ("c5", lambda: bench_c5(rs, torch, dist, dev, rank, world))):
+            if name in args.skip.split(","):
+                continue
+            try:
+                other[name] = fn()
+            except Exception as e:
+                other[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                if dist is not None:  # a rank that failed alone would strand the others inside a collective
+                    raise
+            torch.cuda.empty_cache()
     if rank != 0:
         if dist is not None:
             dist.barrier()
             dist.destroy_process_group()
         return 0
-
-    total_frames = args.steps * world
-    value = total_frames / (ms_max * 1e-3)
-    line = {
-        "metric": "frames/sec (1M Gaussians, 1080p, rigid-animated)", "value": round(value, 2), "unit": "frames/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_max / args.steps, 4),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "gaussians": N_GAUSS, "bodies": N_BODIES, "width": WIDTH, "height": HEIGHT,
-                   "channels": 3, "n_isects_last_frame": n_isects_last, "frames_in_flight_per_gpu": args.in_flight, "sharding": f"frames round-robin over {world} rank(s), no collective",
-                   "l2": "per-frame working set (Gaussians 60 MB + projected 36 MB + 2x(keys+values) >= 200 MB + images 41 MB) "
-                         "exceeds the 126 MB L2 and every frame has new poses; no explicit flush"},
-        "e2e": {"value": round(total_frames / (e2e_ms_max * 1e-3), 2), "unit": "frames/s",
-                "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                "api": "FrameRenderer.render -> rs_render_frame (C ABI); pinned host poses+camera in, pinned host float32 image out, "
-                       "one stream per in-flight frame (H2D, render, D2H in stream order)", "checksum_last_image": e2e_checksum},
-        "e2e_rgb8": {"value": round(total_frames / (e2e8_ms_max * 1e-3), 2), "unit": "frames/s",
-                     "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": HEIGHT * WIDTH * 3,
-                     "note": "same loop, the result read back as the uint8 frame the reference's loop stores (main.py:140-171: "
-                             "x*255+0.5, clamp, truncate), written by the compositing epilogue; extra information, `e2e` is the "
-                             "float32 read-back", "equals_quantised_float_image": rgb8_matches},
-        "gpu_launches": launches,
-        "clocks": clocks,
-    }
-    if world == 1 and not args.no_extras:
-        n_tiles = ((WIDTH + 15) // 16) * ((HEIGHT + 15) // 16)
-        stages, roofline, frame_ms, M = stage_breakdown(fr, sc, q_all, t_all, frames[args.warmup:], peak_gbs, peak_src,
-                                                        n_tiles)
-        line["stages"] = stages
-        line["roofline"] = roofline
-        line["config"]["frame_ms_with_stage_events"] = round(frame_ms, 4)
-        torch.cuda.empty_cache()
-        budget = args.cpu_budget
-        try:
-            line["other_configs"] = other_configs(rs, sc, q_all, t_all)
-        except Exception as e:  # extra information only: never let it take the headline line down
-            line["other_configs"] = {"error": f"{type(e).__name__}: {e}"[:300]}
-        torch.cuda.empty_cache()
+    if other:
+        line["other_configs"] = other
+    if extras and world == 1:
         cpu_frames = [(60 + 37 * i) % N_FRAMES for i in range(64)]  # stops at the CPU budget below
-        times, threads = run_cpu_port(sc_np, cpu_frames, budget_s=budget)
+        times, threads = run_cpu_port(sc_np, cpu_frames, budget_s=args.cpu_budget)
         cpu_fps = len(times) / sum(times)
         line["cpu_baseline"] = {"value": round(cpu_fps, 4), "unit": "frames/s", "cores": threads, "kind": "port",
                                 "sample": f"{len(times)} full frames (animation frames 60, 97, 134, ... stride 37) of the same "
@@ -574,12 +947,10 @@ def main():
     ap.add_argument("--no-split", action="store_true",
                     help="one stream per in-flight frame instead of (high-priority binning stream, compositing stream)")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
-    ap.add_argument("--no-extras", action="store_true", help="skip stages / roofline / cpu_baseline (profiling runs)")
+    ap.add_argument("--no-extras", action="store_true", help="headline only: skip kernels / roofline / other_configs / cpu_baseline")
+    ap.add_argument("--skip", default="", help="comma list of other_configs to skip: c4,c5")
     args = ap.parse_args()
     if args.impl == "reference":
-        if args.steps > 8:
-            args.steps = 8  # bounded sample: each CPU frame takes seconds
-        args.warmup = min(args.warmup, 1)
         return reference_arm(args)
     return ours_arm(args)
 

@@ -14,8 +14,8 @@
  *     (thread-local).  Launch errors are checked (the reference does not check them at all).
  *   - nothing here synchronises the stream or the device, except rs_isect_count_total() and rs_peer_alloc().
  *   - optional pointers may be NULL where marked "optional".
- *   - one process drives ONE device (the deployment model: one rank per GPU): kernel attributes such as the opt-in
- *     shared-memory size are set once per process on the device that is current at the first call.
+ *   - every call acts on the CURRENT device (cudaSetDevice is the caller's business); per-device state (SM count, opt-in
+ *     shared-memory sizes of the kernels) is kept per device, so one process may drive several GPUs.
  */
 #ifndef RIGIDSPLAT_H_
 #define RIGIDSPLAT_H_
@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RS_ABI_VERSION 10
+#define RS_ABI_VERSION 11
 
 /* gsplat/cuda/include/Common.h:46-51 (CameraModelType) */
 enum { RS_PINHOLE = 0, RS_ORTHO = 1, RS_FISHEYE = 2, RS_FTHETA = 3 };
@@ -41,6 +41,14 @@ uint64_t rs_sizeof_args(int which);
 /* number of kernels this library has launched in this process (all threads); bench.py reports its delta over the
  * timed region as `gpu_launches`. */
 uint64_t rs_launch_count(void);
+/* Measurement aid (bench.py `roofline`): per-kernel durations of everything the CALLING THREAD launches through this
+ * library on `stream` between rs_profile_begin() and rs_profile_end().  One CUDA event is recorded on `stream` behind each
+ * kernel launch; rs_profile_end() synchronises on the last one and returns, per kernel in launch order, its name (static
+ * string) and the time since the previous event in milliseconds (kernel + launch gap, as it ran in stream order).  At most
+ * 256 kernels are recorded per profile. */
+int rs_profile_begin(rs_stream_t stream);
+int rs_profile_end(int32_t max_kernels, float *ms /* [max_kernels] */, const char **names /* [max_kernels] */,
+                   int32_t *n_kernels);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Rigid pose table.  Replaces main.py:183-228 (apply_transform) + main.py:173-181 (quat_multiply) +
@@ -194,7 +202,8 @@ typedef struct {
     uint32_t epoch;              /* frame counter, > 0, the same on every rank, +1 per exchange */
     int32_t colors_per_row;      /* colors is [nnz,channels] (1) or per local Gaussian [N,channels] (0) */
     int32_t opacities_per_row;   /* opacities is [nnz] (1) or per local Gaussian [N] (0) */
-    int32_t _pad;
+    int32_t timeout_ms;          /* spin limit of the flag waits; 0 = default (60 s).  A rank that times out on the counts
+                                  * sends no rows and marks the epoch as failed on EVERY rank (error 1 everywhere) */
     void *const *peer_base;      /* device array [world]: this rank's mapping of every rank's receive allocation */
     /* this rank's packed rows (outputs of rs_project_packed_fwd with B = 1): */
     const int32_t *indptr;       /* [world*cameras_per_rank + 1] */

@@ -32,6 +32,41 @@ def orc():
     return oracle
 
 
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "gsplat_ref_cuda.so")
+
+
+@pytest.fixture(scope="session")
+def ref():
+    """The reference's own compiled CUDA extension (oracle/build_ref.py): the GPU-side checker."""
+    import importlib.util
+
+    if not os.path.exists(REF_SO):
+        pytest.skip("oracle/_ref/gsplat_ref_cuda.so not built (needs /root/reference at build time)")
+    import torch  # noqa: F401  (the extension links against libtorch)
+
+    spec = importlib.util.spec_from_file_location("gsplat_ref_cuda", REF_SO)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.fixture(scope="session")
+def refpy(rs):
+    """baseline/install_ref.py: importer of the UNMODIFIED reference python (gsplat package, main.py functions) from
+    baseline/_ref -- git-ignored, installed where /root/reference exists, travels to the GPU box."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("install_ref", os.path.join(ROOT, "baseline", "install_ref.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    if not mod.available():
+        try:
+            mod.install()
+        except FileNotFoundError:
+            pytest.skip("baseline/_ref not installed (needs /root/reference at build time)")
+    return mod
+
+
 def load_golden(name):
     return dict(np.load(os.path.join(GOLDEN, name)))
 
@@ -65,3 +100,24 @@ def pinhole_cameras(C, W, H, f_scale=0.8):
         viewmats[c, 0, 3] = 0.3 * c
     Ks = np.tile(np.array([[f_scale * W, 0, W / 2], [0, f_scale * W, H / 2], [0, 0, 1]], np.float32), (C, 1, 1))
     return viewmats, Ks
+
+
+def apply_transform_per_body(refpy, splats, cluster_ids, body_quats, body_trans):
+    """The reference's animation step: apply_transform() once per body on that body's Gaussians (main.py:366-400, 183-228).
+    Returns the moved (means, quats) and the per-body pivots it used (means.mean(dim=0) of the body, main.py:210)."""
+    import torch
+
+    fns = refpy.reference_functions("main.py", ["apply_transform", "quat_multiply"])
+    means, quats = splats["means"].clone(), splats["quats"].clone()
+    K = body_quats.shape[0]
+    centers = torch.zeros(K, 3, device=means.device)
+    for k in range(K):
+        idx = torch.nonzero(cluster_ids == k).squeeze(-1)
+        if idx.numel() == 0:
+            continue
+        part = {"means": splats["means"][idx], "quats": splats["quats"][idx]}
+        centers[k] = part["means"].mean(dim=0)
+        moved = fns["apply_transform"](part, body_trans[k], body_quats[k])
+        means[idx] = moved["means"]
+        quats[idx] = moved["quats"]
+    return means, quats, centers

@@ -34,3 +34,18 @@ def test_reference_arm_other_ranks_exit_silently():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
                           "--warmup", "1"], capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_both_arms_describe_the_same_workload():
+    """`config` is built by one function for both arms (the driver's same_config check), and every rank times the same set
+    of frames at every world size (per-rank work independent of N)."""
+    sys.path.insert(0, ROOT)
+    import bench
+
+    cfg = bench.base_config()
+    assert cfg["workload"].startswith("c2") and cfg["gaussians"] == 1_000_000 and (cfg["width"], cfg["height"]) == (1920, 1080)
+    base = sorted(bench.bench_frames(0, 25))
+    for rank in range(8):
+        fr = bench.bench_frames(rank, 25)
+        assert sorted(fr) == base and len(set(fr)) == 25
+    assert bench.bench_frames(0, 25) != bench.bench_frames(1, 25)  # rotated, not in lock step

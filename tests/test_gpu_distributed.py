@@ -1,6 +1,7 @@
 """Gaussian-sharded rendering (c5) on real GPUs: `rasterization(distributed=True)` on every rank against a single-GPU
-render of the whole scene.  Runs with as many ranks as there are GPUs (1 on the round-end box: the collectives then
-degenerate to copies but the whole code path -- camera gather, exchange, id globalisation -- still executes over NCCL)."""
+render of the whole scene.  Runs with as many ranks as there are GPUs (up to 8; 1 on the round-end box: the collectives then
+degenerate to copies but the whole code path -- camera gather, exchange, id globalisation -- still executes over NCCL; the
+multi-rank runs are kept under profiles/ and bench.py --gpus N carries its own sharded == single-GPU check)."""
 import importlib
 import os
 import socket
@@ -66,7 +67,7 @@ def _worker(rank, world, port, packed, q):
 
 @pytest.mark.parametrize("packed", [False, True])
 def test_gaussian_sharded_render_matches_single_gpu(rs, packed):
-    world = min(torch.cuda.device_count(), 4)
+    world = min(torch.cuda.device_count(), 8)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -145,7 +146,7 @@ def _peer_worker(rank, world, port, q):
 
 
 def test_peer_memory_exchange_equals_nccl_exchange(rs):
-    world = min(torch.cuda.device_count(), 4)
+    world = min(torch.cuda.device_count(), 8)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()

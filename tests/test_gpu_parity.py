@@ -544,6 +544,30 @@ def test_frame_renderer_sh_matches_rasterization(rs):
     assert float((img1 - want1).abs().max()) <= 1e-4
 
 
+@pytest.mark.parametrize("packed", [False, True])
+def test_rasterization_fused_sh_matches_differentiable_sh_path(rs, packed):
+    """rasterization(sh_degree=3, cluster_ids=...) -- main.py:328-339's call plus the rigid poses.  Without gradients the
+    colours come out of the projection kernel; with gradients the differentiable spherical_harmonics() operator on explicit
+    view directions runs (rendering.py:491-525).  Same image, same meta."""
+    W, H, N, K = 288, 160, 20_000, 3
+    s = synthetic_scene(13, N, K=K)
+    vm, Ks = pinhole_cameras(2, W, H)
+    t = {k: T(v) for k, v in s.items()}
+    g = torch.Generator(device=DEV).manual_seed(4)
+    coeffs = torch.randn(N, 16, 3, device=DEV, generator=g) * 0.3
+    bg = torch.rand(2, 3, device=DEV, generator=g)
+    kw = dict(sh_degree=3, packed=packed, render_mode="RGB+ED", backgrounds=bg, cluster_ids=t["cluster_ids"],
+              body_quats=t["body_quats"], body_trans=t["body_trans"], body_centers=t["body_centers"])
+    args = (t["means"], t["quats"], t["scales"], t["opacities"])
+    with torch.no_grad():
+        img_f, alpha_f, meta_f = rs.rasterization(*args, coeffs, T(vm), T(Ks), W, H, **kw)
+    img_d, alpha_d, meta_d = rs.rasterization(*args, coeffs.clone().requires_grad_(True), T(vm), T(Ks), W, H, **kw)
+    assert img_f.shape == (2, H, W, 4) and float(img_d[..., :3].abs().max()) > 0.1
+    assert torch.equal(meta_f["flatten_ids"], meta_d["flatten_ids"]) and torch.equal(meta_f["radii"], meta_d["radii"])
+    assert float((img_f - img_d.detach()).abs().max()) <= 1e-4
+    assert torch.equal(alpha_f, alpha_d.detach())
+
+
 def test_frame_renderer_rgb8_is_the_quantised_float_frame(rs):
     """The 8-bit frame written by the compositing epilogue equals torchvision save_image's quantisation of the float frame
     (what main.py:140-171 save_rendered_image stores): x * 255 + 0.5, clamp to [0, 255], truncate -- with a background."""

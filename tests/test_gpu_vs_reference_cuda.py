@@ -18,22 +18,10 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import ROOT, pinhole_cameras, synthetic_scene
+from conftest import ROOT, apply_transform_per_body, pinhole_cameras, synthetic_scene
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
-REF_SO = os.path.join(ROOT, "oracle", "_ref", "gsplat_ref_cuda.so")
-
-
-@pytest.fixture(scope="module")
-def ref():
-    if not os.path.exists(REF_SO):
-        pytest.skip("oracle/_ref/gsplat_ref_cuda.so not built (needs /root/reference at build time)")
-    spec = importlib.util.spec_from_file_location("gsplat_ref_cuda", REF_SO)
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    return mod
-
 
 def T(a, dtype=None):
     t = torch.from_numpy(np.ascontiguousarray(a))
@@ -77,24 +65,45 @@ def test_projection_fwd_matches_reference_cuda(rs, ref, C, comp):
         assert ours[4] is None
 
 
-def test_projection_bwd_matches_reference_cuda(rs, ref):
+def test_projection_bwd_matches_reference_cuda(rs, ref, refpy):
+    """Both backward kernels against each other AND against the float64 autograd of the reference's own torch
+    implementation (gsplat/cuda/_torch_impl.py:45-75, 286-374, imported from baseline/_ref): our error against that exact
+    gradient may not exceed twice the reference kernel's own error."""
     W, H = 256, 192
     C = 2
-    s = synthetic_scene(5, 20_000, s_max=0.08)
+    N = 20_000
+    s = synthetic_scene(5, N, s_max=0.08)
     vm, Ks = pinhole_cameras(C, W, H)
     ours, theirs = project_both(rs, ref, s, vm, Ks, W, H, comp=True)
     radii, conics, comps = theirs[0], theirs[3], theirs[4]
     g = torch.Generator(device=DEV).manual_seed(0)
-    v_m2 = torch.randn(C, 20_000, 2, device=DEV, generator=g)
-    v_d = torch.randn(C, 20_000, device=DEV, generator=g)
-    v_con = torch.randn(C, 20_000, 3, device=DEV, generator=g) * 0.1
-    v_comp = torch.randn(C, 20_000, device=DEV, generator=g)
+    v_m2 = torch.randn(C, N, 2, device=DEV, generator=g)
+    v_d = torch.randn(C, N, device=DEV, generator=g)
+    v_con = torch.randn(C, N, 3, device=DEV, generator=g) * 0.1
+    v_comp = torch.randn(C, N, device=DEV, generator=g)
     args = (T(s["means"]), None, T(s["quats"]), T(s["scales"]), T(vm), T(Ks), W, H, 0.3)
     tail = (radii, conics, comps, v_m2, v_d, v_con, v_comp, True)
     o = rs._C.projection_ewa_3dgs_fused_bwd(*args, rs._C.PINHOLE, *tail)
     t = ref.projection_ewa_3dgs_fused_bwd(*args, ref.PINHOLE, *tail)
     for k, name in ((0, "v_means"), (2, "v_quats"), (3, "v_scales"), (4, "v_viewmats")):
-        assert rel_err(o[k], t[k]) < 2e-3, name
+        assert rel_err(o[k], t[k]) < 2e-4, name
+    # exact arbiter: float64 autograd through the reference's torch implementation, cotangents masked to the visible rows
+    refpy.load_reference(rs._C)
+    import importlib
+
+    ti = importlib.import_module("gsplat.cuda._torch_impl")
+    leaves = [T(s[k]).double().requires_grad_() for k in ("means", "quats", "scales")] + [T(vm).double().requires_grad_()]
+    covars, _ = ti._quat_scale_to_covar_preci(leaves[1], leaves[2], True, False, triu=False)
+    _, m2, dep, con, cmp_ = ti._fully_fused_projection(leaves[0], covars, leaves[3], T(Ks).double(), W, H, eps2d=0.3,
+                                                       calc_compensations=True)
+    vis = (radii > 0).all(-1)
+    loss = ((m2 * v_m2.double())[vis].sum() + (dep * v_d.double())[vis].sum() + (con * v_con.double())[vis].sum()
+            + (cmp_ * v_comp.double())[vis].sum())
+    loss.backward()
+    for k, leaf, name in ((0, leaves[0], "v_means"), (2, leaves[1], "v_quats"), (3, leaves[2], "v_scales"),
+                          (4, leaves[3], "v_viewmats")):
+        bad, info = _worse_than_reference(o[k], t[k], leaf.grad)
+        assert not bad, (name, info)
 
 
 @pytest.mark.parametrize("W,H,C", [(256, 256, 1), (1920, 1080, 1), (500, 300, 4)])
@@ -161,8 +170,22 @@ def test_raster_fwd_matches_reference_cuda(rs, ref, D):
     assert torch.equal(rc_o, rc_t)
 
 
+def _worse_than_reference(ours, theirs, exact, slack=2.0):
+    """Gradient bar: our kernel's error against the float64-accumulating CPU oracle must not exceed `slack` x the
+    reference kernel's own error against it (both in max-abs and in L2), plus one float32 ulp of the tensor's scale --
+    i.e. we may differ from the reference only by as much as the reference differs from the exact sum (float atomics in
+    another order), instead of round 1's "2e-3 of the tensor max", which hid errors on small entries."""
+    exact = exact.to(ours.device, torch.float64)
+    e_o, e_t = (ours.double() - exact).abs(), (theirs.double() - exact).abs()
+    ulp = float(exact.abs().max()) * 2.0 ** -23
+    bad_max = float(e_o.max()) > slack * float(e_t.max()) + ulp
+    bad_l2 = float(e_o.norm()) > slack * float(e_t.norm()) + ulp
+    return bad_max or bad_l2, dict(ours_max=float(e_o.max()), ref_max=float(e_t.max()), ours_l2=float(e_o.norm()),
+                                   ref_l2=float(e_t.norm()), scale=float(exact.abs().max()))
+
+
 @pytest.mark.parametrize("D,absgrad", [(3, True), (16, False)])
-def test_raster_bwd_matches_reference_cuda(rs, ref, D, absgrad):
+def test_raster_bwd_matches_reference_cuda(rs, ref, orc, D, absgrad):
     W, H, C = 200, 160, 2
     means2d, conics, colors, opac, off, flat = _raster_inputs(rs, ref, 8, 20_000, W, H, C, D)
     a = (means2d, conics, colors, opac, None, None, W, H, 16, off, flat)
@@ -172,12 +195,17 @@ def test_raster_bwd_matches_reference_cuda(rs, ref, D, absgrad):
     v_ra = torch.randn(ra.shape, device=DEV, generator=g)
     o = rs._C.rasterize_to_pixels_3dgs_bwd(*a, ra, li, v_rc, v_ra, absgrad)
     t = ref.rasterize_to_pixels_3dgs_bwd(*a, ra, li, v_rc, v_ra, absgrad)
+    cpu = lambda x: x.detach().cpu().numpy()
+    exact = orc.rasterize_bwd(cpu(means2d).reshape(-1, 2), cpu(conics).reshape(-1, 3), cpu(colors).reshape(-1, D),
+                              cpu(opac).reshape(-1), W, H, 16, cpu(off), cpu(flat), cpu(ra), cpu(li), cpu(v_rc), cpu(v_ra),
+                              absgrad=absgrad)
     names = ("v_means2d_abs", "v_means2d", "v_conics", "v_colors", "v_opacities")
-    for k in range(1, 5):
-        assert rel_err(o[k], t[k]) < 2e-3, names[k]
-    if absgrad:
-        assert rel_err(o[0], t[0]) < 2e-3
-    else:
+    for k in range(0 if absgrad else 1, 5):
+        want = torch.from_numpy(exact[names[k]]).reshape(t[k].shape)
+        bad, info = _worse_than_reference(o[k], t[k], want)
+        assert not bad, (names[k], info)
+        assert rel_err(o[k], t[k]) < 2e-4, names[k]
+    if not absgrad:
         assert o[0] is None
 
 
@@ -196,6 +224,30 @@ def _torch_rigid(means, quats, ids, bq, bt, bc):
     q2 = torch.stack([w1 * w2 - x1 * x2 - y1 * y2 - z1 * z2, w1 * x2 + x1 * w2 + y1 * z2 - z1 * y2,
                       w1 * y2 - x1 * z2 + y1 * w2 + z1 * x2, w1 * z2 + x1 * y2 - y1 * x2 + z1 * w2], -1)
     return torch.where(sel[:, None], m2, means), torch.where(sel[:, None], q2, quats)
+
+
+# Whole-frame bound against the reference's apply_transform chain at c2 / c3 (1 M Gaussians, 1080p): the measured counts are
+# printed by the tests; these are the asserted ceilings (an order of magnitude below round 1's "1e-4 of all pixels").
+C2_MAX_RADII_FLIPS = 8       # Gaussians (of 1 M) whose integer radii differ
+C2_MAX_PIXEL_FLIPS = 20      # pixels (of 2 073 600) whose RGB differs by more than 1e-4
+
+
+def _frame_diff_stats(m, img, alpha, meta_r, rc_r, ra_r):
+    """Counted differences between a fused frame (FrameRenderer.meta() + images) and the reference chain's outputs."""
+    radii_r = meta_r["radii"].reshape(m["radii"].shape)
+    tpg_r = meta_r["tiles_per_gauss"].reshape(m["tiles_per_gauss"].shape)
+    err = (rc_r - img).abs()
+    mse = float((err.double() ** 2).mean())
+    peak = max(float(rc_r.abs().max()), 1e-12)
+    return {
+        "radii_differ": int((m["radii"] != radii_r).any(-1).sum()),
+        "tile_counts_differ": int((m["tiles_per_gauss"] != tpg_r).sum()),
+        "n_isects_delta": int(m["n_isects"]) - int(meta_r["flatten_ids"].numel()),
+        "pixels_gt_1e-4": int((err > 1e-4).any(-1).sum()),
+        "max_abs_rgb": float(err.max()),
+        "max_abs_alpha": float((ra_r - alpha).abs().max()),
+        "psnr_db": 999.0 if mse == 0.0 else float(10 * np.log10(peak * peak / mse)),
+    }
 
 
 def _reference_frame(ref, means, quats, scales, opac, colors, vm, Ks, W, H):
@@ -232,7 +284,7 @@ def test_c1_frame_vs_reference_cuda(rs, ref):
     assert float(d) < 1e-3
 
 
-def test_c2_full_size_frame_vs_reference_cuda(rs, ref):
+def test_c2_full_size_frame_vs_reference_cuda(rs, ref, refpy):
     """c2 size (1 M Gaussians, 20 bodies, 1080p): FrameRenderer (one C-ABI call) vs the reference kernels chained."""
     import bench
 
@@ -260,15 +312,25 @@ def test_c2_full_size_frame_vs_reference_cuda(rs, ref):
                                                        flat_t)
     assert torch.equal(li_t, m["last_ids"])
     assert float((rc_t - img).abs().max()) <= 1e-4 and float((ra_t - alpha).abs().max()) <= 1e-4
-    # (3) whole frame against the reference chain (torch rigid transform + reference kernels)
-    m_t, q_t = _torch_rigid(sc["means"], sc["quats"], sc["cluster_ids"], bq, bt, sc["body_centers"])
-    rc_r, ra_r, _ = _reference_frame(ref, m_t, q_t, sc["scales"], sc["opacities"], sc["colors"], sc["viewmats"], sc["Ks"],
-                                     W, H)
-    err = (rc_r - img).abs()
-    mse = float((err.double() ** 2).mean())
-    assert mse == 0.0 or 10 * np.log10(1.0 / mse) >= 60.0
-    # pixels whose threshold decisions flipped because a projected mean moved by an ulp are rare
-    assert float((err > 1e-4).float().mean()) < 1e-4
+    # (3) whole frame against the REFERENCE chain: main.py's own apply_transform() once per body (extracted from the
+    #     installed reference copy) + the reference kernels.  Counted, not hidden: Gaussians whose radii / tile counts
+    #     differ, the intersection-count delta, pixels beyond 1e-4 and the max-abs error.
+    m_t, q_t, centers = apply_transform_per_body(refpy, sc, sc["cluster_ids"], bq, bt)
+    # the fused path takes the pivots apply_transform() derives itself (means.mean(dim=0) per body, main.py:210)
+    fr_c = rs.FrameRenderer(sc["means"], sc["quats"], sc["scales"], sc["opacities"], sc["colors"], W, H,
+                            cluster_ids=sc["cluster_ids"], body_centers=centers)
+    img_c, alpha_c = fr_c.render(sc["viewmats"], sc["Ks"], bq, bt)
+    torch.cuda.synchronize()
+    mc = fr_c.meta()
+    rc_r, ra_r, meta_r = _reference_frame(ref, m_t, q_t, sc["scales"], sc["opacities"], sc["colors"], sc["viewmats"],
+                                          sc["Ks"], W, H)
+    stats = _frame_diff_stats(mc, img_c, alpha_c, meta_r, rc_r, ra_r)
+    print("c2 whole frame vs apply_transform chain:", stats)
+    assert stats["psnr_db"] >= 60.0
+    assert stats["radii_differ"] <= C2_MAX_RADII_FLIPS, stats
+    assert stats["pixels_gt_1e-4"] <= C2_MAX_PIXEL_FLIPS, stats
+    if stats["radii_differ"] == 0:
+        assert stats["n_isects_delta"] == 0 and stats["max_abs_rgb"] <= 1e-4, stats
 
 
 def test_cpu_oracle_pinned_to_reference_cuda(rs, ref, orc):
@@ -361,7 +423,7 @@ def test_spherical_harmonics_fwd_bwd_vs_reference_cuda(rs, ref, deg, K):
     assert torch.equal(c32.grad, vco) and torch.equal(d32.grad, vd)
 
 
-def test_c3_full_size_identity_feature_step_vs_reference_cuda(rs, ref):
+def test_c3_full_size_identity_feature_step_vs_reference_cuda(rs, ref, refpy):
     """c3 (BASELINE configs[2]): 1 M Gaussians, 16-dim identity features, fwd + bwd at 1080p through rasterization() with
     the rigid poses fused in; loss = sum(render * w).  Checked against the reference kernels at full size:
       (1) whole chain (torch rigid transform -> reference projection / intersect_tile / rasterize): image parity;
@@ -379,20 +441,24 @@ def test_c3_full_size_identity_feature_step_vs_reference_cuda(rs, ref):
     w = torch.rand(1, H, W, D, device=DEV, generator=g)
     leaves = [sc[k].clone().requires_grad_() for k in ("means", "quats", "scales", "opacities")] + [feats.clone().requires_grad_()]
     vm, Ks = sc["viewmats"], sc["Ks"]
+    m_t, q_t, centers = apply_transform_per_body(refpy, sc, sc["cluster_ids"], bq, bt)  # main.py's own function, per body
     img, alpha, meta = rs.rasterization(*leaves, vm, Ks, W, H, packed=False, cluster_ids=sc["cluster_ids"],
-                                        body_quats=bq, body_trans=bt, body_centers=sc["body_centers"])
+                                        body_quats=bq, body_trans=bt, body_centers=centers)
     meta["means2d"].retain_grad()
     meta["conics"].retain_grad()
     (img * w).sum().backward()
     tw, th = (W + 15) // 16, (H + 15) // 16
 
-    # (1) whole reference chain
-    m_t, q_t = _torch_rigid(sc["means"], sc["quats"], sc["cluster_ids"], bq, bt, sc["body_centers"])
-    rc_r, _, _ = _reference_frame(ref, m_t, q_t, sc["scales"], sc["opacities"], feats, vm, Ks, W, H)
-    err = (rc_r - img.detach()).abs()
-    assert float((err > 1e-4).float().mean()) < 1e-4  # threshold flips where a projected mean moved by an ulp
-    mse = float((err.double() ** 2).mean())
-    assert mse == 0.0 or 10 * np.log10(float(rc_r.abs().max()) ** 2 / mse) >= 60.0
+    # (1) whole reference chain: apply_transform per body -> reference projection / intersect_tile / rasterize
+    rc_r, ra_r, meta_r = _reference_frame(ref, m_t, q_t, sc["scales"], sc["opacities"], feats, vm, Ks, W, H)
+    m_ours = dict(radii=meta["radii"], tiles_per_gauss=meta["tiles_per_gauss"], n_isects=meta["flatten_ids"].numel())
+    stats = _frame_diff_stats(m_ours, img.detach(), alpha.detach(), meta_r, rc_r, ra_r)
+    print("c3 whole frame vs apply_transform chain:", stats)
+    assert stats["psnr_db"] >= 60.0
+    assert stats["radii_differ"] <= C2_MAX_RADII_FLIPS, stats
+    assert stats["pixels_gt_1e-4"] <= C2_MAX_PIXEL_FLIPS, stats
+    if stats["radii_differ"] == 0:
+        assert stats["n_isects_delta"] == 0 and stats["max_abs_rgb"] <= 1e-4 * max(1.0, float(rc_r.abs().max())), stats
 
     # (2) reference compositing on our splats / lists
     means2d, conics = meta["means2d"].detach().contiguous(), meta["conics"].detach().contiguous()
@@ -415,7 +481,7 @@ def test_c3_full_size_identity_feature_step_vs_reference_cuda(rs, ref):
     assert rel_err(leaves[2].grad, v_scales_t) < 2e-3
     m_leaf = sc["means"].clone().requires_grad_()
     q_leaf = sc["quats"].clone().requires_grad_()
-    m2, q2 = _torch_rigid(m_leaf, q_leaf, sc["cluster_ids"], bq, bt, sc["body_centers"])
+    m2, q2 = _torch_rigid(m_leaf, q_leaf, sc["cluster_ids"], bq, bt, centers)
     torch.autograd.backward([m2, q2], [v_means_t, v_quats_t])
     assert rel_err(leaves[0].grad, m_leaf.grad) < 2e-3
     assert rel_err(leaves[1].grad, q_leaf.grad) < 2e-3
