@@ -11,13 +11,19 @@ Public surface (mirrors the reference):
     _C                                 stand-in for the pybind module gsplat/cuda/ext.cpp (same names / positional args)
     RigidPoses, FrameRenderer          rigid-pose table; sync-free fused per-frame renderer (animation loop)
     cgc_contrastive_clustering_loss    examples/utils.py:828-904 (identity-feature training step)
+    SegmentationHead                   examples/simple_trainer.py:442-446 (fused 16 -> 64 -> 16 head of the same step)
     load_cluster_groups, body_properties, PoseStream   clustering / physics data contract (rigid.py)
 """
 from . import _C  # noqa: F401
 from ._C import RigidPoses, RigidSplatError  # noqa: F401
 from .animation import FramePipeline, FrameRenderer  # noqa: F401
 from .rendering import rasterization  # noqa: F401
-from .identity import cgc_contrastive_clustering_loss, cluster_tables  # noqa: F401
+from .identity import (  # noqa: F401
+    SegmentationHead,
+    cgc_contrastive_clustering_loss,
+    cluster_tables,
+    segmentation_head_forward,
+)
 from .io import load_ply  # noqa: F401
 from .rigid import (  # noqa: F401
     PoseStream,

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "librigidsplat.so")
-SOURCES = ["abi.cu", "project.cu", "project_bwd.cu", "isect.cu", "depth_order.cu", "sort.cu", "raster_fwd.cu", "raster_bwd.cu", "frame.cu", "sh.cu", "exchange.cu", "cgc.cu"]
+SOURCES = ["abi.cu", "project.cu", "project_bwd.cu", "isect.cu", "depth_order.cu", "sort.cu", "raster_fwd.cu", "raster_bwd.cu", "frame.cu", "sh.cu", "exchange.cu", "cgc.cu", "seghead.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-use_fast_math", "-lineinfo", "-std=c++17",

@@ -109,6 +109,8 @@ extern "C" uint64_t rs_sizeof_args(int which) {
         return sizeof(rs_exchange_args);
     case 12:
         return sizeof(rs_cgc_args);
+    case 13:
+        return sizeof(rs_seghead_args);
     default:
         return 0;
     }

@@ -7,22 +7,26 @@
 //
 // Here the order is produced by a bucket sort whose steps have no serial chain at all:
 //   K0  min / max of the depth bits of the visible elements, and their number V                     (E reads)
-//   K1  fine-bucket histogram: bucket = (bits - min) >> shift, DORD_BUCKETS = 65536 buckets over the ACTUAL range of
-//       this frame (so the resolution adapts to the scene: ~15 elements per bucket at 1 M)            (E reads, V atomics)
+//   K1  bucket histogram: bucket = (bits - min) >> shift, 8192 (E <= 2 M) or 65536 buckets over the ACTUAL range of this
+//       frame (so the resolution adapts to the scene: ~100 elements per bucket)                        (E reads, V atomics)
 //   K2  exclusive scan of the bucket counts by one CTA; buckets are grouped into sort groups of ~DORD_TARGET elements
 //       (group g starts at the first bucket boundary at or after g * DORD_TARGET)
 //   K3  scatter: every visible element takes the next free slot of its bucket (atomic cursor) and stores the 64-bit
 //       composite (depth bits << 32 | flatten index)                                                  (V atomics, 8 B writes)
-//   K4  one CTA per sort group: the group's composites are sorted in shared memory by a bitonic network (they are unique,
-//       so ascending composite order IS (depth, index) order, whatever order the atomics of K3 produced) and the indices
-//       are written out.  A group that does not fit in shared memory (thousands of elements with depth bits inside one
+//   K4  one CTA per sort group: the group's composites are ordered in shared memory (they are unique, so ascending composite
+//       order IS (depth, index) order, whatever order the atomics of K3 produced) by a second-level counting sort over 2048
+//       sub-buckets of the group's own key range plus an insertion sort of the few multiply-occupied sub-buckets; groups with
+//       long runs of near-identical depths take a bitonic network instead.  A group that does not fit in shared memory (thousands of elements with depth bits inside one
 //       bucket, e.g. a wall facing an orthographic camera) is sorted by the same CTA in global memory with a stable LSD
 //       radix sort over the bits that actually vary -- slow, but correct for any input.
 // Output: elems[0 .. V) and V (device side).  Everything is sized by the SM count / the element bound; no host sync.
 #include "common.cuh"
 
-#define DORD_BUCKET_BITS 16
-#define DORD_BUCKETS (1 << DORD_BUCKET_BITS)
+// 65536 buckets: with 8192 the atomics of K1 / K3 pile up on too few L2 addresses (count 14 -> 37 us, scatter 19 -> 40 us at
+// 1 M elements, profiles/r02_depth_order_experiments.txt), and the scan below no longer cares about the bucket count
+#define DORD_BUCKET_BITS_MAX 16
+#define DORD_BUCKETS_MAX (1 << DORD_BUCKET_BITS_MAX)
+static inline int dord_bucket_bits(int64_t) { return DORD_BUCKET_BITS_MAX; }
 #define DORD_TARGET 896   // elements per sort group (plus the tail of the bucket that crosses the boundary)
 #define DORD_CAP 4096     // composites a CTA sorts in shared memory
 #define DORD_THREADS 256
@@ -36,10 +40,10 @@ struct DordHeader {          // zero-initialised by one memset per call
     unsigned int _pad[3];
 };
 
-__device__ __forceinline__ unsigned int dord_shift(unsigned int kmin, unsigned int kmax) {
+__device__ __forceinline__ unsigned int dord_shift(unsigned int kmin, unsigned int kmax, int bucket_bits) {
     const unsigned int range = kmax - kmin; // buckets must cover [0, range]
     const int width = 32 - __clz(range | 1u);
-    return (unsigned int)max(0, width - DORD_BUCKET_BITS);
+    return (unsigned int)max(0, width - bucket_bits);
 }
 
 // ---- K0 -----------------------------------------------------------------------------------------------------------------
@@ -88,8 +92,8 @@ rs_dord_minmax_kernel(int64_t n_elems, const float *__restrict__ depths, const i
 // ---- K1 -----------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(DORD_THREADS)
 rs_dord_count_kernel(int64_t n_elems, const float *__restrict__ depths, const int32_t *__restrict__ tiles,
-                     const DordHeader *__restrict__ hdr, unsigned int *__restrict__ counts) {
-    const unsigned int kmin = ~hdr->inv_min, shift = dord_shift(kmin, hdr->max);
+                     const DordHeader *__restrict__ hdr, unsigned int *__restrict__ counts, int bucket_bits) {
+    const unsigned int kmin = ~hdr->inv_min, shift = dord_shift(kmin, hdr->max, bucket_bits);
     for (int64_t i = (int64_t)blockIdx.x * DORD_THREADS + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * DORD_THREADS) {
         if (tiles[i] > 0)
             atomicAdd(&counts[(__float_as_uint(depths[i]) - kmin) >> shift], 1u);
@@ -97,69 +101,98 @@ rs_dord_count_kernel(int64_t n_elems, const float *__restrict__ depths, const in
 }
 
 // ---- K2: counts -> bucket cursors (exclusive prefix, in place) + group starts --------------------------------------------
-// One CTA of 32 warps; warp w owns the 2048 consecutive buckets [2048 w, 2048 (w+1)) and walks them 32 at a time (lane l ->
-// bucket 2048 w + 32 j + l), so every load / store instruction of a warp covers one 128-byte line.
-#define DORD_SCAN_THREADS 1024
-#define DORD_ROWS (DORD_BUCKETS / DORD_SCAN_THREADS) // 32-bucket rows per warp
+// 64 CTAs x 1024 buckets (4 consecutive buckets per thread, one 128-bit load / store each).  The CTA totals are chained by a
+// decoupled look-back over one status word per CTA ({flag : 2 | value : 30}: 1 = the CTA's own total, 2 = inclusive prefix;
+// one warp inspects up to 32 predecessors per round trip, so the chain is two steps long).  A single-CTA scan of the same
+// 256 KB took 20 us (one SM's bandwidth and a 64-step dependent chain); this takes the latency of one wave.
+#define DORD_SCAN_THREADS 256
+#define DORD_SCAN_PER_CTA (DORD_SCAN_THREADS * 4)
+#define DORD_SCAN_AGG 0x40000000u
+#define DORD_SCAN_PREFIX 0x80000000u
+#define DORD_SCAN_VALUE 0x3fffffffu
 __global__ void __launch_bounds__(DORD_SCAN_THREADS)
-rs_dord_scan_kernel(DordHeader *__restrict__ hdr, unsigned int *__restrict__ counts, unsigned int *__restrict__ group_start,
-                    int32_t *__restrict__ n_sorted_out) {
-    __shared__ unsigned int warp_tot[32];
+rs_dord_scan_kernel(DordHeader *__restrict__ hdr, unsigned int *__restrict__ counts, unsigned int *__restrict__ state,
+                    unsigned int *__restrict__ group_start, int32_t *__restrict__ n_sorted_out, int bucket_bits) {
+    __shared__ unsigned int warp_tot[DORD_SCAN_THREADS / 32];
+    __shared__ unsigned int s_base;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned int *mine = counts + (size_t)warp * (32 * DORD_ROWS);
-    unsigned int c[DORD_ROWS];
-    unsigned int sum = 0;
+    const unsigned int f0 = blockIdx.x * DORD_SCAN_PER_CTA + threadIdx.x * 4;
+    const uint4 c = *reinterpret_cast<const uint4 *>(counts + f0);
+    const unsigned int sum = c.x + c.y + c.z + c.w;
+    unsigned int incl = sum;
 #pragma unroll
-    for (int j = 0; j < DORD_ROWS; ++j) {
-        c[j] = mine[j * 32 + lane];
-        sum += c[j];
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o)
+            incl += n;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-        sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0)
-        warp_tot[warp] = sum;
+    if (lane == 31)
+        warp_tot[warp] = incl;
     __syncthreads();
-    if (warp == 0) { // exclusive scan of the 32 warp totals
-        const unsigned int w = warp_tot[lane];
-        unsigned int wi = w;
+    unsigned int wbase = 0, total = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned int n = __shfl_up_sync(0xffffffffu, wi, o);
-            if (lane >= o)
-                wi += n;
+    for (int w = 0; w < DORD_SCAN_THREADS / 32; ++w) {
+        const unsigned int t = warp_tot[w];
+        wbase += (w < warp) ? t : 0u;
+        total += t;
+    }
+    if (warp == 0) {
+        volatile unsigned int *st = state;
+        unsigned int prefix = 0;
+        if (blockIdx.x > 0) {
+            if (lane == 0)
+                st[blockIdx.x] = DORD_SCAN_AGG | total;
+            int look = (int)blockIdx.x - 1;
+            while (true) {
+                const int j = look - lane;
+                unsigned int v;
+                do {
+                    v = j >= 0 ? st[j] : DORD_SCAN_PREFIX;
+                } while (__any_sync(0xffffffffu, (v & (DORD_SCAN_AGG | DORD_SCAN_PREFIX)) == 0u));
+                const unsigned int pm = __ballot_sync(0xffffffffu, (v & DORD_SCAN_PREFIX) != 0u);
+                unsigned int val = v & DORD_SCAN_VALUE;
+                if (pm != 0u && lane > (__ffs(pm) - 1))
+                    val = 0u; // behind the nearest published inclusive prefix
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                    val += __shfl_xor_sync(0xffffffffu, val, o);
+                prefix += val;
+                if (pm != 0u)
+                    break;
+                look -= 32;
+            }
         }
-        warp_tot[lane] = wi - w;
+        if (lane == 0) {
+            __threadfence();
+            st[blockIdx.x] = DORD_SCAN_PREFIX | (prefix + total);
+            s_base = prefix;
+        }
     }
     __syncthreads();
     const unsigned int V = hdr->n_visible;
-    if (threadIdx.x == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
         group_start[0] = 0u;
         hdr->n_groups = V / DORD_TARGET + 1u;
         group_start[V / DORD_TARGET + 1u] = V;
-        hdr->shift = dord_shift(~hdr->inv_min, hdr->max);
+        hdr->shift = dord_shift(~hdr->inv_min, hdr->max, bucket_bits);
         if (n_sorted_out != nullptr)
             *n_sorted_out = (int32_t)V;
     }
-    unsigned int carry = warp_tot[warp]; // elements in all buckets before this row
+    unsigned int run = s_base + wbase + incl - sum; // elements in all buckets before this thread's first one
+    const unsigned int cc[4] = {c.x, c.y, c.z, c.w};
+    unsigned int pre[4];
 #pragma unroll
-    for (int j = 0; j < DORD_ROWS; ++j) {
-        unsigned int incl = c[j];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned int n = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o)
-                incl += n;
-        }
-        const unsigned int p = carry + incl - c[j], e = carry + incl;
-        mine[j * 32 + lane] = p; // the bucket's cursor for K3
-        if (c[j] != 0u) {
+    for (int j = 0; j < 4; ++j) {
+        const unsigned int p = run, e = run + cc[j];
+        pre[j] = p; // the bucket's cursor for K3
+        if (cc[j] != 0u) {
             // every multiple g * TARGET inside (p, e]: group g starts at this bucket's END (first boundary at or after it)
             for (unsigned int g = p / DORD_TARGET + 1u; g * DORD_TARGET <= e; ++g)
                 group_start[g] = e;
         }
-        carry += __shfl_sync(0xffffffffu, incl, 31);
+        run = e;
     }
+    *reinterpret_cast<uint4 *>(counts + f0) = make_uint4(pre[0], pre[1], pre[2], pre[3]);
 }
 
 // ---- K3 -----------------------------------------------------------------------------------------------------------------
@@ -260,56 +293,174 @@ __device__ void dord_sort_big(unsigned long long *a, unsigned long long *b, unsi
     __syncthreads();
 }
 
+// Fast path of K4 (n <= DORD_FAST): second-level COUNTING sort in shared memory.  The keys of a group span a narrow range
+// (its buckets are consecutive), so (key - group min) >> s2 spreads them over DORD_SUBS sub-buckets with < 1 element each
+// on average: count, scan, scatter, then order the few sub-buckets that hold more than one composite with an insertion sort
+// by the thread that finds the run.  ~80 instructions per element instead of the ~550 of a bitonic network.
+#define DORD_FAST 2048
+#define DORD_SUBS 2048
+#define DORD_RUN_MAX 48 // longer runs of one sub-bucket (near-identical depths): the group takes the bitonic network instead
+
+__device__ __forceinline__ void dord_bitonic(unsigned long long *s, unsigned int n) {
+    unsigned int m = 32;
+    while (m < n)
+        m <<= 1;
+    for (unsigned int i = n + threadIdx.x; i < m; i += DORD_THREADS)
+        s[i] = ~0ull;
+    __syncthreads();
+    for (unsigned int k = 2; k <= m; k <<= 1) {
+        for (unsigned int j = k >> 1; j > 0; j >>= 1) {
+            for (unsigned int t = threadIdx.x; t < (m >> 1); t += DORD_THREADS) {
+                const unsigned int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)); // index with bit j clear
+                const unsigned int p = i | j;
+                const unsigned long long x = s[i], y = s[p];
+                const bool up = (i & k) == 0;
+                if ((x > y) == up) {
+                    s[i] = y;
+                    s[p] = x;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
 __global__ void __launch_bounds__(DORD_THREADS)
 rs_dord_sort_kernel(const DordHeader *__restrict__ hdr, const unsigned int *__restrict__ group_start,
                     unsigned long long *__restrict__ comp, unsigned long long *__restrict__ comp_alt,
                     int32_t *__restrict__ elems) {
-    __shared__ unsigned long long s[DORD_CAP];
+    __shared__ unsigned long long s[DORD_CAP]; // fast path: [0, FAST) input, [FAST, 2 FAST) output; bitonic: all of it
+    __shared__ unsigned int cnt[DORD_SUBS];
+    __shared__ unsigned int red[2][DORD_THREADS / 32];
     __shared__ unsigned int hist[256];
+    __shared__ unsigned int s_flag;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned int n_groups = hdr->n_groups;
     for (unsigned int g = blockIdx.x; g < n_groups; g += gridDim.x) {
         const unsigned int lo = group_start[g], hi = group_start[g + 1];
         if (hi <= lo)
             continue;
         const unsigned int n = hi - lo;
+        __syncthreads(); // the previous group of this CTA is fully written out
         if (n > DORD_CAP) {
             dord_sort_big(comp + lo, comp_alt + lo, n, hist);
             for (unsigned int i = threadIdx.x; i < n; i += DORD_THREADS)
                 elems[lo + i] = (int32_t)(unsigned int)comp[lo + i];
             continue;
         }
-        unsigned int m = 32;
-        while (m < n)
-            m <<= 1;
-        for (unsigned int i = threadIdx.x; i < m; i += DORD_THREADS)
-            s[i] = i < n ? comp[lo + i] : ~0ull;
-        __syncthreads();
-        // bitonic network over m = 2^q composites (ascending); the composites are unique
-        for (unsigned int k = 2; k <= m; k <<= 1) {
-            for (unsigned int j = k >> 1; j > 0; j >>= 1) {
-                for (unsigned int t = threadIdx.x; t < (m >> 1); t += DORD_THREADS) {
-                    const unsigned int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)); // index with bit j clear
-                    const unsigned int p = i | j;
-                    const unsigned long long x = s[i], y = s[p];
-                    const bool up = (i & k) == 0;
-                    if ((x > y) == up) {
-                        s[i] = y;
-                        s[p] = x;
+        // load + key range of the group
+        unsigned int kmin = 0xffffffffu, kmax = 0u;
+        for (unsigned int i = threadIdx.x; i < n; i += DORD_THREADS) {
+            const unsigned long long c = comp[lo + i];
+            s[i] = c;
+            const unsigned int k = (unsigned int)(c >> 32);
+            kmin = min(kmin, k);
+            kmax = max(kmax, k);
+        }
+        bool fast = n <= DORD_FAST;
+        if (fast) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                kmin = min(kmin, __shfl_xor_sync(0xffffffffu, kmin, o));
+                kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, o));
+            }
+            if (lane == 0) {
+                red[0][warp] = kmin;
+                red[1][warp] = kmax;
+            }
+            for (unsigned int i = threadIdx.x; i < DORD_SUBS; i += DORD_THREADS)
+                cnt[i] = 0u;
+            if (threadIdx.x == 0)
+                s_flag = 0u;
+            __syncthreads();
+#pragma unroll
+            for (int w = 0; w < DORD_THREADS / 32; ++w) {
+                kmin = min(kmin, red[0][w]);
+                kmax = max(kmax, red[1][w]);
+            }
+            const int width = 32 - __clz((kmax - kmin) | 1u);
+            const unsigned int s2 = (unsigned int)max(0, width - 11); // (kmax - kmin) >> s2 < DORD_SUBS
+            for (unsigned int i = threadIdx.x; i < n; i += DORD_THREADS)
+                atomicAdd(&cnt[((unsigned int)(s[i] >> 32) - kmin) >> s2], 1u);
+            __syncthreads();
+            // exclusive scan of the sub-bucket counts: warp w owns 256 consecutive counters, 32 at a time
+            {
+                unsigned int c[DORD_SUBS / DORD_THREADS], sum = 0, big = 0;
+#pragma unroll
+                for (int j = 0; j < DORD_SUBS / DORD_THREADS; ++j) {
+                    c[j] = cnt[warp * (DORD_SUBS / 8) + j * 32 + lane];
+                    sum += c[j];
+                    big = max(big, c[j]);
+                }
+                if (big > DORD_RUN_MAX)
+                    s_flag = 1u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                if (lane == 0)
+                    red[0][warp] = sum;
+                __syncthreads();
+                unsigned int carry = 0;
+#pragma unroll
+                for (int w = 0; w < DORD_THREADS / 32; ++w)
+                    carry += (w < warp) ? red[0][w] : 0u;
+#pragma unroll
+                for (int j = 0; j < DORD_SUBS / DORD_THREADS; ++j) {
+                    unsigned int incl = c[j];
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o)
+                            incl += t;
+                    }
+                    cnt[warp * (DORD_SUBS / 8) + j * 32 + lane] = carry + incl - c[j];
+                    carry += __shfl_sync(0xffffffffu, incl, 31);
+                }
+            }
+            __syncthreads();
+            fast = s_flag == 0u;
+            if (fast) {
+                unsigned long long *out = s + DORD_FAST;
+                for (unsigned int i = threadIdx.x; i < n; i += DORD_THREADS) {
+                    const unsigned long long c = s[i];
+                    out[atomicAdd(&cnt[((unsigned int)(c >> 32) - kmin) >> s2], 1u)] = c;
+                }
+                __syncthreads();
+                // order inside the sub-buckets: the thread at the first slot of a run sorts it (runs are disjoint)
+                for (unsigned int i = threadIdx.x; i < n; i += DORD_THREADS) {
+                    const unsigned int sub = ((unsigned int)(out[i] >> 32) - kmin) >> s2;
+                    if (i > 0 && (((unsigned int)(out[i - 1] >> 32) - kmin) >> s2) == sub)
+                        continue;
+                    unsigned int e = i + 1;
+                    while (e < n && (((unsigned int)(out[e] >> 32) - kmin) >> s2) == sub)
+                        ++e;
+                    for (unsigned int a = i + 1; a < e; ++a) { // insertion sort of out[i .. e)
+                        const unsigned long long v = out[a];
+                        unsigned int q = a;
+                        while (q > i && out[q - 1] > v) {
+                            out[q] = out[q - 1];
+                            --q;
+                        }
+                        out[q] = v;
                     }
                 }
                 __syncthreads();
+                for (unsigned int i = threadIdx.x; i < n; i += DORD_THREADS)
+                    elems[lo + i] = (int32_t)(unsigned int)out[i];
+                continue;
             }
         }
+        __syncthreads();
+        dord_bitonic(s, n);
         for (unsigned int i = threadIdx.x; i < n; i += DORD_THREADS)
             elems[lo + i] = (int32_t)(unsigned int)s[i];
-        __syncthreads();
     }
 }
 
 // ---- host ---------------------------------------------------------------------------------------------------------------
 namespace {
 struct DordLayout {
-    size_t hdr, counts, group_start, comp, comp_alt, total;
+    size_t hdr, state, counts, group_start, comp, comp_alt, total;
 };
 inline size_t dord_align(size_t x) { return (x + 255) & ~(size_t)255; }
 DordLayout dord_layout(int64_t n_elems) {
@@ -322,7 +473,8 @@ DordLayout dord_layout(int64_t n_elems) {
         return at;
     };
     L.hdr = take(sizeof(DordHeader));
-    L.counts = take((size_t)DORD_BUCKETS * 4);
+    L.state = take((size_t)(DORD_BUCKETS_MAX / 1024) * 4); // look-back words of the scan (cleared with the header)
+    L.counts = take((size_t)DORD_BUCKETS_MAX * 4);
     L.group_start = take((E / DORD_TARGET + 3) * 4);
     L.comp = take(E * 8);
     L.comp_alt = take(E * 8);
@@ -349,18 +501,21 @@ int rs_depth_order(int64_t n_elems, const float *depths, const int32_t *tiles, i
     char *w = reinterpret_cast<char *>(workspace);
     DordHeader *hdr = reinterpret_cast<DordHeader *>(w + L.hdr);
     unsigned int *counts = reinterpret_cast<unsigned int *>(w + L.counts);
+    unsigned int *state = reinterpret_cast<unsigned int *>(w + L.state);
     unsigned int *group_start = reinterpret_cast<unsigned int *>(w + L.group_start);
     unsigned long long *comp = reinterpret_cast<unsigned long long *>(w + L.comp);
     unsigned long long *comp_alt = reinterpret_cast<unsigned long long *>(w + L.comp_alt);
     // header + bucket counters in one clear (they are adjacent)
-    RS_CUDA(cudaMemsetAsync(w + L.hdr, 0, L.counts + (size_t)DORD_BUCKETS * 4 - L.hdr, s));
+    const int bits = dord_bucket_bits(n_elems);
+    RS_CUDA(cudaMemsetAsync(w + L.hdr, 0, L.counts + ((size_t)4 << bits) - L.hdr, s));
     const int sms = rs_num_sms();
     const int grid = (int)min((int64_t)sms * 8, (n_elems + DORD_THREADS - 1) / DORD_THREADS);
     rs_dord_minmax_kernel<<<grid, DORD_THREADS, 0, s>>>(n_elems, depths, tiles, hdr);
     RS_LAUNCH_CHECK("rs_dord_minmax_kernel");
-    rs_dord_count_kernel<<<grid, DORD_THREADS, 0, s>>>(n_elems, depths, tiles, hdr, counts);
+    rs_dord_count_kernel<<<grid, DORD_THREADS, 0, s>>>(n_elems, depths, tiles, hdr, counts, bits);
     RS_LAUNCH_CHECK("rs_dord_count_kernel");
-    rs_dord_scan_kernel<<<1, DORD_SCAN_THREADS, 0, s>>>(hdr, counts, group_start, n_sorted_dev);
+    rs_dord_scan_kernel<<<(1 << bits) / DORD_SCAN_PER_CTA, DORD_SCAN_THREADS, 0, s>>>(hdr, counts, state, group_start,
+                                                                                      n_sorted_dev, bits);
     RS_LAUNCH_CHECK("rs_dord_scan_kernel");
     rs_dord_scatter_kernel<<<grid, DORD_THREADS, 0, s>>>(n_elems, depths, tiles, hdr, counts, comp);
     RS_LAUNCH_CHECK("rs_dord_scatter_kernel");

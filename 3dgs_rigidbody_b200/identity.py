@@ -116,3 +116,68 @@ def cgc_contrastive_clustering_loss(feature_map: Tensor, instance_mask: Tensor, 
     if tb.K > MAX_CLUSTERS:
         raise RuntimeError(f"cgc_contrastive_clustering_loss: {tb.K} clusters exceed the kernel limit of {MAX_CLUSTERS}")
     return _CgcLoss.apply(feature_map.reshape(H * W, D), tb, float(eps))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Segmentation head (examples/simple_trainer.py:442-446, 946-947), fused: rs_seghead_fwd / rs_seghead_bwd
+# ---------------------------------------------------------------------------------------------------------------------
+def _seg_args(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor):
+    a = _lib.rs_seghead_args()
+    a.N, a.D, a.H = x.shape[0], x.shape[1], w1.shape[0]
+    a.x, a.w1, a.b1, a.w2, a.b2 = (t.data_ptr() for t in (x, w1, b1, w2, b2))
+    return a
+
+
+class _SegHead(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        lib = _lib.load()
+        x, w1, b1, w2, b2 = (t.contiguous() for t in (x, w1, b1, w2, b2))
+        with torch.cuda.device(x.device):
+            y = torch.empty_like(x)
+            a = _seg_args(x, w1, b1, w2, b2)
+            a.y = y.data_ptr()
+            _lib.check(lib.rs_seghead_fwd(ctypes.byref(a), torch.cuda.current_stream().cuda_stream))
+        ctx.save_for_backward(x, w1, b1, w2, b2)
+        return y
+
+    @staticmethod
+    def backward(ctx, v_y):
+        x, w1, b1, w2, b2 = ctx.saved_tensors
+        lib = _lib.load()
+        v_y = v_y.contiguous()
+        with torch.cuda.device(x.device):
+            v_x = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+            grads = [torch.zeros_like(t) for t in (w1, b1, w2, b2)]
+            a = _seg_args(x, w1, b1, w2, b2)
+            a.v_y = v_y.data_ptr()
+            a.v_x = v_x.data_ptr() if v_x is not None else None
+            a.v_w1, a.v_b1, a.v_w2, a.v_b2 = (g.data_ptr() for g in grads)
+            _lib.check(lib.rs_seghead_bwd(ctypes.byref(a), torch.cuda.current_stream().cuda_stream))
+        return (v_x,) + tuple(g if need else None for g, need in zip(grads, ctx.needs_input_grad[1:]))
+
+
+def segmentation_head_forward(x: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor) -> Tensor:
+    """y = W2 relu(W1 x + b1) + b2 for every row of x [N, D] (torch.nn.Linear weight layout), differentiable; the [N, H]
+    hidden layer never reaches HBM.  Backward supports D = 16, H = 64 (the reference's head)."""
+    for t, n in ((x, "x"), (w1, "w1"), (b1, "b1"), (w2, "w2"), (b2, "b2")):
+        if not t.is_cuda or t.dtype != torch.float32:
+            raise RuntimeError(f"segmentation_head_forward: {n} must be a float32 CUDA tensor")
+    D, H = x.shape[-1], w1.shape[0]
+    if tuple(w1.shape) != (H, D) or tuple(b1.shape) != (H,) or tuple(w2.shape) != (D, H) or tuple(b2.shape) != (D,):
+        raise RuntimeError("segmentation_head_forward: parameter shapes must be [H,D], [H], [D,H], [D]")
+    return _SegHead.apply(x.reshape(-1, D), w1, b1, w2, b2).reshape(x.shape)
+
+
+class SegmentationHead(torch.nn.Sequential):
+    """Drop-in for the reference's `torch.nn.Sequential(Linear(identity_dim, 64), ReLU(), Linear(64, identity_dim))`
+    (examples/simple_trainer.py:442-446): same sub-modules, parameter names (`0.weight`, `0.bias`, `2.weight`, `2.bias`),
+    initialisation and state_dict -- an optimizer or a checkpoint of the reference works unchanged -- but forward / backward
+    run as one fused kernel each (rs_seghead_fwd / rs_seghead_bwd) instead of two / four library GEMMs around a
+    materialised [N, 64] hidden tensor."""
+
+    def __init__(self, identity_dim: int = 16, hidden: int = 64):
+        super().__init__(torch.nn.Linear(identity_dim, hidden), torch.nn.ReLU(), torch.nn.Linear(hidden, identity_dim))
+
+    def forward(self, x: Tensor) -> Tensor:
+        return segmentation_head_forward(x, self[0].weight, self[0].bias, self[2].weight, self[2].bias)

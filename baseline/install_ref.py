@@ -96,5 +96,29 @@ def reference_functions(script: str, names):
     return {n: ns[n] for n in names}
 
 
+def reference_statements(script: str, want):
+    """Statements of a reference script selected by `want(node) -> bool` over every statement of the module (including the
+    ones nested in functions and `if __name__` blocks), in source order, compiled into ONE code object.  For code the
+    reference keeps inline instead of in a function -- e.g. the writer of the `cluster_groups` archive
+    (examples/load_identity_encodings.py:478-486, 566-568).  Returns (code, [source line numbers])."""
+    path = os.path.join(DEST, "_scripts", script)
+    tree = ast.parse(open(path).read())
+    picked = []
+
+    def visit(body):
+        for node in body:
+            if want(node):
+                picked.append(node)
+                continue
+            for field in ("body", "orelse", "finalbody"):
+                sub = getattr(node, field, None)
+                if isinstance(sub, list) and sub and isinstance(sub[0], ast.stmt):
+                    visit(sub)
+
+    visit(tree.body)
+    mod = ast.Module(body=picked, type_ignores=[])
+    return compile(mod, path, "exec"), [n.lineno for n in picked]
+
+
 if __name__ == "__main__":
     print(install(force="-f" in sys.argv))

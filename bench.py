@@ -544,6 +544,25 @@ def c2_api_configs(rs, sc, q_all, t_all, frames, steps=10):
         rs.cgc_contrastive_clustering_loss(fmap, mask, tables=tables).backward()
 
     out["c3_contrastive_loss_fwd_bwd_ms"] = round(_timed_ms(torch, cgc_step, steps), 4)
+    # segmentation head on all N identity encodings (examples/simple_trainer.py:946-947): fused kernels vs the reference's
+    # nn.Sequential (library GEMMs around a materialised [N, 64] hidden tensor)
+    torch.manual_seed(0)
+    ref_head = torch.nn.Sequential(torch.nn.Linear(16, 64), torch.nn.ReLU(), torch.nn.Linear(64, 16)).to(dev)
+    head = rs.SegmentationHead(16, 64).to(dev)
+    head.load_state_dict(ref_head.state_dict())
+    enc = torch.randn(sc["means"].shape[0], 16, device=dev, generator=g).requires_grad_()
+    v_enc = torch.randn(sc["means"].shape[0], 16, device=dev, generator=g)
+
+    def head_step(module):
+        def fn(i=0):
+            enc.grad = None
+            for p in module.parameters():
+                p.grad = None
+            module(enc).backward(v_enc)
+        return fn
+
+    out["c3_segmentation_head_fwd_bwd_ms"] = round(_timed_ms(torch, head_step(head), steps), 4)
+    out["c3_segmentation_head_fwd_bwd_torch_nn_sequential_ms"] = round(_timed_ms(torch, head_step(ref_head), steps), 4)
     return out
 
 

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RS_ABI_VERSION 11
+#define RS_ABI_VERSION 12
 
 /* gsplat/cuda/include/Common.h:46-51 (CameraModelType) */
 enum { RS_PINHOLE = 0, RS_ORTHO = 1, RS_FISHEYE = 2, RS_FTHETA = 3 };
@@ -36,7 +36,8 @@ typedef void *rs_stream_t; /* cudaStream_t */
 int rs_abi_version(void);
 const char *rs_last_error(void);
 /* sizeof() of every args struct, for binding self-checks: which = 0 project_fwd, 1 project_bwd, 2 isect,
- * 3 sort, 4 raster_fwd, 5 raster_bwd, 6 frame, 7 rigid, 8 isect_sorted, 9 sh.  Returns 0 for an unknown id. */
+ * 3 sort, 4 raster_fwd, 5 raster_bwd, 6 frame, 7 rigid, 8 isect_sorted, 9 sh, 10 project_packed_fwd, 11 exchange, 12 cgc,
+ * 13 seghead.  Returns 0 for an unknown id. */
 uint64_t rs_sizeof_args(int which);
 /* number of kernels this library has launched in this process (all threads); bench.py reports its delta over the
  * timed region as `gpu_launches`. */
@@ -405,6 +406,30 @@ typedef struct {
 uint64_t rs_cgc_workspace_floats(int32_t K, int32_t D);
 int rs_cgc_fwd(const rs_cgc_args *a, rs_stream_t stream);
 int rs_cgc_bwd(const rs_cgc_args *a, rs_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Segmentation head of the identity-feature training step, fused: rs_seghead_fwd / rs_seghead_bwd replace
+ * `torch.nn.Sequential(Linear(D, H), ReLU(), Linear(H, D))` applied to the per-Gaussian identity encodings
+ * (examples/simple_trainer.py:442-446 builds it with D = identity_dim = 16, H = 64; :946-947 applies it to all N
+ * encodings every step) and its autograd.  y = W2 relu(W1 x + b1) + b2 with the torch.nn.Linear weight layout
+ * (W1 [H, D], W2 [D, H], row-major).  The [N, H] hidden layer is never written to HBM: forward streams x -> y, backward
+ * recomputes the activations per row and accumulates the weight gradients as register-resident tile products.
+ * Forward: any D <= 32, H <= 128.  Backward: D = 16, H = 64 (the reference's configuration).
+ * ------------------------------------------------------------------------------------------------------------ */
+typedef struct {
+    int64_t N;                   /* rows (Gaussians) */
+    int32_t D, H;                /* feature / hidden width */
+    const float *x;              /* [N, D] */
+    const float *w1, *b1;        /* [H, D], [H] */
+    const float *w2, *b2;        /* [D, H], [D] */
+    float *y;                    /* [N, D] out (rs_seghead_fwd) */
+    const float *v_y;            /* [N, D] (rs_seghead_bwd) */
+    float *v_x;                  /* [N, D] out (rs_seghead_bwd), optional */
+    float *v_w1, *v_b1;          /* [H, D], [H]  ACCUMULATED into: zero-initialised by the caller */
+    float *v_w2, *v_b2;          /* [D, H], [D]  ACCUMULATED into */
+} rs_seghead_args;
+int rs_seghead_fwd(const rs_seghead_args *a, rs_stream_t stream);
+int rs_seghead_bwd(const rs_seghead_args *a, rs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * rs_render_frame: the whole per-frame hot path in one call with NO host synchronisation -- what the commented-out

@@ -123,7 +123,11 @@ def _peer_worker(rank, world, port, q):
                 assert img_p.shape == (Cl, H, W, 4 if variant == "aa" else 3)
                 for k, v in keep.items():
                     assert torch.equal(v, meta_n[k].detach()), (frame, variant, k)
-                assert torch.equal(img_p, img_n.detach()) and torch.equal(alpha_p, alpha_n.detach()), (frame, variant)
+                if variant == "sh":  # no-grad: SH evaluated inside the projection kernel; grad: the separate SH operator
+                    assert float((img_p - img_n.detach()).abs().max()) <= 2e-5, (frame, variant)
+                else:
+                    assert torch.equal(img_p, img_n.detach()), (frame, variant)
+                assert torch.equal(alpha_p, alpha_n.detach()), (frame, variant)
         # (no per-rank content assertion here: a rank whose cameras look away from the scene legitimately receives no rows,
         # and a rank leaving early would strand the others inside a collective)
         # nothing visible anywhere (every Gaussian behind every camera): zero rows sent and received on both routes

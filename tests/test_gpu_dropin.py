@@ -132,3 +132,70 @@ def test_apply_transform_plus_reference_rasterization_vs_fused_frame(rs, ref, re
     assert n_radii <= 2 and n_tiles <= 2
     assert float(err.max()) <= 1e-4
     assert float((alpha_o - alpha_t).abs().max()) <= 1e-4
+
+
+def test_cluster_groups_archive_written_by_the_reference_drives_the_fused_frame(rs, ref, refpy, gsplat_ref, tmp_path):
+    """SURVEY 8f-3, pinned to the reference's own writer: the `cluster_groups` archive is produced by the statements of
+    examples/load_identity_encodings.py that assemble and save it (478-486: label -> object-group lists; 566-568:
+    np.savez_compressed of {str(id): indices}), extracted by AST from the installed reference copy; it is read back both the
+    way main.py does (np.load, main.py:280-297) and by rigid.load_cluster_groups(); then every body is moved -- by
+    apply_transform() on `splats[cluster_groups[id]]` exactly as main.py:294-297 subsets the splats, and by the fused
+    rasterization(cluster_ids=...) -- and the two frames are compared."""
+    import ast as _ast
+
+    W, H, N = 256, 192, 12_000
+    s = synthetic_scene(77, N)
+    t = {k: T(v) for k, v in s.items()}
+    rng = np.random.default_rng(5)
+    anchor_ids_list = [1, 2, 7]
+    kmeans_to_object_id_map = {0: 2, 1: 7, 2: 1}  # k-means label -> object id
+    final_labels = rng.integers(-1, 3, size=N)      # -1 = background
+    path = str(tmp_path / "cluster_groups.npy")     # the reference passes this name; numpy appends ".npz"
+
+    def is_writer(node):
+        src = _ast.unparse(node)
+        if isinstance(node, _ast.Assign) and src.startswith(("object_groups = {obj_id", "object_groups['background'] = []",
+                                                             "save_dict = ")):
+            return True
+        if isinstance(node, _ast.For) and "enumerate(final_labels)" in _ast.unparse(node.iter):
+            return True
+        return isinstance(node, _ast.Expr) and src.startswith("np.savez_compressed(cluster_groups_save_path")
+
+    code, lines = refpy.reference_statements("load_identity_encodings.py", is_writer)
+    # the group-dict initialisation (also present, identically, in the sibling k-means function at :364), the background
+    # list, the assembly loop, save_dict, savez
+    assert 5 <= len(lines) <= 6 and lines[-2:] == sorted(lines[-2:]), lines
+    exec(code, {"np": np, "anchor_ids_list": anchor_ids_list, "kmeans_to_object_id_map": kmeans_to_object_id_map,
+                "final_labels": final_labels, "cluster_groups_save_path": path})
+    archive = path + ".npz"
+    groups = np.load(archive)  # main.py:280
+    assert sorted(groups.files) == ["1", "2", "7", "background"]
+    cluster_ids, names = rs.load_cluster_groups(archive, N, device=torch.device(DEV))
+    assert names == {0: "1", 1: "2", 2: "7"}
+    K = len(names)
+    for k, key in names.items():
+        assert torch.equal(torch.nonzero(cluster_ids == k).squeeze(-1).cpu(), torch.from_numpy(groups[key]).long())
+    assert torch.equal(torch.nonzero(cluster_ids < 0).squeeze(-1).cpu(), torch.from_numpy(groups["background"]).long())
+
+    g = torch.Generator(device=DEV).manual_seed(9)
+    bq = torch.randn(K, 4, device=DEV, generator=g)
+    bt = torch.randn(K, 3, device=DEV, generator=g) * 0.3
+    fns = refpy.reference_functions("main.py", ["apply_transform", "quat_multiply"])
+    means, quats = t["means"].clone(), t["quats"].clone()
+    for k, key in names.items():
+        idx = torch.from_numpy(groups[key]).long().to(DEV)  # main.py:294
+        part = {n: v[idx] for n, v in (("means", t["means"]), ("quats", t["quats"]))}  # main.py:297
+        moved = fns["apply_transform"](part, bt[k], bq[k])
+        means[idx], quats[idx] = moved["means"], moved["quats"]
+    vm, Ks = pinhole_cameras(1, W, H)
+    refpy.set_backend(ref)
+    with torch.no_grad():
+        img_t, alpha_t, meta_t = gsplat_ref.rendering.rasterization(means, quats, t["scales"], t["opacities"], t["colors"], T(vm),
+                                                                    T(Ks), W, H, packed=False)
+    refpy.set_backend(rs._C)
+    with torch.no_grad():
+        img_o, alpha_o, meta_o = rs.rasterization(t["means"], t["quats"], t["scales"], t["opacities"], t["colors"], T(vm), T(Ks),
+                                                  W, H, packed=False, cluster_ids=cluster_ids, body_quats=bq, body_trans=bt)
+    assert int((meta_o["radii"] != meta_t["radii"]).any(-1).sum()) <= 2
+    assert float((img_o - img_t).abs().max()) <= 1e-4 and float((alpha_o - alpha_t).abs().max()) <= 1e-4
+    assert float(alpha_t.mean()) > 0.02
