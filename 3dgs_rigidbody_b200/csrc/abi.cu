@@ -111,6 +111,8 @@ extern "C" uint64_t rs_sizeof_args(int which) {
         return sizeof(rs_cgc_args);
     case 13:
         return sizeof(rs_seghead_args);
+    case 14:
+        return sizeof(rs_exchange_grad_args);
     default:
         return 0;
     }

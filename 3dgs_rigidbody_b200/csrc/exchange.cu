@@ -297,6 +297,107 @@ __global__ void rs_exchange_wait_kernel(const rs_exchange_args a, long long *tot
     }
 }
 
+// ---- transposed exchange (backward) -----------------------------------------------------------------------------------------
+// Gradients of the rows a rank RECEIVED travel back to the ranks that sent them: the transposed all-to-all of
+// gsplat/distributed.py:243-248 (the backward of its differentiable all_to_all), again as direct stores into peer memory.
+// Every rank keeps the W x W row-count matrix of the forward exchange (rs_exchange_read_counts), so no count handshake is
+// needed: the block received from source s -- rows [sum_{s'<s} counts[s'][r], +counts[s][r]) here -- goes to rows
+// [sum_{d<r} counts[s][d], ...) of s's gradient arrays, i.e. exactly where s's packed rows for destination r sit.
+// Each rank owns a second receive allocation for this (same layout function; only the five float columns are used).
+__global__ void rs_exchange_counts_kernel(const rs_exchange_args a, int32_t *out) {
+    char *const *peers = (char *const *)a.peer_base;
+    const ExchangeCtl *mine = (const ExchangeCtl *)peers[a.rank];
+    const unsigned int par = a.epoch & 1u;
+    const int W = a.world;
+    for (int i = threadIdx.x; i < W * W; i += blockDim.x)
+        out[i] = *((volatile const int *)&mine->counts[par][i / W][i % W]);
+}
+
+__global__ void __launch_bounds__(256) rs_exchange_push_grad_kernel(const rs_exchange_grad_args a, const ExchangeLayout lay) {
+    __shared__ long long src_lo[RS_EXCHANGE_MAX_WORLD + 1]; // my received rows of source s start here
+    __shared__ long long dst_lo[RS_EXCHANGE_MAX_WORLD];     // ... and go to this row of s's gradient arrays
+    __shared__ int blk_lo[RS_EXCHANGE_MAX_WORLD + 1];
+    const int W = a.world, r = a.rank;
+    char *const *peers = (char *const *)a.peer_base;
+    ExchangeCtl *mine = (ExchangeCtl *)peers[r];
+    if (threadIdx.x == 0) {
+        long long acc = 0;
+        int blocks = 0;
+        for (int s = 0; s < W; ++s) {
+            src_lo[s] = acc;
+            blk_lo[s] = blocks;
+            const long long n = a.counts[s * W + r];
+            acc += n;
+            blocks += (int)((n + 255) >> 8);
+            long long before = 0;
+            for (int d = 0; d < r; ++d)
+                before += a.counts[s * W + d];
+            dst_lo[s] = before;
+        }
+        src_lo[W] = acc;
+        blk_lo[W] = blocks;
+    }
+    __syncthreads();
+    const int D = a.channels, n_blocks = blk_lo[W];
+    const int t = threadIdx.x;
+    for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+        int s = 0;
+        while (blk >= blk_lo[s + 1])
+            ++s;
+        const long long off = (long long)(blk - blk_lo[s]) << 8;
+        const long long row0 = src_lo[s] + off;
+        const int n = (int)min(256ll, src_lo[s + 1] - row0);
+        const long long out0 = dst_lo[s] + off;
+        if (out0 + n > a.capacity) { // cannot happen when the host sized the arrays from the same matrix; never write outside
+            if (t == 0)
+                mine->error = 2u;
+            continue;
+        }
+        const ExchangeCols c = exchange_cols(peers[s], lay.off);
+        for (int i = t; i < n * 2; i += 256)
+            c.means2d[out0 * 2 + i] = a.v_means2d[row0 * 2 + i];
+        for (int i = t; i < n * 3; i += 256)
+            c.conics[out0 * 3 + i] = a.v_conics[row0 * 3 + i];
+        for (int i = t; i < n * D; i += 256)
+            c.colors[out0 * D + i] = a.v_colors[row0 * D + i];
+        if (t < n) {
+            c.depths[out0 + t] = a.v_depths[row0 + t];
+            c.opacities[out0 + t] = a.v_opacities[row0 + t];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0)
+        last = atomicAdd(&mine->done_ctas, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last) {
+        if (threadIdx.x == 0)
+            mine->done_ctas = 0u;
+        __threadfence_system();
+        if ((int)threadIdx.x < W)
+            st_sys(&((ExchangeCtl *)peers[threadIdx.x])->data_flag[r], a.epoch);
+    }
+}
+
+__global__ void rs_exchange_wait_grad_kernel(const rs_exchange_grad_args a, long long *status) {
+    char *const *peers = (char *const *)a.peer_base;
+    ExchangeCtl *mine = (ExchangeCtl *)peers[a.rank];
+    const bool ok = wait_flags(mine->data_flag, a.world, a.epoch, a.timeout_ms);
+    if (threadIdx.x == 0) {
+        long long behind = 0;
+        for (int s = 0; s < a.world; ++s)
+            if ((int)(ld_sys(&mine->data_flag[s]) - a.epoch) < 0)
+                behind |= 1ll << s;
+        unsigned int err = mine->error;
+        if (!ok)
+            err = 1u;
+        status[0] = err;
+        status[1] = behind;
+        mine->error = 0u;
+    }
+}
+
 static int exchange_check(const rs_exchange_args *a, const char *who) {
     RS_CHECK(a != nullptr, "%s: null args", who);
     RS_CHECK(a->world >= 1 && a->world <= RS_EXCHANGE_MAX_WORLD && a->rank >= 0 && a->rank < a->world,
@@ -333,5 +434,47 @@ extern "C" int rs_exchange_wait(const rs_exchange_args *a, int64_t *totals_dev, 
     RS_CHECK(totals_dev != nullptr, "rs_exchange_wait: totals_dev is required");
     rs_exchange_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(*a, (long long *)totals_dev);
     RS_LAUNCH_CHECK("rs_exchange_wait_kernel");
+    return 0;
+}
+
+extern "C" int rs_exchange_read_counts(const rs_exchange_args *a, int32_t *counts_dev, rs_stream_t stream) {
+    if (int rc = exchange_check(a, "rs_exchange_read_counts"))
+        return rc;
+    RS_CHECK(counts_dev != nullptr, "rs_exchange_read_counts: counts_dev is required");
+    rs_exchange_counts_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*a, counts_dev);
+    RS_LAUNCH_CHECK("rs_exchange_counts_kernel");
+    return 0;
+}
+
+static int exchange_grad_check(const rs_exchange_grad_args *a, const char *who) {
+    RS_CHECK(a != nullptr, "%s: null args", who);
+    RS_CHECK(a->world >= 1 && a->world <= RS_EXCHANGE_MAX_WORLD && a->rank >= 0 && a->rank < a->world,
+             "%s: bad world / rank (%d / %d)", who, a->world, a->rank);
+    RS_CHECK(a->channels >= 1 && a->channels <= RS_MAX_CHANNELS && a->capacity >= 0, "%s: bad channels / capacity", who);
+    RS_CHECK(a->peer_base != nullptr && a->epoch != 0u && a->counts != nullptr, "%s: peer table / counts missing or epoch 0", who);
+    return 0;
+}
+
+extern "C" int rs_exchange_push_grad(const rs_exchange_grad_args *a, rs_stream_t stream) {
+    if (int rc = exchange_grad_check(a, "rs_exchange_push_grad"))
+        return rc;
+    RS_CHECK(a->v_means2d && a->v_depths && a->v_conics && a->v_opacities && a->v_colors, "rs_exchange_push_grad: null gradient pointer");
+    ExchangeLayout lay;
+    uint64_t off[RS_EXCHANGE_COLUMNS + 1];
+    if (int rc = rs_exchange_layout(a->capacity, a->channels, off))
+        return rc;
+    for (int i = 0; i < RS_EXCHANGE_COLUMNS; ++i)
+        lay.off[i] = off[i];
+    rs_exchange_push_grad_kernel<<<rs_num_sms() * 2, 256, 0, (cudaStream_t)stream>>>(*a, lay);
+    RS_LAUNCH_CHECK("rs_exchange_push_grad_kernel");
+    return 0;
+}
+
+extern "C" int rs_exchange_wait_grad(const rs_exchange_grad_args *a, int64_t *status_dev, rs_stream_t stream) {
+    if (int rc = exchange_grad_check(a, "rs_exchange_wait_grad"))
+        return rc;
+    RS_CHECK(status_dev != nullptr, "rs_exchange_wait_grad: status_dev is required");
+    rs_exchange_wait_grad_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(*a, (long long *)status_dev);
+    RS_LAUNCH_CHECK("rs_exchange_wait_grad_kernel");
     return 0;
 }

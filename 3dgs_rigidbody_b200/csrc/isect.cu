@@ -733,7 +733,7 @@ extern "C" int rs_isect_sorted(const rs_isect_sorted_args *b, rs_stream_t stream
         int64_t grid = min((a->capacity + 255) / 256, (int64_t)rs_num_sms() * 8);
         grid = max(grid, (int64_t)rs_num_sms());
         if ((reinterpret_cast<uintptr_t>(tkeys) & 15) == 0)
-            rs_isect_offsets32_kernel<<<(unsigned)min(grid, (int64_t)rs_num_sms() * 4), 256, 0, s>>>(
+            rs_isect_offsets32_kernel<<<(unsigned)grid, 256, 0, s>>>(
                 tkeys, a->capacity, a->n_isects, (uint32_t)a->I, n_tiles, tile_n_bits, b->tile_offsets);
         else
             rs_isect_offsets_kernel<uint32_t><<<(unsigned)grid, 256, 0, s>>>(tkeys, a->capacity, a->n_isects, (uint32_t)a->I,

@@ -195,6 +195,7 @@ class PeerSplatExchange:
     _instances: Dict[Tuple, "PeerSplatExchange"] = {}
     _usable: Dict = {}  # process group -> bool (probed once, collectively)
     enabled: bool = True  # False routes no-grad packed calls through the NCCL all-to-all too (A/B measurements)
+    differentiable: bool = True  # False keeps training (gradients flowing back) on the NCCL all-to-all
     initial_capacity: Optional[int] = None  # rows; None = this rank's row count of the first call (regrown on demand)
     timeout_ms: int = int(os.environ.get("RS_EXCHANGE_TIMEOUT_MS", "0"))  # 0 = the library default (60 s)
 
@@ -235,6 +236,11 @@ class PeerSplatExchange:
         self.epoch = 0
         self.buffers: Optional[_PeerBuffers] = None
         self.totals = torch.zeros(4, dtype=torch.int64, device=device)
+        # transposed exchange (backward): a second peer-mapped allocation per rank + its own epoch counter
+        self.grad_epoch = 0
+        self.grad_buffers: Optional[_PeerBuffers] = None
+        self.grad_status = torch.zeros(2, dtype=torch.int64, device=device)
+        self._last_args = None
 
     def _regrow(self, capacity: int) -> None:
         torch.cuda.synchronize(self.device)
@@ -280,6 +286,7 @@ class PeerSplatExchange:
                                    f"the spin limit (data flags behind: {behind & 0xffff:#x}, count flags behind: "
                                    f"{behind >> 16:#x}); set RS_EXCHANGE_TIMEOUT_MS to wait longer")
             if err == 0:
+                self._last_args = a
                 break
             self._regrow(int(worst * 1.25) + 1024)  # identical decision on every rank: `worst` comes from the full matrix
         b, dev = self.buffers, self.device
@@ -288,3 +295,82 @@ class PeerSplatExchange:
                 b.column(3, got, (), "<f4", torch.float32, dev),
                 b.column(4, got, (self.channels,), "<f4", torch.float32, dev),
                 b.column(6, got, (), "<i8", torch.int64, dev), b.column(7, got, (), "<i8", torch.int64, dev))
+
+
+    # ---- differentiable form: forward = the exchange above, backward = the transposed exchange over peer memory -----------
+    def exchange_differentiable(self, cameras_per_rank: int, indptr: Tensor, camera_ids: Tensor, gaussian_ids: Tensor,
+                                radii: Tensor, means2d: Tensor, depths: Tensor, conics: Tensor, opacities_rows: Tensor,
+                                colors_rows: Tensor, gaussian_base: int):
+        """Same rows as exchange() for per-row opacities / colours ([nnz], [nnz, D]), with gradients flowing back to this
+        rank's packed rows through rs_exchange_push_grad (gsplat/distributed.py:243-248 without NCCL).  The returned
+        tensors are copies (autograd keeps them until the backward pass; the receive arrays are reused by the next call)."""
+        return _PeerExchangeFn.apply(self, cameras_per_rank, indptr, camera_ids, gaussian_ids, radii, gaussian_base,
+                                     means2d, depths, conics, opacities_rows, colors_rows)
+
+    def _read_counts(self) -> Tensor:
+        counts = torch.empty(self.world * self.world, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.rs_exchange_read_counts(ctypes.byref(self._last_args), counts.data_ptr(),
+                                                        torch.cuda.current_stream(self.device).cuda_stream))
+        return counts
+
+    def _push_grads(self, counts: Tensor, grad_capacity: int, nnz_local: int, grads):
+        """grads = (v_means2d, v_depths, v_conics, v_opacities, v_colors) of the rows this rank received -> the gradients of
+        the rows it sent, [nnz_local, ...] each."""
+        if self.grad_buffers is None or self.grad_buffers.capacity < grad_capacity:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+            if self.grad_buffers is not None:
+                self.grad_buffers.release(self.group)
+            self.grad_buffers = _PeerBuffers(self.lib, self.group, self.device, int(grad_capacity * 1.25) + 1024, self.channels)
+        self.grad_epoch += 1
+        keep = [g.contiguous() for g in grads]
+        a = _lib.rs_exchange_grad_args()
+        a.world, a.rank, a.channels, a.timeout_ms = self.world, self.rank, self.channels, int(self.timeout_ms)
+        a.capacity, a.epoch = self.grad_buffers.capacity, self.grad_epoch
+        a.peer_base, a.counts = self.grad_buffers.table.data_ptr(), counts.data_ptr()
+        a.v_means2d, a.v_depths, a.v_conics, a.v_opacities, a.v_colors = [g.data_ptr() for g in keep]
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.rs_exchange_push_grad(ctypes.byref(a), stream))
+            _lib.check(self.lib.rs_exchange_wait_grad(ctypes.byref(a), self.grad_status.data_ptr(), stream))
+        err, behind = self.grad_status.tolist()
+        if err != 0:
+            raise RuntimeError(f"PeerSplatExchange rank {self.rank} backward epoch {self.grad_epoch}: transposed exchange failed "
+                               f"(error {err}, sources behind {behind:#x})")
+        b, dev, n = self.grad_buffers, self.device, nnz_local
+        return (b.column(0, n, (2,), "<f4", torch.float32, dev).clone(), b.column(1, n, (), "<f4", torch.float32, dev).clone(),
+                b.column(2, n, (3,), "<f4", torch.float32, dev).clone(), b.column(3, n, (), "<f4", torch.float32, dev).clone(),
+                b.column(4, n, (self.channels,), "<f4", torch.float32, dev).clone())
+
+
+class _PeerExchangeFn(torch.autograd.Function):
+    """Row exchange over NVLink peer memory as an autograd node: backward is the transposed exchange."""
+
+    @staticmethod
+    def forward(ctx, peer: PeerSplatExchange, cameras_per_rank, indptr, camera_ids, gaussian_ids, radii, gaussian_base,
+                means2d, depths, conics, opacities_rows, colors_rows):
+        out = peer.exchange(cameras_per_rank, indptr, camera_ids, gaussian_ids, radii, means2d.detach(), depths.detach(),
+                            conics.detach(), None, opacities_rows.detach(), True, colors_rows.detach(), True, gaussian_base)
+        ctx.peer, ctx.nnz_local = peer, int(means2d.shape[0])
+        ctx.counts = peer._read_counts()
+        # every rank's gradient arrays share one layout, so they are sized for the largest row count any rank sent
+        cap = torch.tensor([ctx.nnz_local], dtype=torch.int64, device=peer.device)
+        dist.all_reduce(cap, op=dist.ReduceOp.MAX, group=peer.group)
+        ctx.grad_capacity = int(cap.item())
+        radii_r, m2, d, con, op, col, cam, gid = (t.clone() for t in out)
+        ctx.mark_non_differentiable(radii_r, cam, gid)
+        return radii_r, m2, d, con, op, col, cam, gid
+
+    @staticmethod
+    def backward(ctx, _v_radii, v_m2, v_d, v_con, v_op, v_col, _v_cam, _v_gid):
+        peer = ctx.peer
+        got = int(ctx.counts.view(peer.world, peer.world)[:, peer.rank].sum().item())
+        dev = peer.device
+
+        def dense(v, tail):
+            return v if v is not None else torch.zeros((got,) + tail, dtype=torch.float32, device=dev)
+
+        grads = (dense(v_m2, (2,)), dense(v_d, ()), dense(v_con, (3,)), dense(v_op, ()), dense(v_col, (peer.channels,)))
+        g_m2, g_d, g_con, g_op, g_col = peer._push_grads(ctx.counts, ctx.grad_capacity, ctx.nnz_local, grads)
+        return (None,) * 7 + (g_m2, g_d, g_con, g_op, g_col)

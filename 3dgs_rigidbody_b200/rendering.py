@@ -213,12 +213,15 @@ def rasterization(
     # differentiable all-to-all below.
     needs_grad = torch.is_grad_enabled() and any(
         t is not None and t.requires_grad for t in (means, quats, scales, covars, opacities, colors, viewmats))
-    peer_path = shard is not None and packed and means.is_cuda and not needs_grad
-    if peer_path:
+    peer_path = peer_grad = False
+    if shard is not None and packed and means.is_cuda:
         from .distributed import PeerSplatExchange
 
         # same host, peer access between all devices, <= 16 ranks -- else the NCCL route below (probed once per group)
-        peer_path = PeerSplatExchange.enabled and PeerSplatExchange.usable(shard.group, device)
+        usable = PeerSplatExchange.enabled and PeerSplatExchange.usable(shard.group, device)
+        peer_path = usable and not needs_grad
+        # training: the same exchange as an autograd node whose backward is the transposed peer-memory exchange
+        peer_grad = usable and needs_grad and PeerSplatExchange.differentiable
 
     # ---- 1. project (rigid transform fused in; without gradients also the SH colours) -------------------------------------
     from . import _C
@@ -289,6 +292,18 @@ def rasterization(
         radii, means2d, depths, conics, alpha_in, shaded, camera_ids, gaussian_ids = peer.exchange(
             shard.local_cameras, indptr, camera_ids, gaussian_ids, radii, means2d, depths, conics, compensations,
             opacities, False, table, per_row, shard.gaussian_base)
+        d.C = shard.local_cameras
+        n_images = d.C
+        image_ids = camera_ids
+        batch_ids = torch.zeros_like(camera_ids)
+    elif peer_grad:
+        n_ch = int(shaded.shape[-1])
+        peer = PeerSplatExchange.get(shard.group, device, n_ch)
+        edges = torch.arange(d.C + 1, device=device, dtype=camera_ids.dtype)
+        indptr = torch.searchsorted(camera_ids.contiguous(), edges).to(torch.int32)  # rows are ordered by camera
+        radii, means2d, depths, conics, alpha_in, shaded, camera_ids, gaussian_ids = peer.exchange_differentiable(
+            shard.local_cameras, indptr, camera_ids, gaussian_ids, radii, means2d, depths, conics, alpha_in,
+            shaded.reshape(-1, n_ch), shard.gaussian_base)
         d.C = shard.local_cameras
         n_images = d.C
         image_ids = camera_ids

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RS_ABI_VERSION 12
+#define RS_ABI_VERSION 13
 
 /* gsplat/cuda/include/Common.h:46-51 (CameraModelType) */
 enum { RS_PINHOLE = 0, RS_ORTHO = 1, RS_FISHEYE = 2, RS_FTHETA = 3 };
@@ -37,7 +37,7 @@ int rs_abi_version(void);
 const char *rs_last_error(void);
 /* sizeof() of every args struct, for binding self-checks: which = 0 project_fwd, 1 project_bwd, 2 isect,
  * 3 sort, 4 raster_fwd, 5 raster_bwd, 6 frame, 7 rigid, 8 isect_sorted, 9 sh, 10 project_packed_fwd, 11 exchange, 12 cgc,
- * 13 seghead.  Returns 0 for an unknown id. */
+ * 13 seghead, 14 exchange_grad.  Returns 0 for an unknown id. */
 uint64_t rs_sizeof_args(int which);
 /* number of kernels this library has launched in this process (all threads); bench.py reports its delta over the
  * timed region as `gpu_launches`. */
@@ -224,6 +224,28 @@ int rs_exchange_push(const rs_exchange_args *a, rs_stream_t stream);
  * exceeded -- nothing was written for the overfull destination, diagnostics: bit s = source s's data flag is behind,
  * bit 16 + s = its count flag is behind} */
 int rs_exchange_wait(const rs_exchange_args *a, int64_t *totals_dev, rs_stream_t stream);
+
+/* The transposed exchange (backward of the above; replaces the backward of the differentiable all_to_all of
+ * gsplat/distributed.py:243-248): gradients of the rows this rank RECEIVED are stored straight into the gradient arrays of
+ * the ranks that sent them, at the positions of their packed rows.  rs_exchange_read_counts keeps the forward exchange's
+ * W x W row-count matrix (counts[s * world + d] = rows source s sent to destination d) so that no handshake is needed later.
+ * Every rank owns a SECOND receive allocation for gradients (rs_exchange_layout(capacity >= its own row count, channels);
+ * only the float columns means2d | depths | conics | opacities | colors are used), mapped by every peer. */
+typedef struct {
+    int32_t world, rank, channels;
+    int32_t timeout_ms;          /* spin limit of rs_exchange_wait_grad, 0 = default */
+    int64_t capacity;            /* rows of every rank's gradient arrays */
+    uint32_t epoch;              /* backward counter, > 0, the same on every rank, +1 per transposed exchange */
+    int32_t _pad;
+    void *const *peer_base;      /* device array [world]: this rank's mapping of every rank's GRADIENT allocation */
+    const int32_t *counts;       /* device [world * world], from rs_exchange_read_counts of the matching forward */
+    const float *v_means2d, *v_depths, *v_conics, *v_opacities, *v_colors; /* gradients of the received rows, forward order */
+} rs_exchange_grad_args;
+int rs_exchange_read_counts(const rs_exchange_args *a, int32_t *counts_dev /* [world * world] device */, rs_stream_t stream);
+int rs_exchange_push_grad(const rs_exchange_grad_args *a, rs_stream_t stream);
+/* hold `stream` until every peer's gradient rows of this epoch have landed; status_dev (device int64[2]) = {error: 0 ok |
+ * 1 timeout | 2 a block did not fit, sources whose flag is behind (bit s)} */
+int rs_exchange_wait_grad(const rs_exchange_grad_args *a, int64_t *status_dev, rs_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Tile intersection.  Replaces `intersect_tile` (Ops.h:186-198, csrc/Intersect.cpp:15-149, kernels

@@ -23,12 +23,12 @@ def test_struct_layouts_match(rs):
     order = [_lib.rs_project_fwd_args, _lib.rs_project_bwd_args, _lib.rs_isect_args, _lib.rs_sort_args,
              _lib.rs_raster_fwd_args, _lib.rs_raster_bwd_args, _lib.rs_frame_args, _lib.rs_rigid_t,
              _lib.rs_isect_sorted_args, _lib.rs_sh_args, _lib.rs_project_packed_fwd_args, _lib.rs_exchange_args, _lib.rs_cgc_args,
-             _lib.rs_seghead_args]
+             _lib.rs_seghead_args, _lib.rs_exchange_grad_args]
     for which, st in enumerate(order):
         assert lib.rs_sizeof_args(which) == ctypes.sizeof(st), st.__name__
     assert lib.rs_sizeof_args(99) == 0
     header_version = int(re.search(r"#define\s+RS_ABI_VERSION\s+(\d+)", open(_lib.HEADER).read()).group(1))
-    assert lib.rs_abi_version() == header_version >= 12
+    assert lib.rs_abi_version() == header_version >= 13
 
 
 def test_host_only_entry_points(rs):

@@ -162,3 +162,73 @@ def test_peer_memory_exchange_equals_nccl_exchange(rs):
         p.join(timeout=60)
     for rank, msg in results:
         assert msg == "ok", f"rank {rank}:\n{msg}"
+
+
+def _peer_grad_worker(rank, world, port, q):
+    """Training through the peer-memory exchange: forward rows pushed over NVLink, gradients pushed back by the transposed
+    exchange (rs_exchange_push_grad) -- against the differentiable NCCL all-to-all route on the same inputs, two steps in a row
+    (the second reuses the persistent gradient arrays), plus the single-GPU gradients of this rank's shard."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from conftest import pinhole_cameras, synthetic_scene
+
+        rs = importlib.import_module("3dgs_rigidbody_b200")
+        dmod = importlib.import_module("3dgs_rigidbody_b200.distributed")
+        W, H, N, Cl = 256, 192, 24_000, 2
+        s = synthetic_scene(5, N, K=3)
+        vm, Ks = pinhole_cameras(world * Cl, W, H)
+        t = {k: torch.from_numpy(v).to(dev) for k, v in s.items()}
+        vm, Ks = torch.from_numpy(vm).to(dev), torch.from_numpy(Ks).to(dev)
+        mine = slice(rank * Cl, (rank + 1) * Cl)
+        lo, hi = rank * N // world, (rank + 1) * N // world
+        g = torch.Generator(device=dev).manual_seed(11)
+        wgt = torch.rand(Cl, H, W, 3, device=dev, generator=g)
+        rigid = dict(cluster_ids=t["cluster_ids"][lo:hi], body_quats=t["body_quats"], body_trans=t["body_trans"],
+                     body_centers=t["body_centers"])
+        names = ("means", "quats", "scales", "opacities", "colors")
+
+        def step(route_peer, shift):
+            dmod.PeerSplatExchange.differentiable = route_peer
+            leaves = [t[k][lo:hi].clone().requires_grad_(True) for k in names]
+            leaves[0].data += shift
+            img, alpha, meta = rs.rasterization(*leaves, vm[mine], Ks[mine], W, H, packed=True, distributed=True, **rigid)
+            ((img * wgt).sum() + alpha.sum()).backward()
+            return img.detach(), [l.grad.clone() for l in leaves]
+
+        for shift in (0.0, 0.05):
+            img_n, grads_n = step(False, shift)
+            img_p, grads_p = step(True, shift)
+            assert torch.equal(img_p, img_n), shift
+            for name, gp, gn in zip(names, grads_p, grads_n):
+                scale = max(float(gn.abs().max()), 1e-12)
+                assert float((gp - gn).abs().max()) <= 2e-4 * scale, (shift, name, float((gp - gn).abs().max()), scale)
+                assert float(gn.abs().sum()) > 0 or name == "quats"
+        peer = next(p for p in dmod.PeerSplatExchange._instances.values() if p.grad_buffers is not None)
+        assert peer.grad_epoch == 2
+        q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_peer_memory_backward_equals_nccl_backward(rs):
+    world = min(torch.cuda.device_count(), 8)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_grad_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in results:
+        assert msg == "ok", f"rank {rank}:\n{msg}"

@@ -34,11 +34,14 @@ def main():
         for b in range(6):
             mask[20 + a * 260:20 + a * 260 + 240, 20 + b * 315:20 + b * 315 + 290] = 1 + a * 6 + b
     tables = rs.cluster_tables(mask, 30)
+    torch.manual_seed(0)
+    head = rs.SegmentationHead(16, 64).to(dev)
     for step in range(args.steps):
         bq, bt = bench.domino_poses(bench.N_BODIES, frame=60 + step, device=dev, centers=sc["body_centers"])
-        for t in leaves + [feats]:
+        for t in leaves + [feats] + list(head.parameters()):
             t.grad = None
-        img, _, _ = rs.rasterization(*leaves, feats, sc["viewmats"], sc["Ks"], W, H, packed=False, cluster_ids=sc["cluster_ids"],
+        processed = head(feats)  # examples/simple_trainer.py:946-947
+        img, _, _ = rs.rasterization(*leaves, processed, sc["viewmats"], sc["Ks"], W, H, packed=False, cluster_ids=sc["cluster_ids"],
                                      body_quats=bq, body_trans=bt, body_centers=sc["body_centers"])
         loss = (img * w).sum() + rs.cgc_contrastive_clustering_loss(img[0], mask, tables=tables)
         loss.backward()

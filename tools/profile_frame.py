@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """One c2 frame at a time through FrameRenderer on a single stream: the target of the `ncu --set full` captures.
 
-    ncu --set full --clock-control none --import-source on -s <14 * warm-up frames> -c 14 -o gpurun_out/prof \
+    ncu --set full --clock-control none --import-source on -s <13 * warm-up frames> -c 13 -o gpurun_out/prof \
         python tools/profile_frame.py --frames 4
-A frame is 14 kernel launches (projection, tile count, scan, 2 histograms, 6 sort passes, emission, offsets, compositing);
+A frame is 13 kernel launches (projection; depth order: min/max, count, scan, scatter, sort; tile count, scan, emission; 2
+tile-key radix passes; offsets; compositing);
 `--packed` profiles the packed projection instead (1 launch per frame)."""
 import argparse
 import importlib
