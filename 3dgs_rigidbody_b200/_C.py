@@ -403,6 +403,25 @@ def projection_ewa_3dgs_packed_bwd(
 # ---------------------------------------------------------------------------------------------------------------------
 # tile intersection (Ops.h:186-204; csrc/Intersect.cpp:15-168)
 # ---------------------------------------------------------------------------------------------------------------------
+# The per-tile offsets fall out of the depth-ordered binning for free (32-bit tile keys, rs_isect_sorted.tile_offsets).  They
+# are kept for the one isect_ids tensor the last sorted intersect_tile() returned; intersect_offset() hands them out when it is
+# called with that very tensor object, unmodified -- which is what rasterization() does (rendering.py:880-892: isect_tiles ->
+# isect_offset_encode) -- instead of re-deriving them from the 64-bit ids.
+_OFFSETS_CACHE: dict = {}
+
+
+def _remember_offsets(isect_ids: Tensor, offsets: Tensor, I: int, tile_width: int, tile_height: int) -> None:
+    import weakref
+
+    _OFFSETS_CACHE.clear()
+    _OFFSETS_CACHE["entry"] = (weakref.ref(isect_ids), isect_ids._version, int(I), int(tile_width), int(tile_height), offsets)
+
+
+# n_isects of the last sorted intersect_tile() call per problem shape: sizes the outputs of the next call of that shape so
+# that it needs no host round trip before the sort (see intersect_tile)
+_ISECT_CAPACITY_HINT: dict = {}
+
+
 def intersect_tile(
     means2d: Tensor,  # [..., N, 2] or [nnz, 2]
     radii: Tensor,  # [..., N, 2] or [nnz, 2]
@@ -444,6 +463,34 @@ def intersect_tile(
         a.capacity = 0
         n_isects = 0
         s = _stream()
+        hint_key = (dev.index, n_elems, int(I), int(tile_width), int(tile_height))
+        hint = _ISECT_CAPACITY_HINT.get(hint_key) if (sort and n_elems > 0) else None
+        if hint is not None:
+            # Same problem shape as an earlier call: size the outputs from that call's count (+25 %) and enqueue count,
+            # ordering, emission and sort back to back; the ONE host read of the call (the reference syncs mid-way,
+            # csrc/Intersect.cpp:79-80) moves to the end, where it overlaps with the sort instead of stalling the stream.
+            cap = int(hint * 1.25) + 1024
+            isect_ids = torch.empty(cap, dtype=torch.int64, device=dev)
+            flatten_ids = torch.empty(cap, dtype=torch.int32, device=dev)
+            status = torch.empty(2, dtype=torch.int32, device=dev)
+            _lib.check(lib.rs_isect_count(ctypes.byref(a), s))
+            sa = _lib.rs_isect_sorted_args()
+            ctypes.memmove(ctypes.byref(sa.isect), ctypes.byref(a), ctypes.sizeof(a))
+            sa.isect.isect_ids, sa.isect.flatten_ids, sa.isect.capacity = _ptr(isect_ids), _ptr(flatten_ids), cap
+            sa.isect.n_isects, sa.isect.overflow = status.data_ptr(), status.data_ptr() + 4
+            ws_bytes = lib.rs_isect_sorted_workspace_bytes(n_elems, cap)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            offsets = torch.empty((int(I), int(tile_height), int(tile_width)), dtype=torch.int32, device=dev)
+            sa.tile_offsets = offsets.data_ptr()
+            sa.workspace, sa.workspace_bytes = ws.data_ptr(), ws_bytes
+            _lib.check(lib.rs_isect_sorted(ctypes.byref(sa), s))
+            n_isects, overflow = status.tolist()
+            _ISECT_CAPACITY_HINT[hint_key] = max(n_isects, 1)
+            if not overflow:
+                ids_view = isect_ids[:n_isects]
+                _remember_offsets(ids_view, offsets, I, tile_width, tile_height)
+                return tiles_per_gauss, ids_view, flatten_ids[:n_isects]
+            # more intersections than the hint allowed for: fall through to the exactly sized path
         if n_elems > 0:
             _lib.check(lib.rs_isect_count(ctypes.byref(a), s))
             _lib.check(lib.rs_isect_scan(ctypes.byref(a), s))
@@ -451,6 +498,8 @@ def intersect_tile(
             # the one host sync of the compat path (csrc/Intersect.cpp:79-80)
             _lib.check(lib.rs_isect_count_total(ctypes.byref(a), s, ctypes.byref(out)))
             n_isects = out.value
+            if sort:
+                _ISECT_CAPACITY_HINT[hint_key] = max(n_isects, 1)
         isect_ids = torch.empty(n_isects, dtype=torch.int64, device=dev)
         flatten_ids = torch.empty(n_isects, dtype=torch.int32, device=dev)
         if n_isects > 0:
@@ -464,15 +513,21 @@ def intersect_tile(
                 ctypes.memmove(ctypes.byref(sa.isect), ctypes.byref(a), ctypes.sizeof(a))
                 ws_bytes = lib.rs_isect_sorted_workspace_bytes(n_elems, n_isects)
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-                sa.tile_offsets = None
+                offsets = torch.empty((int(I), int(tile_height), int(tile_width)), dtype=torch.int32, device=dev)
+                sa.tile_offsets = offsets.data_ptr()
                 sa.workspace, sa.workspace_bytes = ws.data_ptr(), ws_bytes
                 _lib.check(lib.rs_isect_sorted(ctypes.byref(sa), s))
+                _remember_offsets(isect_ids, offsets, I, tile_width, tile_height)
     return tiles_per_gauss, isect_ids, flatten_ids
 
 
 def intersect_offset(isect_ids: Tensor, I: int, tile_width: int, tile_height: int) -> Tensor:
     lib = _lib.load()
     _check(isect_ids, "isect_ids", torch.int64)
+    hit = _OFFSETS_CACHE.get("entry")
+    if hit is not None and hit[0]() is isect_ids and hit[1] == isect_ids._version and hit[2:5] == (int(I), int(tile_width),
+                                                                                                 int(tile_height)):
+        return hit[5].clone()  # the caller owns its result (a second call must not alias the first)
     dev = isect_ids.device
     with torch.cuda.device(dev):
         offsets = torch.empty((I, tile_height, tile_width), dtype=torch.int32, device=dev)

@@ -9,17 +9,17 @@
 //     the 5 steps a lane keeps one half of its values and trades the other half, so the whole vector costs ~NV shuffles
 //     instead of 5*NV, and the totals end up spread over NV lanes which then issue ONE predicated red.global each.
 //   * per-lane destination pointers (which output array / component a lane ends up owning) are computed once per thread.
-//   * CTA-level reduction: the eight warps of a tile all touch the same splats, so instead of one red.global per (warp,
-//     splat, component) the owning lanes add into a shared-memory accumulator [256 splats][NV] (odd pitch: the NV lanes of
-//     one splat hit NV different banks) and the CTA flushes ONE red.global per (tile, splat, component) when it moves on to
-//     the next batch -- 2-3x fewer global atomics, and none of them contended inside the CTA.  (-DRS_BWD_SMEM_REDUCE=0
-//     builds the per-warp variant for A/B runs.)
+//   * (experiment, off by default: -DRS_BWD_SMEM_REDUCE=1) CTA-level reduction: the owning lanes add into a shared-memory
+//     accumulator [256 splats][NV] and the CTA flushes ONE red.global per (tile, splat, component) per batch.  Measured
+//     SLOWER -- 1.63 ms vs 1.03 ms at c3 (profiles/r02_raster_bwd_smem_reduce_experiment.txt): float atomicAdd on shared
+//     memory is a compare-and-swap loop that spins when the eight warps of a tile hit the same words, while red.global is
+//     a fire-and-forget L2 operation.
 // Per-pixel math follows RasterizeToPixels3DGSBwd.cu:160-242.
 #include "common.cuh"
 
 #define RAST_THREADS 256
 #ifndef RS_BWD_SMEM_REDUCE
-#define RS_BWD_SMEM_REDUCE 1
+#define RS_BWD_SMEM_REDUCE 0
 #endif
 
 int rs_check_raster_args(const rs_raster_fwd_args *a, const char *who);

@@ -151,8 +151,11 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v) {
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// resident CTAs per SM the pass kernel is compiled for (register cap) and launched with: 58 KB (u32) / 74 KB (u64) of
+// shared memory per CTA at 16 items per thread; larger tiles (-DSORT_ITEMS=24|32 experiments) leave room for fewer CTAs
+#define SORT_CTAS_PER_SM(KeyT) (SORT_ITEMS <= 16 ? (sizeof(KeyT) == 4 ? 3 : 2) : (SORT_ITEMS <= 24 && sizeof(KeyT) == 4 ? 2 : 1))
 template <typename KeyT>
-__global__ void __launch_bounds__(SORT_THREADS, sizeof(KeyT) == 4 ? 3 : 2)
+__global__ void __launch_bounds__(SORT_THREADS, SORT_CTAS_PER_SM(KeyT))
 sort_pass_kernel(const KeyT *__restrict__ keys_in, const int32_t *__restrict__ vals_in, KeyT *__restrict__ keys_out,
                  int32_t *__restrict__ vals_out, int64_t n_bound, const int32_t *__restrict__ n_dev, int shift,
                  uint32_t mask, int pass, int nb_stride, uint32_t *__restrict__ ws) {
@@ -387,7 +390,7 @@ static int radix_sort_impl(int64_t n_bound, const int32_t *n_dev, int begin_bit,
                                                                   ws);
         RS_LAUNCH_CHECK("sort_hist_kernel");
     }
-    const int pass_grid = min(nb, sms * (sizeof(KeyT) == 4 ? 3 : 2));
+    const int pass_grid = min(nb, sms * SORT_CTAS_PER_SM(KeyT));
     const KeyT *kin = keys_in;
     const int32_t *vin = vals_in;
     for (int p = 0; p < passes; ++p) {

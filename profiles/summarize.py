@@ -59,8 +59,35 @@ def raw(path):
         print(" ".join(out))
 
 
+def traffic(paths, source):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch and kernel (median launch) -> JSON for bench.py's
+    `roofline.traffic` (profiles/r02_kernel_traffic.json)."""
+    import json
+    import re
+
+    out = {}
+    for path in paths:
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        ki, ri, wi, ti = (hdr.index(k) for k in ("Kernel Name", "dram__bytes_read.sum", "dram__bytes_write.sum",
+                                                 "gpu__time_duration.sum"))
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        per = collections.OrderedDict()
+        for r in rows[2:]:
+            name = re.sub(r"^void ", "", r[ki]).split("<")[0].split("(")[0]
+            b = float(r[ri].replace(",", "")) * scale[units[ri]] + float(r[wi].replace(",", "")) * scale[units[wi]]
+            per.setdefault(name, []).append((b, float(r[ti].replace(",", "")), units[ti]))
+        for name, v in per.items():
+            v.sort()
+            b, t, tu = v[len(v) // 2]
+            out[name] = {"dram_bytes_per_launch": int(b), "launches_captured": len(v), "time": f"{t:g} {tu}"}
+    print(json.dumps({"source": source, "kernels": out}, indent=1))
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], int(sys.argv[3]))
+    elif sys.argv[1] == "traffic":
+        traffic(sys.argv[3:], sys.argv[2])
     else:
         raw(sys.argv[2])

@@ -130,6 +130,29 @@ def test_isect_sort_offsets_bit_exact_vs_reference_cuda(rs, ref, W, H, C):
     assert torch.equal(ids_ou, ids_tu) and torch.equal(flat_ou, flat_tu)
 
 
+def test_intersect_tile_capacity_hint_path_is_exact(rs, ref):
+    """The second sorted intersect_tile() call of a problem shape sizes its outputs from the first call's count and reads the
+    count back only after the sort is enqueued; a frame with MORE intersections than the hint allows must fall back to the
+    exactly sized path.  All three calls against the reference's kernel + cub sort, bit for bit."""
+    W, H, C = 640, 360, 2
+    s = synthetic_scene(33, 40_000, s_max=0.05, spread=1.5)
+    vm, Ks = pinhole_cameras(C, W, H)
+    ours, _ = project_both(rs, ref, s, vm, Ks, W, H)
+    radii, means2d, depths = ours[0], ours[1], ours[2]
+    tw, th = (W + 15) // 16, (H + 15) // 16
+    rs._C._ISECT_CAPACITY_HINT.clear()
+    sizes = []
+    for scale in (1, 1, 4, 1):  # first call (exact path), hint path, overflow of the hint, hint path again
+        r = torch.where(radii > 0, radii * scale, radii)
+        a = (means2d, r, depths, None, None, C, 16, tw, th, True, False)
+        tpg_o, ids_o, flat_o = rs._C.intersect_tile(*a)
+        tpg_t, ids_t, flat_t = ref.intersect_tile(*a)
+        assert torch.equal(tpg_o, tpg_t) and torch.equal(ids_o, ids_t) and torch.equal(flat_o, flat_t), scale
+        assert torch.equal(rs._C.intersect_offset(ids_o, C, tw, th), ref.intersect_offset(ids_t, C, tw, th))
+        sizes.append(ids_o.numel())
+    assert sizes[2] > 2 * sizes[1] and sizes[3] == sizes[0]
+
+
 def _raster_inputs(rs, ref, seed, N, W, H, C, D):
     s = synthetic_scene(seed, N, s_max=0.08)
     vm, Ks = pinhole_cameras(C, W, H)
