@@ -417,11 +417,6 @@ def _remember_offsets(isect_ids: Tensor, offsets: Tensor, I: int, tile_width: in
     _OFFSETS_CACHE["entry"] = (weakref.ref(isect_ids), isect_ids._version, int(I), int(tile_width), int(tile_height), offsets)
 
 
-# n_isects of the last sorted intersect_tile() call per problem shape: sizes the outputs of the next call of that shape so
-# that it needs no host round trip before the sort (see intersect_tile)
-_ISECT_CAPACITY_HINT: dict = {}
-
-
 def intersect_tile(
     means2d: Tensor,  # [..., N, 2] or [nnz, 2]
     radii: Tensor,  # [..., N, 2] or [nnz, 2]
@@ -463,34 +458,6 @@ def intersect_tile(
         a.capacity = 0
         n_isects = 0
         s = _stream()
-        hint_key = (dev.index, n_elems, int(I), int(tile_width), int(tile_height))
-        hint = _ISECT_CAPACITY_HINT.get(hint_key) if (sort and n_elems > 0) else None
-        if hint is not None:
-            # Same problem shape as an earlier call: size the outputs from that call's count (+25 %) and enqueue count,
-            # ordering, emission and sort back to back; the ONE host read of the call (the reference syncs mid-way,
-            # csrc/Intersect.cpp:79-80) moves to the end, where it overlaps with the sort instead of stalling the stream.
-            cap = int(hint * 1.25) + 1024
-            isect_ids = torch.empty(cap, dtype=torch.int64, device=dev)
-            flatten_ids = torch.empty(cap, dtype=torch.int32, device=dev)
-            status = torch.empty(2, dtype=torch.int32, device=dev)
-            _lib.check(lib.rs_isect_count(ctypes.byref(a), s))
-            sa = _lib.rs_isect_sorted_args()
-            ctypes.memmove(ctypes.byref(sa.isect), ctypes.byref(a), ctypes.sizeof(a))
-            sa.isect.isect_ids, sa.isect.flatten_ids, sa.isect.capacity = _ptr(isect_ids), _ptr(flatten_ids), cap
-            sa.isect.n_isects, sa.isect.overflow = status.data_ptr(), status.data_ptr() + 4
-            ws_bytes = lib.rs_isect_sorted_workspace_bytes(n_elems, cap)
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-            offsets = torch.empty((int(I), int(tile_height), int(tile_width)), dtype=torch.int32, device=dev)
-            sa.tile_offsets = offsets.data_ptr()
-            sa.workspace, sa.workspace_bytes = ws.data_ptr(), ws_bytes
-            _lib.check(lib.rs_isect_sorted(ctypes.byref(sa), s))
-            n_isects, overflow = status.tolist()
-            _ISECT_CAPACITY_HINT[hint_key] = max(n_isects, 1)
-            if not overflow:
-                ids_view = isect_ids[:n_isects]
-                _remember_offsets(ids_view, offsets, I, tile_width, tile_height)
-                return tiles_per_gauss, ids_view, flatten_ids[:n_isects]
-            # more intersections than the hint allowed for: fall through to the exactly sized path
         if n_elems > 0:
             _lib.check(lib.rs_isect_count(ctypes.byref(a), s))
             _lib.check(lib.rs_isect_scan(ctypes.byref(a), s))
@@ -498,8 +465,6 @@ def intersect_tile(
             # the one host sync of the compat path (csrc/Intersect.cpp:79-80)
             _lib.check(lib.rs_isect_count_total(ctypes.byref(a), s, ctypes.byref(out)))
             n_isects = out.value
-            if sort:
-                _ISECT_CAPACITY_HINT[hint_key] = max(n_isects, 1)
         isect_ids = torch.empty(n_isects, dtype=torch.int64, device=dev)
         flatten_ids = torch.empty(n_isects, dtype=torch.int32, device=dev)
         if n_isects > 0:

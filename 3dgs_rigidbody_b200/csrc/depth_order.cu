@@ -486,8 +486,20 @@ DordLayout dord_layout(int64_t n_elems) {
 uint64_t rs_depth_order_workspace_bytes(int64_t n_elems) { return dord_layout(n_elems).total; }
 
 // elems_out[0 .. V) = visible elements (tiles[e] > 0) in ascending (depth bits, index) order; *n_sorted_dev = V.
+// clears header, look-back words and bucket counters of a depth-order workspace (one memset)
+int rs_depth_order_prepare(void *workspace, int64_t n_elems, cudaStream_t s) {
+    const DordLayout L = dord_layout(n_elems);
+    char *w = reinterpret_cast<char *>(workspace);
+    RS_CUDA(cudaMemsetAsync(w + L.hdr, 0, L.counts + ((size_t)4 << dord_bucket_bits(n_elems)) - L.hdr, s));
+    return 0;
+}
+// the three words {max(~bits), max(bits), visible rows} a fused producer accumulates (DordHeader's first fields)
+uint32_t *rs_depth_order_stats_ptr(void *workspace, int64_t n_elems) {
+    return reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(workspace) + dord_layout(n_elems).hdr);
+}
+
 int rs_depth_order(int64_t n_elems, const float *depths, const int32_t *tiles, int32_t *elems_out, int32_t *n_sorted_dev,
-                   void *workspace, uint64_t workspace_bytes, cudaStream_t s) {
+                   void *workspace, uint64_t workspace_bytes, cudaStream_t s, bool stats_ready) {
     RS_CHECK(n_elems >= 0 && n_elems < ((int64_t)1 << 31), "rs_depth_order: bad element count");
     RS_CHECK(n_sorted_dev != nullptr, "rs_depth_order: n_sorted_dev is required");
     if (n_elems == 0) {
@@ -505,13 +517,15 @@ int rs_depth_order(int64_t n_elems, const float *depths, const int32_t *tiles, i
     unsigned int *group_start = reinterpret_cast<unsigned int *>(w + L.group_start);
     unsigned long long *comp = reinterpret_cast<unsigned long long *>(w + L.comp);
     unsigned long long *comp_alt = reinterpret_cast<unsigned long long *>(w + L.comp_alt);
-    // header + bucket counters in one clear (they are adjacent)
     const int bits = dord_bucket_bits(n_elems);
-    RS_CUDA(cudaMemsetAsync(w + L.hdr, 0, L.counts + ((size_t)4 << bits) - L.hdr, s));
     const int sms = rs_num_sms();
     const int grid = (int)min((int64_t)sms * 8, (n_elems + DORD_THREADS - 1) / DORD_THREADS);
-    rs_dord_minmax_kernel<<<grid, DORD_THREADS, 0, s>>>(n_elems, depths, tiles, hdr);
-    RS_LAUNCH_CHECK("rs_dord_minmax_kernel");
+    if (!stats_ready) { // else: cleared by rs_depth_order_prepare, statistics accumulated by the projection kernel
+        if (int e = rs_depth_order_prepare(workspace, n_elems, s))
+            return e;
+        rs_dord_minmax_kernel<<<grid, DORD_THREADS, 0, s>>>(n_elems, depths, tiles, hdr);
+        RS_LAUNCH_CHECK("rs_dord_minmax_kernel");
+    }
     rs_dord_count_kernel<<<grid, DORD_THREADS, 0, s>>>(n_elems, depths, tiles, hdr, counts, bits);
     RS_LAUNCH_CHECK("rs_dord_count_kernel");
     rs_dord_scan_kernel<<<(1 << bits) / DORD_SCAN_PER_CTA, DORD_SCAN_THREADS, 0, s>>>(hdr, counts, state, group_start,

@@ -174,6 +174,14 @@ static int render_frame_impl(const rs_frame_args *a, rs_stream_t stream, cudaEve
     const bool do_bin = a->stages == 0 || (a->stages & RS_FRAME_BIN), do_composite = a->stages == 0 || (a->stages & RS_FRAME_COMPOSITE);
     if (ev)
         RS_CUDA(cudaEventRecord(ev[0], s));
+    // the depth statistics the ordering starts from (min / max of the visible depth bits, their number) come out of the
+    // projection kernel: one kernel and one pass over depths + tile counts less per frame
+    const int64_t E = (int64_t)p.C * p.N;
+    if (do_bin && E > 0) {
+        if (int e = rs_isect_sorted_prepare(w + L.bin_ws, E, a->max_isects, stream))
+            return e;
+        p.depth_stats = rs_isect_sorted_depth_stats(w + L.bin_ws, E, a->max_isects);
+    }
     if (do_bin)
         if (int e = rs_project_fwd(&p, stream))
             return e;
@@ -187,6 +195,7 @@ static int render_frame_impl(const rs_frame_args *a, rs_stream_t stream, cudaEve
     sa.tile_offsets = offsets;
     sa.workspace = w + L.bin_ws;
     sa.workspace_bytes = L.bin_ws_bytes;
+    sa.depth_stats_ready = p.depth_stats != nullptr ? 1 : 0;
     if (do_bin)
         if (int e = rs_isect_sorted(&sa, stream))
             return e;

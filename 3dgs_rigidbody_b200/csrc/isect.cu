@@ -405,7 +405,9 @@ int rs_sort_ws_prepare(void *workspace, cudaStream_t s);
 // depth_order.cu
 uint64_t rs_depth_order_workspace_bytes(int64_t n_elems);
 int rs_depth_order(int64_t n_elems, const float *depths, const int32_t *tiles, int32_t *elems_out, int32_t *n_sorted_dev,
-                   void *workspace, uint64_t workspace_bytes, cudaStream_t s);
+                   void *workspace, uint64_t workspace_bytes, cudaStream_t s, bool stats_ready);
+int rs_depth_order_prepare(void *workspace, int64_t n_elems, cudaStream_t s);
+uint32_t *rs_depth_order_stats_ptr(void *workspace, int64_t n_elems);
 
 // block sums of the tile counts taken in depth order
 __global__ void __launch_bounds__(RS_ISECT_THREADS)
@@ -661,6 +663,18 @@ extern "C" uint64_t rs_isect_sorted_workspace_bytes(int64_t n_elems, int64_t cap
     return bin_layout(n_elems, capacity).total;
 }
 
+extern "C" int rs_isect_sorted_prepare(void *workspace, int64_t n_elems, int64_t capacity, rs_stream_t stream) {
+    RS_CHECK(workspace != nullptr && n_elems >= 0 && capacity >= 0, "rs_isect_sorted_prepare: bad arguments");
+    const BinLayout L = bin_layout(n_elems, capacity);
+    return rs_depth_order_prepare(reinterpret_cast<char *>(workspace) + L.dord_ws, n_elems > 0 ? n_elems : 1, (cudaStream_t)stream);
+}
+extern "C" uint32_t *rs_isect_sorted_depth_stats(void *workspace, int64_t n_elems, int64_t capacity) {
+    if (workspace == nullptr || n_elems < 0 || capacity < 0)
+        return nullptr;
+    const BinLayout L = bin_layout(n_elems, capacity);
+    return rs_depth_order_stats_ptr(reinterpret_cast<char *>(workspace) + L.dord_ws, n_elems > 0 ? n_elems : 1);
+}
+
 extern "C" int rs_isect_sorted(const rs_isect_sorted_args *b, rs_stream_t stream) {
     RS_CHECK(b != nullptr, "rs_isect_sorted: null args");
     const rs_isect_args *a = &b->isect;
@@ -700,7 +714,8 @@ extern "C" int rs_isect_sorted(const rs_isect_sorted_args *b, rs_stream_t stream
     if (a->n_elems > 0) {
         // 1. depth order of the visible elements: bucket sort on the depth bits (depth_order.cu), ties by flatten index
         if (int e = rs_depth_order(a->n_elems, a->depths, a->tiles_per_gauss, reinterpret_cast<int32_t *>(w + L.elems),
-                                   reinterpret_cast<int32_t *>(w + L.n_sorted), w + L.dord_ws, L.dord_ws_bytes, s))
+                                   reinterpret_cast<int32_t *>(w + L.n_sorted), w + L.dord_ws, L.dord_ws_bytes, s,
+                                   b->depth_stats_ready != 0))
             return e;
         // 2a. block sums of the tile counts in depth order
         rs_bin_count_kernel<<<nb, RS_ISECT_THREADS, 0, s>>>(a->n_elems, n_sorted, elems, a->tiles_per_gauss, block_sums);

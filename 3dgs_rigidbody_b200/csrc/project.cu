@@ -157,6 +157,26 @@ __device__ __forceinline__ void rs_pack_finish(const PackOut &po, unsigned int c
     }
 }
 
+// depth statistics of the rows with at least one tile (first step of the depth ordering, see depth_order.cu): warp
+// reduction, then one atomic triple per warp that saw such a row (fire-and-forget RED operations)
+__device__ __forceinline__ void rs_project_depth_stats(uint32_t *stats, bool counted, float depth) {
+    const unsigned int k = __float_as_uint(depth);
+    unsigned int inv_min = counted ? ~k : 0u, mx = counted ? k : 0u;
+    const unsigned int cnt = __popc(__ballot_sync(0xffffffffu, counted));
+    if (cnt == 0u)
+        return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        inv_min = max(inv_min, __shfl_xor_sync(0xffffffffu, inv_min, o));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(stats + 0, inv_min);
+        atomicMax(stats + 1, mx);
+        atomicAdd(stats + 2, cnt);
+    }
+}
+
 struct ProjSmem {
     float cam[2][16];
     int sums[8];
@@ -319,6 +339,12 @@ rs_project_fwd_kernel(const rs_project_fwd_args a, const PackOut po) {
                                     (uint32_t)a.tile_height);
             a.tiles_per_gauss[row] = cnt;
             my_tiles += cnt;
+            if (a.depth_stats != nullptr && cnt > 0) { // general path (not the frame path): per-row atomics
+                const unsigned int k = __float_as_uint(o.depth);
+                atomicMax(a.depth_stats + 0, ~k);
+                atomicMax(a.depth_stats + 1, k);
+                atomicAdd(a.depth_stats + 2, 1u);
+            }
         }
     }
     if (a.block_sums != nullptr) {
@@ -484,14 +510,18 @@ rs_project_fwd_staged_kernel(const rs_project_fwd_args a, const PackOut po) {
         po.camera_ids[row] = img - bid * C;
         po.gaussian_ids[row] = gid;
     }
+    int cnt = 0;
     if (in_range) {
         rs_store_projected(a, row, o, ok, opac);
         if (a.sh_coeffs != nullptr && ok)
             rs_project_sh_color(a, cam, mean, src0 + t, row);
-        if (a.tiles_per_gauss != nullptr)
-            a.tiles_per_gauss[row] = rs_tile_count(o.rx, o.ry, o.mx, o.my, (uint32_t)a.tile_size, (uint32_t)a.tile_width,
-                                                   (uint32_t)a.tile_height);
+        if (a.tiles_per_gauss != nullptr) {
+            cnt = rs_tile_count(o.rx, o.ry, o.mx, o.my, (uint32_t)a.tile_size, (uint32_t)a.tile_width, (uint32_t)a.tile_height);
+            a.tiles_per_gauss[row] = cnt;
+        }
     }
+    if (!PACKED && a.depth_stats != nullptr) // (every thread of the CTA reaches this point when not PACKED)
+        rs_project_depth_stats(a.depth_stats, cnt > 0, o.depth);
 }
 
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -513,6 +543,8 @@ static int rs_project_launch(const rs_project_fwd_args *a, PackOut *po, cudaStre
     if (a->tiles_per_gauss != nullptr)
         RS_CHECK(a->tile_size > 0 && a->tile_width > 0 && a->tile_height > 0,
                  "%s: tile geometry required for fused tile counting", who);
+    RS_CHECK(a->depth_stats == nullptr || (a->tiles_per_gauss != nullptr && po == nullptr),
+             "%s: depth_stats needs tiles_per_gauss and dense (not packed) rows", who);
     if (a->sh_coeffs != nullptr)
         RS_CHECK(a->sh_colors != nullptr && a->sh_degree >= 0 && a->sh_degree <= 4 &&
                      (a->sh_degree + 1) * (a->sh_degree + 1) <= a->sh_K,

@@ -9,8 +9,9 @@
 //   backward  a CTA takes 128 rows at a time: every thread recomputes its row's hidden activations, forms v_h = relu'(a) *
 //             W2^T v_y and v_x = W1^T v_h, and parks h / v_h / x / v_y of the chunk in shared memory (column-major with an odd
 //             pitch: conflict-free both ways); then the weight gradients v_W2 += v_y^T h, v_W1 += v_h^T x (two D x H tile
-//             products over the 128 rows) are accumulated in registers, 8 entries of each matrix per thread, across all chunks
-//             of a persistent CTA, and flushed with one atomicAdd per entry and CTA.
+//             products over the 128 rows) are accumulated in registers -- a 2 x 8 tile of v_W2 in each of 64 threads, a 4 x 4 tile
+//             of v_W1 in each of the other 64 -- across all chunks of a persistent CTA, and flushed with one atomicAdd per entry
+//             and CTA.
 // float32 throughout, FMA order fixed per row (deterministic forward; weight gradients differ only by the atomic flush order).
 #include "common.cuh"
 
@@ -18,8 +19,8 @@
 #define SEG_MAX_D 32
 #define SEG_MAX_H 128
 
-struct SegWeights { // shared-memory image of the four parameter tensors
-    float *w1, *b1, *w2, *b2;
+struct SegWeights { // shared-memory image of the four parameter tensors; w2 is held TRANSPOSED ([H][D]) so that the
+    float *w1, *b1, *w2, *b2; // weights of one hidden unit are one contiguous row in both matrices (float4 broadcasts)
 };
 __device__ __forceinline__ SegWeights seg_load_weights(const rs_seghead_args &a, float *smem) {
     SegWeights w;
@@ -30,7 +31,8 @@ __device__ __forceinline__ SegWeights seg_load_weights(const rs_seghead_args &a,
     w.b2 = w.w2 + D * H;
     for (int i = threadIdx.x; i < H * D; i += blockDim.x) {
         w.w1[i] = a.w1[i];
-        w.w2[i] = a.w2[i];
+        const int o = i / H, j = i - o * H; // a.w2 is [D][H]
+        w.w2[j * D + o] = a.w2[i];
     }
     for (int i = threadIdx.x; i < H; i += blockDim.x)
         w.b1[i] = a.b1[i];
@@ -58,13 +60,25 @@ __global__ void __launch_bounds__(SEG_THREADS) rs_seghead_fwd_kernel(const rs_se
 #pragma unroll 4
         for (int j = 0; j < H; ++j) {
             float h = w.b1[j];
+            const float4 *r1 = reinterpret_cast<const float4 *>(w.w1 + j * D);
+            const float4 *r2 = reinterpret_cast<const float4 *>(w.w2 + j * D);
 #pragma unroll
-            for (int i = 0; i < D; ++i)
-                h = fmaf(w.w1[j * D + i], x[i], h);
+            for (int i = 0; i < D; i += 4) {
+                const float4 q = r1[i >> 2];
+                h = fmaf(q.x, x[i], h);
+                h = fmaf(q.y, x[i + 1], h);
+                h = fmaf(q.z, x[i + 2], h);
+                h = fmaf(q.w, x[i + 3], h);
+            }
             h = fmaxf(h, 0.f);
 #pragma unroll
-            for (int o = 0; o < D; ++o)
-                y[o] = fmaf(w.w2[o * H + j], h, y[o]);
+            for (int o = 0; o < D; o += 4) {
+                const float4 q = r2[o >> 2];
+                y[o] = fmaf(q.x, h, y[o]);
+                y[o + 1] = fmaf(q.y, h, y[o + 1]);
+                y[o + 2] = fmaf(q.z, h, y[o + 2]);
+                y[o + 3] = fmaf(q.w, h, y[o + 3]);
+            }
         }
 #pragma unroll
         for (int o = 0; o < D; o += 4)
@@ -90,7 +104,7 @@ __global__ void __launch_bounds__(SEG_THREADS) rs_seghead_fwd_generic_kernel(con
                 h = fmaf(w.w1[j * D + i], x[i], h);
             h = fmaxf(h, 0.f);
             for (int o = 0; o < D; ++o)
-                y[o] = fmaf(w.w2[o * H + j], h, y[o]);
+                y[o] = fmaf(w.w2[j * D + o], h, y[o]);
         }
         for (int o = 0; o < D; ++o)
             a.y[n * D + o] = y[o];
@@ -111,13 +125,17 @@ __global__ void __launch_bounds__(SEG_THREADS) rs_seghead_bwd_kernel(const rs_se
     float *vys = xs + D * SEG_PITCH;                                      // [D][PITCH]
     __syncthreads();
     const int t = threadIdx.x;
-    // gradient entries owned by this thread: v_W2[o2][j2 .. j2+8) and v_W1[j1][i1 .. i1+8)
-    const int o2 = t >> 3, j2 = (t & 7) * 8;
-    const int j1 = t >> 1, i1 = (t & 1) * 8;
-    float g2[8], g1[8], gb2 = 0.f, gb1 = 0.f;
+    // gradient entries owned by this thread, a 2 x 8 (threads 0..63: v_W2[oa .. oa+2)[ja .. ja+8)) or 4 x 4 (threads 64..127:
+    // v_W1[ja .. ja+4)[oa .. oa+4)) register tile: 10 / 8 shared-memory loads per 16 FMAs and row of the chunk
+    const bool on_w2 = t < 64;
+    const int u = t & 63;
+    const int oa = on_w2 ? (u >> 3) * 2 : (u & 3) * 4; // v_W2: output row pair      | v_W1: input column quad
+    const int ja = on_w2 ? (u & 7) * 8 : (u >> 2) * 4; // v_W2: hidden column octet  | v_W1: hidden row quad
+    float g[16], gb[4];
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
-        g2[q] = g1[q] = 0.f;
+    for (int q = 0; q < 16; ++q)
+        g[q] = 0.f;
+    gb[0] = gb[1] = gb[2] = gb[3] = 0.f;
 
     const int64_t n_chunks = (a.N + SEG_CHUNK - 1) / SEG_CHUNK;
     for (int64_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
@@ -140,20 +158,29 @@ __global__ void __launch_bounds__(SEG_THREADS) rs_seghead_bwd_kernel(const rs_se
         }
 #pragma unroll 4
         for (int j = 0; j < H; ++j) {
-            float pre = w.b1[j];
+            float pre = w.b1[j], vh = 0.f;
+            float w1r[D];
+            const float4 *r1 = reinterpret_cast<const float4 *>(w.w1 + j * D);
+            const float4 *r2 = reinterpret_cast<const float4 *>(w.w2 + j * D);
+#pragma unroll
+            for (int i = 0; i < D; i += 4) {
+                const float4 q = r1[i >> 2];
+                w1r[i] = q.x, w1r[i + 1] = q.y, w1r[i + 2] = q.z, w1r[i + 3] = q.w;
+                const float4 u = r2[i >> 2];
+                vh = fmaf(u.x, vy[i], vh);
+                vh = fmaf(u.y, vy[i + 1], vh);
+                vh = fmaf(u.z, vy[i + 2], vh);
+                vh = fmaf(u.w, vy[i + 3], vh);
+            }
 #pragma unroll
             for (int i = 0; i < D; ++i)
-                pre = fmaf(w.w1[j * D + i], x[i], pre);
-            float vh = 0.f;
-#pragma unroll
-            for (int o = 0; o < D; ++o)
-                vh = fmaf(w.w2[o * H + j], vy[o], vh);
+                pre = fmaf(w1r[i], x[i], pre);
             vh = (pre > 0.f && live) ? vh : 0.f;
             hs[j * SEG_PITCH + t] = live ? fmaxf(pre, 0.f) : 0.f;
             vhs[j * SEG_PITCH + t] = vh;
 #pragma unroll
             for (int i = 0; i < D; ++i)
-                vx[i] = fmaf(w.w1[j * D + i], vh, vx[i]);
+                vx[i] = fmaf(w1r[i], vh, vx[i]);
         }
         if (live && a.v_x != nullptr) {
 #pragma unroll
@@ -162,31 +189,66 @@ __global__ void __launch_bounds__(SEG_THREADS) rs_seghead_bwd_kernel(const rs_se
         }
         __syncthreads();
         // weight-gradient tile products over the rows of the chunk
+        if (on_w2) {
+            const float *pa = vys + oa * SEG_PITCH, *pb = hs + ja * SEG_PITCH;
 #pragma unroll 4
-        for (int r = 0; r < SEG_CHUNK; ++r) {
-            const float vyo = vys[o2 * SEG_PITCH + r];
-            const float vhj = vhs[j1 * SEG_PITCH + r];
+            for (int r = 0; r < SEG_CHUNK; ++r) {
+                const float a0 = pa[r], a1 = pa[SEG_PITCH + r];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                g2[q] = fmaf(vyo, hs[(j2 + q) * SEG_PITCH + r], g2[q]);
-                g1[q] = fmaf(vhj, xs[(i1 + q) * SEG_PITCH + r], g1[q]);
+                for (int q = 0; q < 8; ++q) {
+                    const float hq = pb[q * SEG_PITCH + r];
+                    g[q] = fmaf(a0, hq, g[q]);
+                    g[8 + q] = fmaf(a1, hq, g[8 + q]);
+                }
+                if (ja == 0) { // one thread per output-row pair also sums the bias gradient
+                    gb[0] += a0;
+                    gb[1] += a1;
+                }
             }
-            if ((t & 7) == 0)
-                gb2 += vyo;
-            if ((t & 1) == 0)
-                gb1 += vhj;
+        } else {
+            const float *pa = vhs + ja * SEG_PITCH, *pb = xs + oa * SEG_PITCH;
+#pragma unroll 4
+            for (int r = 0; r < SEG_CHUNK; ++r) {
+                float av[4], bv[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    av[q] = pa[q * SEG_PITCH + r];
+                    bv[q] = pb[q * SEG_PITCH + r];
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int p = 0; p < 4; ++p)
+                        g[q * 4 + p] = fmaf(av[q], bv[p], g[q * 4 + p]);
+                if (oa == 0) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        gb[q] += av[q];
+                }
+            }
         }
         __syncthreads();
     }
+    if (on_w2) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        atomicAdd(a.v_w2 + o2 * H + j2 + q, g2[q]);
-        atomicAdd(a.v_w1 + j1 * D + i1 + q, g1[q]);
+        for (int q = 0; q < 8; ++q) {
+            atomicAdd(a.v_w2 + oa * H + ja + q, g[q]);
+            atomicAdd(a.v_w2 + (oa + 1) * H + ja + q, g[8 + q]);
+        }
+        if (ja == 0) {
+            atomicAdd(a.v_b2 + oa, gb[0]);
+            atomicAdd(a.v_b2 + oa + 1, gb[1]);
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int p = 0; p < 4; ++p)
+                atomicAdd(a.v_w1 + (ja + q) * D + oa + p, g[q * 4 + p]);
+            if (oa == 0)
+                atomicAdd(a.v_b1 + ja + q, gb[q]);
+        }
     }
-    if ((t & 7) == 0)
-        atomicAdd(a.v_b2 + o2, gb2);
-    if ((t & 1) == 0)
-        atomicAdd(a.v_b1 + j1, gb1);
 }
 
 static int seg_check(const rs_seghead_args *a, const char *who) {

@@ -64,52 +64,58 @@ __device__ __forceinline__ int block_excl_scan_256(int v, int *wsum, int *total)
 // ---------------------------------------------------------------------------------------------------------------------
 // histograms of all passes + look-back reset.  ws[WS_HIST..] and ws[WS_TICKET..] are zeroed by a memset before.
 // ---------------------------------------------------------------------------------------------------------------------
+// Four privatised copies of every pass histogram (copy = lane & 3): digits that are constant across a warp (the high bits of
+// tile ids in emission order, zero upper key bytes) then serialise 8 deep instead of 32 deep, without any per-key
+// shuffle / ballot to detect them -- 2 instructions per key and pass (shift-and-mask, ATOMS).
+#define SORT_HIST_COPIES 4
 template <typename KeyT>
 __global__ void __launch_bounds__(SORT_THREADS)
 sort_hist_kernel(const KeyT *__restrict__ keys, int64_t n_bound, const int32_t *__restrict__ n_dev, int begin_bit,
                  int end_bit, int passes, int nb_stride, uint32_t *__restrict__ ws) {
-    __shared__ unsigned int h[SORT_MAX_PASSES][RADIX];
+    __shared__ unsigned int h[SORT_MAX_PASSES][SORT_HIST_COPIES][RADIX];
     const int64_t n = sort_count(n_bound, n_dev);
-    for (int p = 0; p < passes; ++p)
-        h[p][threadIdx.x] = 0;
+    for (int i = threadIdx.x; i < passes * SORT_HIST_COPIES * RADIX; i += SORT_THREADS)
+        (&h[0][0][0])[i] = 0u;
     __syncthreads();
-    const int lane = threadIdx.x & 31;
+    const int copy = threadIdx.x & (SORT_HIST_COPIES - 1);
     const int width = sort_digit_width(end_bit - begin_bit);
-    constexpr int UNROLL = 4; // independent loads in flight per thread
-    for (int64_t base = (int64_t)blockIdx.x * (SORT_THREADS * UNROLL); base < n;
-         base += (int64_t)gridDim.x * (SORT_THREADS * UNROLL)) {
-        KeyT key[UNROLL];
-        bool valid[UNROLL];
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const int64_t idx = base + u * SORT_THREADS + threadIdx.x;
-            valid[u] = idx < n;
-            key[u] = valid[u] ? keys[idx] : (KeyT)0;
+    constexpr int VEC = 16 / sizeof(KeyT); // keys per 128-bit load
+    const int64_t n_vec = n / VEC;
+    const bool aligned = (reinterpret_cast<uintptr_t>(keys) & 15) == 0;
+    auto count_key = [&](KeyT key) {
+        for (int p = 0; p < passes; ++p) {
+            const int shift = begin_bit + p * width;
+            const int bits = min(width, end_bit - shift);
+            atomicAdd(&h[p][copy][(uint32_t)(key >> shift) & ((1u << bits) - 1u)], 1u);
         }
-#pragma unroll
-        for (int u = 0; u < UNROLL; ++u) {
-            const unsigned act = __ballot_sync(0xffffffffu, valid[u]);
-            for (int p = 0; p < passes; ++p) {
-                const int shift = begin_bit + p * width;
-                const int bits = min(width, end_bit - shift);
-                const uint32_t d = (uint32_t)(key[u] >> shift) & ((1u << bits) - 1u);
-                // nearly sorted inputs (tile ids in emission order) put a whole warp on one digit: one add for all
-                const uint32_t d0 = __shfl_sync(0xffffffffu, d, __ffs(act | 0x80000000u) - 1);
-                const unsigned same = __ballot_sync(0xffffffffu, valid[u] && d == d0);
-                if (same == act) {
-                    if (lane == 0 && act)
-                        atomicAdd(&h[p][d0], (unsigned)__popc(act));
-                } else if (valid[u]) {
-                    atomicAdd(&h[p][d], 1u);
-                }
+    };
+    if (aligned) {
+        for (int64_t v = (int64_t)blockIdx.x * SORT_THREADS + threadIdx.x; v < n_vec; v += (int64_t)gridDim.x * SORT_THREADS) {
+            const uint4 q = reinterpret_cast<const uint4 *>(keys)[v];
+            if constexpr (sizeof(KeyT) == 4) {
+                count_key((KeyT)q.x);
+                count_key((KeyT)q.y);
+                count_key((KeyT)q.z);
+                count_key((KeyT)q.w);
+            } else {
+                count_key((KeyT)(((unsigned long long)q.y << 32) | q.x));
+                count_key((KeyT)(((unsigned long long)q.w << 32) | q.z));
             }
         }
     }
+    // tail (or everything, for a misaligned key array)
+    for (int64_t i = (aligned ? n_vec * VEC : 0) + (int64_t)blockIdx.x * SORT_THREADS + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * SORT_THREADS)
+        count_key(keys[i]);
     __syncthreads();
-    for (int p = 0; p < passes; ++p) {
-        const unsigned v = h[p][threadIdx.x];
+    for (int i = threadIdx.x; i < passes * RADIX; i += SORT_THREADS) {
+        const int p = i / RADIX, d = i - p * RADIX;
+        unsigned int v = 0;
+#pragma unroll
+        for (int c = 0; c < SORT_HIST_COPIES; ++c)
+            v += h[p][c][d];
         if (v)
-            atomicAdd(&ws[WS_HIST + p * RADIX + threadIdx.x], v);
+            atomicAdd(&ws[WS_HIST + p * RADIX + d], v);
     }
     // reset the look-back words of the tiles this sort will use
     const int64_t words = (n + SORT_TILE - 1) / SORT_TILE * RADIX;
@@ -122,11 +128,14 @@ sort_hist_kernel(const KeyT *__restrict__ keys, int64_t n_bound, const int32_t *
 }
 
 template <typename KeyT> struct SortSmem {
-    KeyT keys[SORT_TILE];
-    int32_t vals[SORT_TILE];
+    // the re-ordered tile: 32-bit keys travel with their value as ONE 64-bit word (one STS.64 / LDS.64 per pair instead of
+    // two stores and two loads: the pass kernel is bound by the shared-memory / MIO instruction queue, not by bandwidth);
+    // 64-bit keys keep two arrays
+    KeyT keys[sizeof(KeyT) == 4 ? 1 : SORT_TILE];
+    int32_t vals[sizeof(KeyT) == 4 ? 1 : SORT_TILE];
+    uint2 kv[sizeof(KeyT) == 4 ? SORT_TILE : 1];
     int32_t vals_stage[SORT_TILE]; // the tile's values in input order, landed by cp.async while the keys are ranked
-    int wh[SORT_WARPS][RADIX]; // per-warp digit counters -> exclusive per-warp offsets
-    int bin_start[RADIX];      // first slot of each digit inside the re-ordered tile
+    int wh[SORT_WARPS][RADIX]; // per-warp digit counters -> first slot of (warp, digit) inside the re-ordered tile
     int delta[RADIX];          // global index of slot i of the re-ordered tile = delta[digit] + i
     int real[RADIX];           // digit counts of this tile without padding
     int gstart[RADIX];         // exclusive scan of the global digit histogram
@@ -240,6 +249,7 @@ sort_pass_kernel(const KeyT *__restrict__ keys_in, const int32_t *__restrict__ v
         __syncthreads();
 
         // thread t handles digit t: per-warp exclusive offsets, tile-level digit start, published aggregate
+        int bin_start = 0;
         {
             int sum = 0;
 #pragma unroll
@@ -256,8 +266,11 @@ sort_pass_kernel(const KeyT *__restrict__ keys_in, const int32_t *__restrict__ v
             st_volatile_u32(lookback + (size_t)tile * RADIX + threadIdx.x,
                             (tile == 0 ? LB_INCLUSIVE : LB_AGGREGATE) | (uint32_t)real);
             sm.real[threadIdx.x] = real;
-            const int start = block_excl_scan_256(sum, sm.wsum, nullptr); // (contains the barrier that publishes sm.real)
-            sm.bin_start[threadIdx.x] = start;
+            bin_start = block_excl_scan_256(sum, sm.wsum, nullptr); // (contains the barrier that publishes sm.real)
+            // first slot of every (warp, digit) group inside the re-ordered tile: one load per pair in the scatter below
+#pragma unroll
+            for (int w = 0; w < SORT_WARPS; ++w)
+                sm.wh[w][threadIdx.x] += bin_start;
         }
         // Decoupled look-back, one digit per thread.  Windowed: LB_WINDOW independent loads per L2 round trip -- when all
         // tiles of a wave start together, the inclusive prefix can only advance one window per round trip, and that chain
@@ -320,7 +333,7 @@ sort_pass_kernel(const KeyT *__restrict__ keys_in, const int32_t *__restrict__ v
                 st_volatile_u32(lookback + (size_t)tile * RADIX + d, LB_INCLUSIVE | (uint32_t)(excl + sm.real[d]));
             }
             // global index of slot i of the re-ordered tile = delta[digit] + i
-            sm.delta[d] = sm.gstart[d] + excl - sm.bin_start[d];
+            sm.delta[d] = sm.gstart[d] + excl - bin_start;
         }
         asm volatile("cp.async.wait_group 0;\n" ::: "memory"); // this thread's value copies have landed ...
         __syncthreads();                                       // ... and so have everyone else's
@@ -328,20 +341,34 @@ sort_pass_kernel(const KeyT *__restrict__ keys_in, const int32_t *__restrict__ v
 #pragma unroll
         for (int k = 0; k < SORT_ITEMS; ++k) {
             const uint32_t d = (uint32_t)(key[k] >> shift) & mask;
-            const int pos = sm.bin_start[d] + sm.wh[warp][d] + rank[k];
+            const int pos = sm.wh[warp][d] + rank[k];
             const int local = wbase + k * 32 + lane;
-            sm.keys[pos] = key[k];
-            if (local < count)
-                sm.vals[pos] = vals_in != nullptr ? sm.vals_stage[local] : (int32_t)(tile_start + local);
+            const int32_t v = vals_in != nullptr ? sm.vals_stage[min(local, SORT_TILE - 1)] : (int32_t)(tile_start + local);
+            if constexpr (sizeof(KeyT) == 4) {
+                sm.kv[pos] = make_uint2((uint32_t)key[k], (uint32_t)v); // padding keys land behind slot `count`: never read
+            } else {
+                sm.keys[pos] = key[k];
+                if (local < count)
+                    sm.vals[pos] = v;
+            }
         }
         __syncthreads();
 
         for (int i = threadIdx.x; i < count; i += SORT_THREADS) {
-            const KeyT kk = sm.keys[i];
+            KeyT kk;
+            int32_t vv;
+            if constexpr (sizeof(KeyT) == 4) {
+                const uint2 p = sm.kv[i];
+                kk = (KeyT)p.x;
+                vv = (int32_t)p.y;
+            } else {
+                kk = sm.keys[i];
+                vv = sm.vals[i];
+            }
             const uint32_t d = (uint32_t)(kk >> shift) & mask;
             const int64_t out = (int64_t)(sm.delta[d] + i);
             keys_out[out] = kk;
-            vals_out[out] = sm.vals[i];
+            vals_out[out] = vv;
         }
     }
 }
@@ -385,7 +412,7 @@ static int radix_sort_impl(int64_t n_bound, const int32_t *n_dev, int begin_bit,
     const int sms = rs_num_sms();
     if (!hist_ready) { // else: the producer of the keys already filled ws (rs_sort_ws_prepare + its own histogramming)
         RS_CUDA(cudaMemsetAsync(ws, 0, (size_t)WS_LOOKBACK * sizeof(uint32_t), s));
-        const int hist_grid = (int)min((int64_t)sms * 2, (n_bound + SORT_THREADS * 4 - 1) / (SORT_THREADS * 4));
+        const int hist_grid = (int)min((int64_t)sms * 6, (n_bound + SORT_THREADS * 4 - 1) / (SORT_THREADS * 4));
         sort_hist_kernel<KeyT><<<hist_grid, SORT_THREADS, 0, s>>>(keys_in, n_bound, n_dev, begin_bit, end_bit, passes, nb,
                                                                   ws);
         RS_LAUNCH_CHECK("sort_hist_kernel");

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RS_ABI_VERSION 13
+#define RS_ABI_VERSION 14
 
 /* gsplat/cuda/include/Common.h:46-51 (CameraModelType) */
 enum { RS_PINHOLE = 0, RS_ORTHO = 1, RS_FISHEYE = 2, RS_FTHETA = 3 };
@@ -108,6 +108,11 @@ typedef struct {
     const float *sh_coeffs;     /* [B,N,sh_K,3] optional */
     float *sh_colors;           /* [B,C,N,3] out, required with sh_coeffs */
     int32_t sh_degree, sh_K;
+    /* optional (needs tiles_per_gauss): statistics of the depth bits of the rows with at least one tile, accumulated with
+     * atomics into depth_stats[0] = max(~bits), [1] = max(bits), [2] = number of such rows ([3] unused); must be zeroed by the
+     * caller.  They are the first step of the depth ordering of rs_isect_sorted (depth_stats_ready), which rs_render_frame
+     * fuses this way. */
+    uint32_t *depth_stats;
 } rs_project_fwd_args;
 int rs_project_fwd(const rs_project_fwd_args *a, rs_stream_t stream);
 
@@ -297,7 +302,15 @@ typedef struct {
     int32_t *tile_offsets;       /* [I,tile_height,tile_width] out, optional */
     void *workspace;             /* rs_isect_sorted_workspace_bytes(n_elems, capacity) bytes */
     uint64_t workspace_bytes;
+    /* != 0: the depth statistics of the visible rows were already accumulated into rs_isect_sorted_depth_stats(workspace)
+     * by the producer of the rows (rs_project_fwd_args.depth_stats) after rs_isect_sorted_prepare(); 0: computed here */
+    int32_t depth_stats_ready;
+    int32_t _pad;
 } rs_isect_sorted_args;
+/* for a caller that fuses the depth statistics into its projection: clear the ordering state of `workspace` (enqueued on
+ * `stream`, BEFORE the kernel that accumulates the statistics) / where that kernel has to accumulate them */
+int rs_isect_sorted_prepare(void *workspace, int64_t n_elems, int64_t capacity, rs_stream_t stream);
+uint32_t *rs_isect_sorted_depth_stats(void *workspace, int64_t n_elems, int64_t capacity);
 uint64_t rs_isect_sorted_workspace_bytes(int64_t n_elems, int64_t capacity);
 int rs_isect_sorted(const rs_isect_sorted_args *a, rs_stream_t stream);
 
