@@ -133,8 +133,8 @@ template <typename KeyT> struct SortSmem {
     // 64-bit keys keep two arrays
     KeyT keys[sizeof(KeyT) == 4 ? 1 : SORT_TILE];
     int32_t vals[sizeof(KeyT) == 4 ? 1 : SORT_TILE];
-    uint2 kv[sizeof(KeyT) == 4 ? SORT_TILE : 1];
-    int32_t vals_stage[SORT_TILE]; // the tile's values in input order, landed by cp.async while the keys are ranked
+    alignas(16) uint2 kv[sizeof(KeyT) == 4 ? SORT_TILE : 1];
+    alignas(16) int32_t vals_stage[SORT_TILE]; // the tile's values in input order, landed by 16-byte cp.async while the keys are ranked
     int wh[SORT_WARPS][RADIX]; // per-warp digit counters -> first slot of (warp, digit) inside the re-ordered tile
     int delta[RADIX];          // global index of slot i of the re-ordered tile = delta[digit] + i
     int real[RADIX];           // digit counts of this tile without padding
