@@ -568,6 +568,8 @@ def rasterize_to_pixels_3dgs_fwd(
         # staging records (32 B per projected splat), packed by rs_raster_fwd itself on this path
         records = torch.empty((max(a.n_rows, 1), 8), dtype=torch.float32, device=dev)
         a.records, a.records_ready = records.data_ptr(), 0
+        counter = torch.zeros(1, dtype=torch.int32, device=dev)  # work counter of the persistent compositing kernel
+        a.tile_counter = counter.data_ptr()
         _lib.check(lib.rs_raster_fwd(ctypes.byref(a), _stream()))
     return renders, alphas, last_ids
 

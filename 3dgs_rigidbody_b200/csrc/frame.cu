@@ -13,7 +13,7 @@ int rs_isect_ids_from_offsets(const int32_t *offsets, const int32_t *flatten_ids
 namespace {
 struct FrameLayout {
     size_t radii, means2d, depths, conics, records, sh_colors, tiles_per_gauss, block_sums, isect_ids, flatten_ids, bin_ws, bin_ws_bytes,
-        tile_offsets, last_ids, total;
+        tile_offsets, last_ids, tile_counter, total;
 };
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -41,6 +41,7 @@ FrameLayout make_layout(int32_t C, int32_t N, int32_t W, int32_t H, int32_t tile
     L.bin_ws = take(L.bin_ws_bytes);
     L.tile_offsets = take((size_t)C * tw * th * 4);
     L.last_ids = take((size_t)C * W * H * 4);
+    L.tile_counter = take(256); // work counter of the persistent compositing kernel (zeroed per frame)
     L.total = o;
     return L;
 }
@@ -232,6 +233,9 @@ static int render_frame_impl(const rs_frame_args *a, rs_stream_t stream, cudaEve
     r.records = p.records;
     r.records_ready = 1;
     r.n_rows = (int64_t)p.C * p.N;
+    r.tile_counter = reinterpret_cast<uint32_t *>(w + L.tile_counter);
+    if (do_composite)
+        RS_CUDA(cudaMemsetAsync(w + L.tile_counter, 0, 4, s));
     if (do_composite)
         if (int e = rs_raster_fwd(&r, stream))
             return e;

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RS_ABI_VERSION 14
+#define RS_ABI_VERSION 15
 
 /* gsplat/cuda/include/Common.h:46-51 (CameraModelType) */
 enum { RS_PINHOLE = 0, RS_ORTHO = 1, RS_FISHEYE = 2, RS_FTHETA = 3 };
@@ -375,6 +375,9 @@ typedef struct {
      * a frame (main.py:140-171 save_rendered_image -> torchvision save_image: x * 255 + 0.5, clamp to [0, 255], truncate);
      * needs channels >= 3.  Written by the compositing epilogue next to the float image. */
     uint8_t *render_rgb8;
+    /* optional device uint32, ZERO when the call is enqueued (and not shared with another launch in flight): work counter of
+     * the persistent compositing kernel (tiles are then handed out dynamically instead of in a fixed stride).  NULL is fine. */
+    uint32_t *tile_counter;
 } rs_raster_fwd_args;
 int rs_raster_fwd(const rs_raster_fwd_args *a, rs_stream_t stream);
 
