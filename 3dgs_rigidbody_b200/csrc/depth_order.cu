@@ -7,8 +7,8 @@
 //
 // Here the order is produced by a bucket sort whose steps have no serial chain at all:
 //   K0  min / max of the depth bits of the visible elements, and their number V                     (E reads)
-//   K1  bucket histogram: bucket = (bits - min) >> shift, 8192 (E <= 2 M) or 65536 buckets over the ACTUAL range of this
-//       frame (so the resolution adapts to the scene: ~100 elements per bucket)                        (E reads, V atomics)
+//   K1  bucket histogram: bucket = (bits - min) >> shift, 2^16 .. 2^20 buckets (~32 elements per bucket beyond 2 M elements)
+//       over the ACTUAL depth range of this frame, so the resolution adapts to the scene              (E reads, V atomics)
 //   K2  exclusive scan of the bucket counts by one CTA; buckets are grouped into sort groups of ~DORD_TARGET elements
 //       (group g starts at the first bucket boundary at or after g * DORD_TARGET)
 //   K3  scatter: every visible element takes the next free slot of its bucket (atomic cursor) and stores the 64-bit
@@ -22,11 +22,18 @@
 // Output: elems[0 .. V) and V (device side).  Everything is sized by the SM count / the element bound; no host sync.
 #include "common.cuh"
 
-// 65536 buckets: with 8192 the atomics of K1 / K3 pile up on too few L2 addresses (count 14 -> 37 us, scatter 19 -> 40 us at
-// 1 M elements, profiles/r02_depth_order_experiments.txt), and the scan below no longer cares about the bucket count
-#define DORD_BUCKET_BITS_MAX 16
+// Bucket count: 65536 up to 2 M elements, then ~32 elements per bucket up to 2^20 buckets.  Too few buckets and the atomics
+// of K1 / K3 pile up on too few L2 addresses (8192 buckets at 1 M elements: count 14 -> 37 us, scatter 19 -> 40 us,
+// profiles/r02_depth_order_experiments.txt); the look-back scan does not care about the bucket count.
+#define DORD_BUCKET_BITS_MIN 16
+#define DORD_BUCKET_BITS_MAX 20
 #define DORD_BUCKETS_MAX (1 << DORD_BUCKET_BITS_MAX)
-static inline int dord_bucket_bits(int64_t) { return DORD_BUCKET_BITS_MAX; }
+static inline int dord_bucket_bits(int64_t n_elems) {
+    int bits = DORD_BUCKET_BITS_MIN;
+    while (bits < DORD_BUCKET_BITS_MAX && ((int64_t)32 << bits) < n_elems)
+        ++bits;
+    return bits;
+}
 #define DORD_TARGET 896   // elements per sort group (plus the tail of the bucket that crosses the boundary)
 #define DORD_CAP 4096     // composites a CTA sorts in shared memory
 #define DORD_THREADS 256
@@ -500,7 +507,7 @@ uint32_t *rs_depth_order_stats_ptr(void *workspace, int64_t n_elems) {
 
 int rs_depth_order(int64_t n_elems, const float *depths, const int32_t *tiles, int32_t *elems_out, int32_t *n_sorted_dev,
                    void *workspace, uint64_t workspace_bytes, cudaStream_t s, bool stats_ready) {
-    RS_CHECK(n_elems >= 0 && n_elems < ((int64_t)1 << 31), "rs_depth_order: bad element count");
+    RS_CHECK(n_elems >= 0 && n_elems < ((int64_t)1 << 30), "rs_depth_order: bad element count (limit 2^30)");
     RS_CHECK(n_sorted_dev != nullptr, "rs_depth_order: n_sorted_dev is required");
     if (n_elems == 0) {
         RS_CUDA(cudaMemsetAsync(n_sorted_dev, 0, sizeof(int32_t), s));

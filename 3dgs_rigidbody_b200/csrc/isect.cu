@@ -680,7 +680,7 @@ extern "C" int rs_isect_sorted(const rs_isect_sorted_args *b, rs_stream_t stream
     const rs_isect_args *a = &b->isect;
     if (int e = check_isect_args(a, "rs_isect_sorted"))
         return e;
-    RS_CHECK(a->n_elems < ((int64_t)1 << 31), "rs_isect_sorted: too many elements");
+    RS_CHECK(a->n_elems < ((int64_t)1 << 30), "rs_isect_sorted: too many elements (limit 2^30)");
     RS_CHECK(a->capacity >= 0 && a->capacity < ((int64_t)1 << 31), "rs_isect_sorted: bad capacity");
     RS_CHECK(a->n_isects != nullptr, "rs_isect_sorted: n_isects (device) required");
     RS_CHECK(a->n_elems == 0 || (a->means2d && a->radii && a->depths && a->tiles_per_gauss),

@@ -40,16 +40,27 @@ def _world() -> Tuple[int, int]:
 class GaussianShardExchange:
     """Bookkeeping + collectives of one distributed `rasterization()` call."""
 
+    _layout_cache: Dict = {}
+
     def __init__(self, n_local: int, c_local: int, device: torch.device, group=None):
         self.group = group
         self.rank, self.world = _world()
         self.device = device
-        mine = torch.tensor([n_local, c_local], dtype=torch.int64, device=device)
-        table = torch.empty(self.world * 2, dtype=torch.int64, device=device)
-        dist.all_gather_into_tensor(table, mine, group=group)
-        table = table.reshape(self.world, 2).cpu()
-        self.n_per_rank: List[int] = table[:, 0].tolist()
-        self.c_per_rank: List[int] = table[:, 1].tolist()
+        # (Gaussians, cameras) of every rank.  Render / animation loops (no gradients) call this every frame with a static
+        # scene: the table is then gathered once per (group, local sizes) instead of costing a collective and a host sync per
+        # frame; with gradients enabled (training: densification changes the shard sizes) it is gathered on every call.
+        key = (id(group) if group is not None else None, str(device), int(n_local), int(c_local))
+        cached = None if torch.is_grad_enabled() else GaussianShardExchange._layout_cache.get(key)
+        if cached is None:
+            mine = torch.tensor([n_local, c_local], dtype=torch.int64, device=device)
+            table = torch.empty(self.world * 2, dtype=torch.int64, device=device)
+            dist.all_gather_into_tensor(table, mine, group=group)
+            table = table.reshape(self.world, 2).cpu()
+            cached = (table[:, 0].tolist(), table[:, 1].tolist())
+            if not torch.is_grad_enabled():
+                GaussianShardExchange._layout_cache[key] = cached
+        self.n_per_rank: List[int] = list(cached[0])
+        self.c_per_rank: List[int] = list(cached[1])
         # the reference requires the same number of cameras on every rank (rendering.py:374-375)
         assert len(set(self.c_per_rank)) == 1, f"every rank must own the same number of cameras, got {self.c_per_rank}"
         self.local_cameras = c_local
@@ -324,7 +335,10 @@ class PeerSplatExchange:
                 self.grad_buffers.release(self.group)
             self.grad_buffers = _PeerBuffers(self.lib, self.group, self.device, int(grad_capacity * 1.25) + 1024, self.channels)
         self.grad_epoch += 1
-        keep = [g.contiguous() for g in grads]
+        # a rank whose cameras saw nothing received no rows: its gradient tensors are empty (NULL data pointers); the kernel
+        # then has no block to copy, but the library insists on valid pointers
+        keep = [g.contiguous() if g.numel() > 0 else torch.zeros((1,) + tuple(g.shape[1:]), dtype=g.dtype, device=g.device)
+                for g in grads]
         a = _lib.rs_exchange_grad_args()
         a.world, a.rank, a.channels, a.timeout_ms = self.world, self.rank, self.channels, int(self.timeout_ms)
         a.capacity, a.epoch = self.grad_buffers.capacity, self.grad_epoch
