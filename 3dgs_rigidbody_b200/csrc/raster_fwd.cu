@@ -64,8 +64,11 @@ template <int CDIM> struct RastCfg {
 // for each other, only for data, so a warp whose sub-block is touched by few splats runs ahead by up to STAGES-1 batches
 // instead of idling at a block barrier after every batch (34 % of all stall samples in the barrier version,
 // profiles/r01c).  When every pixel of the tile is saturated the producer stops gathering (early termination).
+#ifndef RS_RASTER_MIN_CTAS
+#define RS_RASTER_MIN_CTAS 1 // resident CTAs per SM the compiler must leave registers for (experiments: 6, 7)
+#endif
 template <int CDIM, bool VEC_COLORS>
-__global__ void __launch_bounds__(RAST_THREADS)
+__global__ void __launch_bounds__(RAST_THREADS, (CDIM <= 4) ? RS_RASTER_MIN_CTAS : 1)
 rs_raster_fwd_kernel(const rs_raster_fwd_args a, const int ch_off, const int ch_cnt) {
     using Cfg = RastCfg<CDIM>;
     constexpr int CP = Cfg::CP;

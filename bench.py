@@ -962,7 +962,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--max-isects", type=int, default=24_000_000)
-    ap.add_argument("--in-flight", type=int, default=4, help="frames in flight per GPU (streams + workspaces)")
+    ap.add_argument("--in-flight", type=int, default=6, help="frames in flight per GPU (streams + workspaces)")
     ap.add_argument("--no-split", action="store_true",
                     help="one stream per in-flight frame instead of (high-priority binning stream, compositing stream)")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
