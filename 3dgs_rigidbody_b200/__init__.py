@@ -34,6 +34,14 @@ from .rigid import (  # noqa: F401
     make_rigid,
 )
 from .sh import spherical_harmonics  # noqa: F401
+
+
+def __getattr__(name):  # torch.distributed-dependent classes are imported on first use
+    if name in ("ShardedFrameRenderer", "PeerSplatExchange", "GaussianShardExchange"):
+        from . import distributed as _d
+
+        return getattr(_d, name)
+    raise AttributeError(name)
 from .wrapper import (  # noqa: F401
     fully_fused_projection,
     isect_offset_encode,

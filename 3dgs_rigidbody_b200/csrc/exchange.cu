@@ -398,6 +398,18 @@ __global__ void rs_exchange_wait_grad_kernel(const rs_exchange_grad_args a, long
     }
 }
 
+// Rows [received, capacity) of this rank's receive arrays still hold an earlier frame.  rs_exchange_seal zeroes their radii,
+// which makes them invisible to everything downstream (zero tiles), so that a caller can run tile binning and compositing over
+// the whole CAPACITY with device-side counts only -- no host read of the row count between the exchange and the render.
+__global__ void __launch_bounds__(256)
+rs_exchange_seal_kernel(const rs_exchange_args a, const ExchangeLayout lay, const long long *totals) {
+    char *const *peers = (char *const *)a.peer_base;
+    int2 *radii = reinterpret_cast<int2 *>(peers[a.rank] + lay.off[5]);
+    const long long got = totals[2] == 0 ? min(totals[0], (long long)a.capacity) : 0; // failed epoch: nothing is valid
+    for (long long i = got + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.capacity; i += (long long)gridDim.x * blockDim.x)
+        radii[i] = make_int2(0, 0);
+}
+
 static int exchange_check(const rs_exchange_args *a, const char *who) {
     RS_CHECK(a != nullptr, "%s: null args", who);
     RS_CHECK(a->world >= 1 && a->world <= RS_EXCHANGE_MAX_WORLD && a->rank >= 0 && a->rank < a->world,
@@ -478,5 +490,23 @@ extern "C" int rs_exchange_wait_grad(const rs_exchange_grad_args *a, int64_t *st
     RS_CHECK(status_dev != nullptr, "rs_exchange_wait_grad: status_dev is required");
     rs_exchange_wait_grad_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(*a, (long long *)status_dev);
     RS_LAUNCH_CHECK("rs_exchange_wait_grad_kernel");
+    return 0;
+}
+
+extern "C" int rs_exchange_seal(const rs_exchange_args *a, const int64_t *totals_dev, rs_stream_t stream) {
+    if (int rc = exchange_check(a, "rs_exchange_seal"))
+        return rc;
+    RS_CHECK(totals_dev != nullptr, "rs_exchange_seal: totals_dev (from rs_exchange_wait) is required");
+    if (a->capacity == 0)
+        return 0;
+    ExchangeLayout lay;
+    uint64_t off[RS_EXCHANGE_COLUMNS + 1];
+    if (int rc = rs_exchange_layout(a->capacity, a->channels, off))
+        return rc;
+    for (int i = 0; i < RS_EXCHANGE_COLUMNS; ++i)
+        lay.off[i] = off[i];
+    const int grid = (int)min((int64_t)rs_num_sms() * 4, (a->capacity + 255) / 256);
+    rs_exchange_seal_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*a, lay, (const long long *)totals_dev);
+    RS_LAUNCH_CHECK("rs_exchange_seal_kernel");
     return 0;
 }

@@ -388,3 +388,208 @@ class _PeerExchangeFn(torch.autograd.Function):
         grads = (dense(v_m2, (2,)), dense(v_d, ()), dense(v_con, (3,)), dense(v_op, ()), dense(v_col, (peer.channels,)))
         g_m2, g_d, g_con, g_op, g_col = peer._push_grads(ctx.counts, ctx.grad_capacity, ctx.nnz_local, grads)
         return (None,) * 7 + (g_m2, g_d, g_con, g_op, g_col)
+
+
+class ShardedFrameRenderer:
+    """One Gaussian-sharded frame (BASELINE config c5) with NO host synchronisation on the way: the distributed counterpart
+    of animation.FrameRenderer.
+
+    Same data flow as rasterization(distributed=True, packed=True) -- gsplat/rendering.py:366-381, 527-611: cameras are
+    all-gathered, every rank projects ITS Gaussians to ALL cameras, the projected splats travel to the rank owning the camera,
+    binning and compositing are local -- but every size stays on the device: the packed projection writes into capacity-sized
+    row buffers (device-side nnz / indptr), the peer-memory exchange places rows from the device-side count matrix,
+    rs_exchange_seal blanks the unused tail of the receive arrays, and tile binning / compositing run over the whole row
+    capacity with the device-side intersection count (as rs_render_frame does on one GPU).  The reference reads back sizes
+    three times per frame (projection nnz, all-to-all counts, intersection count); here the host reads NOTHING unless
+    `check()` is called (one read of six integers: rows received, capacity needed, exchange error, intersections, overflow),
+    so the ranks do not drift apart between frames.  Per-Gaussian colours [N, D] (sh_degree=None), no gradients.
+    All ranks of the group must call render() the same number of times (it contains the exchange)."""
+
+    def __init__(self, means: Tensor, quats: Tensor, scales: Tensor, opacities: Tensor, colors: Tensor, width: int,
+                 height: int, cameras_per_rank: int, group=None, max_isects: Optional[int] = None,
+                 row_capacity: Optional[int] = None, cluster_ids: Optional[Tensor] = None,
+                 body_centers: Optional[Tensor] = None, near_plane: float = 0.01, far_plane: float = 1e10,
+                 radius_clip: float = 0.0, eps2d: float = 0.3):
+        self.lib = _lib.load()
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        dev = means.device
+        self.device = dev
+        self.means, self.quats, self.scales, self.opacities, self.colors = (t.contiguous() for t in (means, quats, scales,
+                                                                                                     opacities, colors))
+        self.cluster_ids, self.body_centers = cluster_ids, body_centers
+        self.N, self.D = int(means.shape[0]), int(colors.shape[-1])
+        self.W, self.H, self.Cl = int(width), int(height), int(cameras_per_rank)
+        self.Ct = self.Cl * self.world
+        self.tile_w, self.tile_h = (self.W + 15) // 16, (self.H + 15) // 16
+        self.near_plane, self.far_plane, self.radius_clip, self.eps2d = near_plane, far_plane, radius_clip, eps2d
+        sizes = torch.empty(self.world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(sizes, torch.tensor([self.N], dtype=torch.int64, device=dev), group=group)
+        self.gaussian_base = int(sizes[: self.rank].sum().item())
+        self.peer = PeerSplatExchange.get(group, dev, self.D)
+        # packed projection: every (camera, Gaussian) pair fits, so the projection can never overflow
+        cap_p = max(self.N * self.Ct, 1)
+        self.cap_p = cap_p
+        with torch.cuda.device(dev):
+            self.p_ids = torch.empty((3, cap_p), dtype=torch.int64, device=dev)
+            self.p_radii = torch.empty((cap_p, 2), dtype=torch.int32, device=dev)
+            self.p_means2d = torch.empty((cap_p, 2), dtype=torch.float32, device=dev)
+            self.p_depths = torch.empty((cap_p,), dtype=torch.float32, device=dev)
+            self.p_conics = torch.empty((cap_p, 3), dtype=torch.float32, device=dev)
+            self.p_indptr = torch.zeros(self.Ct + 1, dtype=torch.int32, device=dev)
+            self.p_nnz = torch.zeros(1, dtype=torch.int64, device=dev)
+            self.p_ws = torch.empty(max(int(self.lib.rs_project_packed_workspace_bytes(1, self.Ct, self.N)), 16),
+                                    dtype=torch.uint8, device=dev)
+            self.cams = torch.empty(self.Ct, 25, dtype=torch.float32, device=dev)
+            self.totals = torch.zeros(4, dtype=torch.int64, device=dev)
+            self.status = torch.zeros(4, dtype=torch.int32, device=dev)
+            self.render_colors = torch.empty(self.Cl, self.H, self.W, self.D, dtype=torch.float32, device=dev)
+            self.render_alphas = torch.empty(self.Cl, self.H, self.W, 1, dtype=torch.float32, device=dev)
+            self.last_ids = torch.empty(self.Cl, self.H, self.W, dtype=torch.int32, device=dev)
+            self.offsets = torch.empty(self.Cl, self.tile_h, self.tile_w, dtype=torch.int32, device=dev)
+        self.row_capacity = row_capacity
+        self.max_isects = max_isects
+        self._alloc_rows = 0
+
+    # ---- sizing -------------------------------------------------------------------------------------------------------------
+    def _alloc_render(self, rows: int, max_isects: int) -> None:
+        dev = self.device
+        self._alloc_rows, self.max_isects = rows, max_isects
+        with torch.cuda.device(dev):
+            self.tiles_per_gauss = torch.empty(rows, dtype=torch.int32, device=dev)
+            self.block_sums = torch.empty(self.lib.rs_isect_num_blocks(rows) + 2, dtype=torch.int32, device=dev)
+            self.records = torch.empty((rows, 8), dtype=torch.float32, device=dev)
+            self.flatten_ids = torch.empty(max_isects, dtype=torch.int32, device=dev)
+            nbytes = int(self.lib.rs_isect_sorted_workspace_bytes(rows, max_isects))
+            self.bin_ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self.tile_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+
+    def _size_once(self, viewmats: Tensor, Ks: Tensor, rigid) -> None:
+        """First frame only: one ordinary (synchronising) sharded render tells how many rows and intersections this scene
+        produces; the persistent arrays get 25 % head room on top of the largest rank's numbers."""
+        from .rendering import rasterization
+
+        kw = {}
+        if rigid is not None:
+            kw = dict(cluster_ids=self.cluster_ids, body_quats=rigid[0], body_trans=rigid[1], body_centers=self.body_centers)
+        with torch.no_grad():
+            _, _, meta = rasterization(self.means, self.quats, self.scales, self.opacities, self.colors, viewmats, Ks, self.W,
+                                       self.H, packed=True, distributed=True, near_plane=self.near_plane,
+                                       far_plane=self.far_plane, radius_clip=self.radius_clip, eps2d=self.eps2d, **kw)
+        need = torch.tensor([meta["gaussian_ids"].numel(), meta["flatten_ids"].numel()], dtype=torch.int64, device=self.device)
+        dist.all_reduce(need, op=dist.ReduceOp.MAX, group=self.group)
+        rows, isects = (int(v) for v in need.tolist())
+        rows = max(int(rows * 1.25) + 4096, int(self.row_capacity or 0))
+        isects = max(int(isects * 1.25) + 65536, int(self.max_isects or 0))
+        if self.peer.buffers is None or self.peer.buffers.capacity < rows:
+            self.peer._regrow(rows)
+        self._alloc_render(self.peer.buffers.capacity, isects)
+
+    # ---- one frame ----------------------------------------------------------------------------------------------------------
+    def render(self, viewmats: Tensor, Ks: Tensor, body_quats: Optional[Tensor] = None, body_trans: Optional[Tensor] = None):
+        """Enqueue one frame on the current stream; returns views of the renderer-owned (render_colors [Cl,H,W,D],
+        render_alphas [Cl,H,W,1]).  Nothing is read back; call check() when the sizes must be verified."""
+        lib, dev = self.lib, self.device
+        rigid = None
+        if self.cluster_ids is not None:
+            if body_quats is None or body_trans is None:
+                raise RuntimeError("ShardedFrameRenderer.render: body_quats and body_trans are required with cluster_ids")
+            rigid = (body_quats.contiguous(), body_trans.contiguous())
+        if self._alloc_rows == 0 or self.peer.buffers is None or self.peer.buffers.capacity != self._alloc_rows:
+            self._size_once(viewmats, Ks, rigid)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            # 1. cameras of every rank (the one NCCL call of the frame: 25 floats per camera, no host involvement)
+            local = torch.cat([viewmats.reshape(self.Cl, 16), Ks.reshape(self.Cl, 9)], dim=1).contiguous()
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.cams, local, group=self.group)
+            else:
+                self.cams.copy_(local)
+            vm_all = self.cams[:, :16].contiguous()
+            Ks_all = self.cams[:, 16:].contiguous()
+            # 2. packed projection of MY Gaussians to ALL cameras (device-side nnz / indptr)
+            pa = _lib.rs_project_packed_fwd_args()
+            a = pa.proj
+            a.B, a.C, a.N = 1, self.Ct, self.N
+            a.image_width, a.image_height, a.camera_model = self.W, self.H, 0
+            a.eps2d, a.near_plane, a.far_plane, a.radius_clip = self.eps2d, self.near_plane, self.far_plane, self.radius_clip
+            a.means, a.quats, a.scales = self.means.data_ptr(), self.quats.data_ptr(), self.scales.data_ptr()
+            a.opacities, a.viewmats, a.Ks = self.opacities.data_ptr(), vm_all.data_ptr(), Ks_all.data_ptr()
+            if rigid is not None:
+                from ._C import RigidPoses
+
+                RigidPoses(self.cluster_ids, rigid[0], rigid[1], self.body_centers).fill(a.rigid)
+            a.radii, a.means2d = self.p_radii.data_ptr(), self.p_means2d.data_ptr()
+            a.depths, a.conics = self.p_depths.data_ptr(), self.p_conics.data_ptr()
+            pa.capacity = self.cap_p
+            pa.indptr = self.p_indptr.data_ptr()
+            pa.batch_ids, pa.camera_ids, pa.gaussian_ids = (self.p_ids[i].data_ptr() for i in range(3))
+            pa.nnz, pa.workspace = self.p_nnz.data_ptr(), self.p_ws.data_ptr()
+            _lib.check(lib.rs_project_packed_fwd(ctypes.byref(pa), stream))
+            # 3. exchange over peer memory: push, wait, blank the unused tail of the receive arrays
+            peer, buf = self.peer, self.peer.buffers
+            peer.epoch += 1
+            x = _lib.rs_exchange_args()
+            x.world, x.rank, x.cameras_per_rank, x.channels = self.world, self.rank, self.Cl, self.D
+            x.capacity, x.epoch = buf.capacity, peer.epoch
+            x.colors_per_row, x.opacities_per_row, x.timeout_ms = 0, 0, int(peer.timeout_ms)
+            x.peer_base = buf.table.data_ptr()
+            x.indptr, x.camera_ids, x.gaussian_ids = self.p_indptr.data_ptr(), self.p_ids[1].data_ptr(), self.p_ids[2].data_ptr()
+            x.radii, x.means2d, x.depths, x.conics = (t.data_ptr() for t in (self.p_radii, self.p_means2d, self.p_depths,
+                                                                            self.p_conics))
+            x.compensations = None
+            x.opacities, x.colors = self.opacities.data_ptr(), self.colors.data_ptr()
+            x.gaussian_base, x.nnz = self.gaussian_base, self.cap_p
+            _lib.check(lib.rs_exchange_push(ctypes.byref(x), stream))
+            _lib.check(lib.rs_exchange_wait(ctypes.byref(x), self.totals.data_ptr(), stream))
+            _lib.check(lib.rs_exchange_seal(ctypes.byref(x), self.totals.data_ptr(), stream))
+            peer._last_args = x
+            col = lambda i: buf.own + buf.offsets[i]
+            rows = buf.capacity
+            # 4. tile binning over the row capacity (rows beyond the received ones have zero radii)
+            ia = _lib.rs_isect_args()
+            ia.n_elems, ia.N, ia.I = rows, 0, self.Cl
+            ia.tile_size, ia.tile_width, ia.tile_height = 16, self.tile_w, self.tile_h
+            ia.means2d, ia.radii, ia.depths, ia.image_ids = col(0), col(5), col(1), col(6)
+            ia.tiles_per_gauss, ia.block_sums = self.tiles_per_gauss.data_ptr(), self.block_sums.data_ptr()
+            ia.n_isects, ia.overflow = self.status.data_ptr(), self.status.data_ptr() + 4
+            ia.isect_ids, ia.flatten_ids, ia.capacity = None, self.flatten_ids.data_ptr(), self.max_isects
+            _lib.check(lib.rs_isect_count(ctypes.byref(ia), stream))
+            sa = _lib.rs_isect_sorted_args()
+            ctypes.memmove(ctypes.byref(sa.isect), ctypes.byref(ia), ctypes.sizeof(ia))
+            sa.tile_offsets = self.offsets.data_ptr()
+            sa.workspace, sa.workspace_bytes = self.bin_ws.data_ptr(), self.bin_ws.numel()
+            _lib.check(lib.rs_isect_sorted(ctypes.byref(sa), stream))
+            # 5. compositing of my cameras
+            self.tile_counter.zero_()
+            r = _lib.rs_raster_fwd_args()
+            r.I, r.N, r.channels = self.Cl, 0, self.D
+            r.image_width, r.image_height, r.tile_size = self.W, self.H, 16
+            r.tile_width, r.tile_height = self.tile_w, self.tile_h
+            r.n_isects, r.n_isects_dev = self.max_isects, self.status.data_ptr()
+            r.means2d, r.conics, r.colors, r.opacities = col(0), col(2), col(4), col(3)
+            r.tile_offsets, r.flatten_ids = self.offsets.data_ptr(), self.flatten_ids.data_ptr()
+            r.render_colors, r.render_alphas = self.render_colors.data_ptr(), self.render_alphas.data_ptr()
+            r.last_ids = self.last_ids.data_ptr()
+            r.records, r.records_ready, r.n_rows = self.records.data_ptr(), 0, rows
+            r.tile_counter = self.tile_counter.data_ptr()
+            _lib.check(lib.rs_raster_fwd(ctypes.byref(r), stream))
+        return self.render_colors, self.render_alphas
+
+    def check(self) -> Dict[str, int]:
+        """The one host read: sizes and flags of the LAST frame.  Raises when the exchange failed; returns a dict with
+        `regrow` = True when a capacity was exceeded (the arrays are then re-sized collectively: render the frame again)."""
+        got, worst, err, behind = self.totals.tolist()
+        n_isects, overflow = self.status[:2].tolist()
+        if err == 1:
+            raise RuntimeError(f"ShardedFrameRenderer rank {self.rank}: a peer did not arrive within the spin limit "
+                               f"(flags behind {behind:#x})")
+        flag = torch.tensor([1 if (err == 2 or overflow) else 0, worst, n_isects], dtype=torch.int64, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=self.group)
+        regrow, worst_all, isects_all = (int(v) for v in flag.tolist())
+        if regrow:
+            rows = max(int(worst_all * 1.25) + 4096, self.peer.buffers.capacity)
+            if rows > self.peer.buffers.capacity:
+                self.peer._regrow(rows)
+            self._alloc_render(self.peer.buffers.capacity, max(int(isects_all * 1.25) + 65536, self.max_isects))
+        return dict(rows=got, rows_needed=worst_all, n_isects=n_isects, regrow=bool(regrow))

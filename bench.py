@@ -726,6 +726,38 @@ def bench_c5(rs, torch, dist, dev, rank, world, n_total=20_000_000, steps=5, war
                                     "n_isects_total": int(st[0]), "visible_rows_total": int(st[1])}
     dmod.PeerSplatExchange.enabled = True
     dmod.PeerSplatExchange._usable.clear()
+    # ---- the same frame without any host read on the way (distributed.ShardedFrameRenderer) ----------------------------
+    try:
+        if dist is None:
+            raise RuntimeError("needs a torch.distributed process group (run with --gpus N >= 2)")
+        fr = dmod.ShardedFrameRenderer(sc["means"], sc["quats"], sc["scales"], sc["opac"], sc["colors"], W, H, cl)
+        for _ in range(warmup):
+            img_f, alpha_f = fr.render(vm[mine], Ks[mine])
+        info = fr.check()
+        same = bool(torch.equal(img_f, img)) if dist is not None else None  # `img`: the last frame of the route above
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fr.render(vm[mine], Ks[mine])
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.barrier()
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0]) / steps
+        out["peer_exchange_sync_free"] = {"ms_per_step": round(ms, 3), "camera_frames_per_s": round(n_cams / (ms * 1e-3), 2),
+                                          "host_reads_per_frame": 0, "rows_received_rank0": info["rows"],
+                                          "n_isects_rank0": info["n_isects"], "regrow": info["regrow"],
+                                          "image_equal_to_rasterization_route": same}
+        del fr
+    except Exception as e:
+        out["peer_exchange_sync_free"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        if dist is not None:
+            raise
     del sc
     torch.cuda.empty_cache()
     return out

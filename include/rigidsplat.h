@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RS_ABI_VERSION 15
+#define RS_ABI_VERSION 16
 
 /* gsplat/cuda/include/Common.h:46-51 (CameraModelType) */
 enum { RS_PINHOLE = 0, RS_ORTHO = 1, RS_FISHEYE = 2, RS_FTHETA = 3 };
@@ -229,6 +229,10 @@ int rs_exchange_push(const rs_exchange_args *a, rs_stream_t stream);
  * exceeded -- nothing was written for the overfull destination, diagnostics: bit s = source s's data flag is behind,
  * bit 16 + s = its count flag is behind} */
 int rs_exchange_wait(const rs_exchange_args *a, int64_t *totals_dev, rs_stream_t stream);
+/* after rs_exchange_wait: zero the radii of the rows [received, capacity) of this rank's receive arrays (stale rows of earlier
+ * frames), so that tile binning / compositing can run over the whole capacity with device-side counts only (a sync-free
+ * sharded frame: distributed.ShardedFrameRenderer) */
+int rs_exchange_seal(const rs_exchange_args *a, const int64_t *totals_dev, rs_stream_t stream);
 
 /* The transposed exchange (backward of the above; replaces the backward of the differentiable all_to_all of
  * gsplat/distributed.py:243-248): gradients of the rows this rank RECEIVED are stored straight into the gradient arrays of

@@ -232,3 +232,62 @@ def test_peer_memory_backward_equals_nccl_backward(rs):
         p.join(timeout=60)
     for rank, msg in results:
         assert msg == "ok", f"rank {rank}:\n{msg}"
+
+
+def _syncfree_worker(rank, world, port, q):
+    """ShardedFrameRenderer (no host read between projection and image) against rasterization(distributed=True, packed=True)
+    on the same shards: bit-equal frames over an animation, sizes confirmed by the single check() read."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from conftest import pinhole_cameras, synthetic_scene
+
+        rs = importlib.import_module("3dgs_rigidbody_b200")
+        W, H, N, Cl = 320, 240, 40_000, 2
+        s = synthetic_scene(8, N, K=3)
+        vm, Ks = pinhole_cameras(world * Cl, W, H)
+        t = {k: torch.from_numpy(v).to(dev) for k, v in s.items()}
+        vm, Ks = torch.from_numpy(vm).to(dev), torch.from_numpy(Ks).to(dev)
+        mine = slice(rank * Cl, (rank + 1) * Cl)
+        lo, hi = rank * N // world, (rank + 1) * N // world
+        shard = [t[k][lo:hi].contiguous() for k in ("means", "quats", "scales", "opacities", "colors")]
+        ids = t["cluster_ids"][lo:hi].contiguous()
+        fr = rs.ShardedFrameRenderer(*shard, W, H, Cl, cluster_ids=ids, body_centers=t["body_centers"])
+        for frame in range(4):
+            bt = t["body_trans"] + 0.07 * frame
+            img, alpha = fr.render(vm[mine], Ks[mine], t["body_quats"], bt)
+            got_img, got_alpha = img.clone(), alpha.clone()
+            info = fr.check()
+            assert not info["regrow"], info
+            with torch.no_grad():
+                want, want_a, meta = rs.rasterization(*shard, vm[mine], Ks[mine], W, H, packed=True, distributed=True,
+                                                      cluster_ids=ids, body_quats=t["body_quats"], body_trans=bt,
+                                                      body_centers=t["body_centers"])
+            assert info["rows"] == meta["gaussian_ids"].numel() and info["n_isects"] == meta["flatten_ids"].numel(), (frame, info)
+            assert torch.equal(got_img, want) and torch.equal(got_alpha, want_a), frame
+        q.put((rank, "ok"))
+    except Exception:  # pragma: no cover
+        import traceback
+
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sync_free_sharded_frame_equals_distributed_rasterization(rs):
+    world = min(torch.cuda.device_count(), 8)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_syncfree_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=600) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in results:
+        assert msg == "ok", f"rank {rank}:\n{msg}"
