@@ -42,6 +42,9 @@ class FrameRenderer:
         camera_model: int = PINHOLE,
         sh_degree: Optional[int] = None,  # with it, `colors` holds SH coefficients [N,K,3] (main.py renders with degree 3)
         rgb8: bool = False,  # also keep the frame as uint8 [C,H,W,3] (`render_rgb8`), quantised like save_rendered_image
+        tight_tiles: bool = False,  # list a (tile, splat) pair only where the splat can reach alpha >= 1/255 inside the
+        # tile (rs_frame_args.tight_tiles): bit-identical images from ~20 % fewer intersections; meta() then returns a
+        # subset of the reference's lists.  False: exactly the reference's lists.
     ):
         self.lib = _lib.load()
         dev = means.device
@@ -64,6 +67,7 @@ class FrameRenderer:
         self.N, self.D, self.C, self.W, self.H = N, D, n_cameras, int(width), int(height)
         self.near_plane, self.far_plane, self.radius_clip, self.eps2d = near_plane, far_plane, radius_clip, eps2d
         self.camera_model = camera_model
+        self.tight_tiles = bool(tight_tiles)
         self.device = dev
         self.tile_size = 16
         self.tile_width = (self.W + 15) // 16
@@ -121,6 +125,7 @@ class FrameRenderer:
         a.status = self.status.data_ptr()
         a.render_rgb8 = self.render_rgb8.data_ptr() if self.render_rgb8 is not None else None
         a.out_tile_offsets = None
+        a.tight_tiles = 1 if self.tight_tiles else 0
         return a
 
     def render(self, viewmats: Tensor, Ks: Tensor, body_quats: Optional[Tensor] = None,

@@ -13,7 +13,7 @@ int rs_isect_ids_from_offsets(const int32_t *offsets, const int32_t *flatten_ids
 namespace {
 struct FrameLayout {
     size_t radii, means2d, depths, conics, records, sh_colors, tiles_per_gauss, block_sums, isect_ids, flatten_ids, bin_ws, bin_ws_bytes,
-        tile_offsets, last_ids, tile_counter, total;
+        tile_offsets, last_ids, tile_counter, footprints, total;
 };
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -42,6 +42,7 @@ FrameLayout make_layout(int32_t C, int32_t N, int32_t W, int32_t H, int32_t tile
     L.tile_offsets = take((size_t)C * tw * th * 4);
     L.last_ids = take((size_t)C * W * H * 4);
     L.tile_counter = take(256); // work counter of the persistent compositing kernel (zeroed per frame)
+    L.footprints = take(E * 16); // tight tile lists (rs_frame_args.tight_tiles)
     L.total = o;
     return L;
 }
@@ -171,6 +172,7 @@ static int render_frame_impl(const rs_frame_args *a, rs_stream_t stream, cudaEve
         p.sh_colors = reinterpret_cast<float *>(w + L.sh_colors);
     p.tiles_per_gauss = reinterpret_cast<int32_t *>(w + L.tiles_per_gauss);
     p.block_sums = nullptr; // the depth-ordered binning computes its own block sums
+    p.tile_footprints = a->tight_tiles != 0 ? reinterpret_cast<uint32_t *>(w + L.footprints) : nullptr;
     RS_CHECK(a->stages >= 0 && a->stages <= 3, "rs_render_frame: bad stages %d", a->stages);
     const bool do_bin = a->stages == 0 || (a->stages & RS_FRAME_BIN), do_composite = a->stages == 0 || (a->stages & RS_FRAME_COMPOSITE);
     if (ev)
@@ -197,6 +199,7 @@ static int render_frame_impl(const rs_frame_args *a, rs_stream_t stream, cudaEve
     sa.workspace = w + L.bin_ws;
     sa.workspace_bytes = L.bin_ws_bytes;
     sa.depth_stats_ready = p.depth_stats != nullptr ? 1 : 0;
+    sa.tile_footprints = p.tile_footprints;
     if (do_bin)
         if (int e = rs_isect_sorted(&sa, stream))
             return e;

@@ -451,10 +451,15 @@ struct BinEmitSmem {
     unsigned int hist[4 * 256]; // up to 4 passes of 8-bit digits over the (image | tile) bits
 };
 
+// FOOTPRINTS: the tiles of an element come from its tile footprint (rs_project_fwd_args.tile_footprints, one 16-byte load
+// instead of radii + means2d + count): bounding rectangle + a 64-bit mask of the listed tiles when the rectangle has at
+// most 64 of them.
+template <bool FOOTPRINTS>
 __global__ void __launch_bounds__(RS_ISECT_THREADS)
-rs_bin_emit_kernel(const rs_isect_args a, const int32_t *__restrict__ elems, const int32_t *__restrict__ n_sorted,
+rs_bin_emit_kernel(const rs_isect_args a, const uint4 *__restrict__ footprints, const int32_t *__restrict__ elems, const int32_t *__restrict__ n_sorted,
                    uint32_t tile_n_bits, uint32_t *__restrict__ tile_keys, int32_t *__restrict__ vals,
                    uint32_t *__restrict__ sort_ws, int sort_bits, int sort_nb_stride) {
+    constexpr bool TIGHT = FOOTPRINTS;
     __shared__ BinEmitSmem sm;
     const int64_t n_live = min((int64_t)*n_sorted, (int64_t)a.n_elems); // visible elements, in depth order
     // digit histograms of the keys this CTA emits, for every pass of the tile sort that follows (saves that sort its own
@@ -468,6 +473,7 @@ rs_bin_emit_kernel(const rs_isect_args a, const int32_t *__restrict__ elems, con
         sm.n_big = 0;
     int cnt[4], elem[4];
     uint32_t x0[4], y0[4], w[4], hi[4];
+    unsigned long long mask[TIGHT ? 4 : 1];
     int tsum = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -476,7 +482,26 @@ rs_bin_emit_kernel(const rs_isect_args a, const int32_t *__restrict__ elems, con
         elem[k] = 0;
         x0[k] = y0[k] = hi[k] = 0;
         w[k] = 1;
-        if (i < n_live) {
+        if (TIGHT)
+            mask[TIGHT ? k : 0] = 0ull;
+        if (TIGHT) {
+            if (i < n_live) {
+                const int32_t e = elems[i];
+                const uint4 f = footprints[e];
+                const uint32_t fw = f.w & 0xffffu, fh = f.w >> 16, n = fw * fh;
+                const unsigned long long m = (unsigned long long)f.x | ((unsigned long long)f.y << 32);
+                c = (n <= 64u) ? __popcll(m) : (int)n;
+                if (c > 0) {
+                    x0[k] = f.z & 0xffffu;
+                    y0[k] = f.z >> 16;
+                    w[k] = fw;
+                    mask[TIGHT ? k : 0] = m;
+                    const uint32_t iid = (a.image_ids != nullptr) ? (uint32_t)a.image_ids[e] : (uint32_t)(e / a.N);
+                    hi[k] = iid << tile_n_bits;
+                    elem[k] = e;
+                }
+            }
+        } else if (i < n_live) {
             const int32_t e = elems[i];
             c = a.tiles_per_gauss[e];
             if (c > 0) {
@@ -545,7 +570,19 @@ rs_bin_emit_kernel(const rs_isect_args a, const int32_t *__restrict__ elems, con
         for (int k = 0; k < 4; ++k) {
             const int s0 = start[k], s1 = start[k] + cnt[k];
             const int lo = max(s0, B), up = min(s1, Bend);
-            if (lo < up) {
+            if (TIGHT && cnt[k] <= 64 && lo < up) { // masked rectangles (more than 64 tiles: all of them, below)
+                unsigned long long mm = mask[TIGHT ? k : 0];
+                for (int skip = lo - s0; skip > 0; --skip)
+                    mm &= mm - 1ull; // listed tiles that went into earlier windows
+                const uint32_t inv = 65536u / w[k] + 1u; // t / w for t < 64, w <= 64
+                for (int sl = lo; sl < up; ++sl) {
+                    const uint32_t t = (uint32_t)__ffsll((long long)mm) - 1u;
+                    mm &= mm - 1ull;
+                    const uint32_t row = (t * inv) >> 16;
+                    sm.skey[sl - B] = hi[k] | ((y0[k] + row) * tile_w + x0[k] + (t - row * w[k]));
+                    sm.sval[sl - B] = elem[k];
+                }
+            } else if (lo < up) {
                 const uint32_t r = (uint32_t)(lo - s0);
                 uint32_t ty = y0[k] + r / w[k];
                 uint32_t tx = x0[k] + r % w[k];
@@ -733,9 +770,14 @@ extern "C" int rs_isect_sorted(const rs_isect_sorted_args *b, rs_stream_t stream
         if (int err = rs_sort_ws_prepare(w + L.sort_ws, s)) // the emission kernel accumulates the sort's histograms
             return err;
         const int sort_nb_stride = (int)((a->capacity + SORT_TILE - 1) / SORT_TILE);
-        rs_bin_emit_kernel<<<nb, RS_ISECT_THREADS, 0, s>>>(e, elems, n_sorted, tile_n_bits, tk_buf1, tv_buf1,
-                                                           reinterpret_cast<uint32_t *>(w + L.sort_ws), tile_bits,
-                                                           sort_nb_stride);
+        if (b->tile_footprints != nullptr)
+            rs_bin_emit_kernel<true><<<nb, RS_ISECT_THREADS, 0, s>>>(
+                e, reinterpret_cast<const uint4 *>(b->tile_footprints), elems, n_sorted, tile_n_bits, tk_buf1, tv_buf1,
+                reinterpret_cast<uint32_t *>(w + L.sort_ws), tile_bits, sort_nb_stride);
+        else
+            rs_bin_emit_kernel<false><<<nb, RS_ISECT_THREADS, 0, s>>>(e, nullptr, elems, n_sorted, tile_n_bits, tk_buf1,
+                                                                      tv_buf1, reinterpret_cast<uint32_t *>(w + L.sort_ws),
+                                                                      tile_bits, sort_nb_stride);
         RS_LAUNCH_CHECK("rs_bin_emit_kernel");
         // 3. stable sort on the (image | tile) bits only
         int passes = 0;

@@ -349,8 +349,16 @@ rs_project_fwd_kernel(const rs_project_fwd_args a, const PackOut po) {
         if (a.sh_coeffs != nullptr && ok)
             rs_project_sh_color(a, cam, mean, gsrc, row);
         if (a.tiles_per_gauss != nullptr) {
-            int cnt = rs_tile_count(o.rx, o.ry, o.mx, o.my, (uint32_t)a.tile_size, (uint32_t)a.tile_width,
+            int cnt;
+            if (a.tile_footprints != nullptr) {
+                uint4 fp;
+                cnt = rs_tile_footprint(o.mx, o.my, o.rx, o.ry, o.ca, o.cb, o.cc, opac, (uint32_t)a.tile_size,
+                                        (uint32_t)a.tile_width, (uint32_t)a.tile_height, fp);
+                reinterpret_cast<uint4 *>(a.tile_footprints)[row] = fp;
+            } else {
+                cnt = rs_tile_count(o.rx, o.ry, o.mx, o.my, (uint32_t)a.tile_size, (uint32_t)a.tile_width,
                                     (uint32_t)a.tile_height);
+            }
             a.tiles_per_gauss[row] = cnt;
             my_tiles += cnt;
             if (a.depth_stats != nullptr && cnt > 0) { // general path (not the frame path): per-row atomics
@@ -525,12 +533,32 @@ rs_project_fwd_staged_kernel(const rs_project_fwd_args a, const PackOut po) {
         po.gaussian_ids[row] = gid;
     }
     int cnt = 0;
+    if constexpr (!PACKED) { // (every thread of the CTA reaches this point when not PACKED)
+        if (a.tile_footprints != nullptr) { // tight tile lists, computed warp-wide
+            __shared__ RsFootWarp foot[PROJ_CHUNK / 32];
+            uint4 fp;
+            cnt = rs_tile_footprint_warp(in_range && ok, o.mx, o.my, o.rx, o.ry, o.ca, o.cb, o.cc, opac, (uint32_t)a.tile_size,
+                                         (uint32_t)a.tile_width, (uint32_t)a.tile_height, fp, foot[threadIdx.x >> 5]);
+            if (in_range) {
+                reinterpret_cast<uint4 *>(a.tile_footprints)[row] = fp;
+                a.tiles_per_gauss[row] = cnt;
+            }
+        }
+    }
     if (in_range) {
         rs_store_projected(a, row, o, ok, opac);
         if (a.sh_coeffs != nullptr && ok)
             rs_project_sh_color(a, cam, mean, src0 + t, row);
-        if (a.tiles_per_gauss != nullptr) {
-            cnt = rs_tile_count(o.rx, o.ry, o.mx, o.my, (uint32_t)a.tile_size, (uint32_t)a.tile_width, (uint32_t)a.tile_height);
+        if (a.tiles_per_gauss != nullptr && (PACKED || a.tile_footprints == nullptr)) {
+            if (a.tile_footprints != nullptr) {
+                uint4 fp;
+                cnt = rs_tile_footprint(o.mx, o.my, o.rx, o.ry, o.ca, o.cb, o.cc, opac, (uint32_t)a.tile_size,
+                                        (uint32_t)a.tile_width, (uint32_t)a.tile_height, fp);
+                reinterpret_cast<uint4 *>(a.tile_footprints)[row] = fp;
+            } else {
+                cnt = rs_tile_count(o.rx, o.ry, o.mx, o.my, (uint32_t)a.tile_size, (uint32_t)a.tile_width,
+                                    (uint32_t)a.tile_height);
+            }
             a.tiles_per_gauss[row] = cnt;
         }
     }
@@ -559,6 +587,9 @@ static int rs_project_launch(const rs_project_fwd_args *a, PackOut *po, cudaStre
     if (a->tiles_per_gauss != nullptr)
         RS_CHECK(a->tile_size > 0 && a->tile_width > 0 && a->tile_height > 0,
                  "%s: tile geometry required for fused tile counting", who);
+    RS_CHECK(a->tile_footprints == nullptr || (a->tiles_per_gauss != nullptr && a->opacities != nullptr &&
+                                               aligned16(a->tile_footprints)),
+             "%s: tile_footprints needs tiles_per_gauss, opacities and a 16-byte aligned array", who);
     RS_CHECK(a->depth_stats == nullptr || (a->tiles_per_gauss != nullptr && po == nullptr),
              "%s: depth_stats needs tiles_per_gauss and dense (not packed) rows", who);
     if (a->sh_coeffs != nullptr)

@@ -338,7 +338,7 @@ def kernel_rooflines(rs, _lib, fr, sc, q_all, t_all, frames, peak_gbs, peak_src,
         seen[name] = k + 1
         what, nbytes = name, None
         if name.startswith("rs_project_fwd"):
-            what, nbytes = "rigid transform + EWA projection + tile count + compositing records", N * 48 + E * 68
+            what, nbytes = "rigid transform + EWA projection + tile count + compositing records", N * 48 + E * (84 if fr.tight_tiles else 68)
         elif name == "rs_dord_minmax_kernel":
             what, nbytes = "depth order 1/5: min / max of the visible depth bits", E * 8
         elif name == "rs_dord_count_kernel":
@@ -566,7 +566,7 @@ def c2_api_configs(rs, sc, q_all, t_all, frames, steps=10):
     return out
 
 
-def bench_c4(rs, torch, dist, dev, rank, world, frames=6, warmup=1, in_flight=3):
+def bench_c4(rs, torch, dist, dev, rank, world, frames=6, warmup=1, in_flight=3, tight_tiles=True):
     """c4 (BASELINE configs[3]): 6 M Gaussians, 500 rigid bodies, 8 ring cameras at 3840x2160.  The 8 cameras of every
     animation frame are sharded over the ranks (camera c of frame f -> rank (c + f) % world: every rank sees every viewpoint,
     so the busiest one does not pin a rank), Gaussians replicated, NO collective on the data path.  camera-frames/s over all
@@ -577,7 +577,8 @@ def bench_c4(rs, torch, dist, dev, rank, world, frames=6, warmup=1, in_flight=3)
     q_all, t_all = torch.from_numpy(q_np).to(dev), torch.from_numpy(t_np).to(dev)
     cams_of = lambda f: [c for c in range(C) if (c + f) % world == rank]
     pipe = rs.FramePipeline(in_flight, sc["means"], sc["quats"], sc["scales"], sc["opacities"], sc["colors"], W, H,
-                            cluster_ids=sc["cluster_ids"], body_centers=sc["body_centers"], max_isects=96_000_000)
+                            cluster_ids=sc["cluster_ids"], body_centers=sc["body_centers"], max_isects=96_000_000,
+                            tight_tiles=tight_tiles)
 
     def run(fs):
         for f in fs:
@@ -614,7 +615,7 @@ def bench_c4(rs, torch, dist, dev, rank, world, frames=6, warmup=1, in_flight=3)
     ms = float(t[0])
     del pipe, sc
     torch.cuda.empty_cache()
-    return {"workload": "c4: 6M Gaussians, 500 bodies, 8 ring cameras 3840x2160; the cameras of each animation frame sharded over the ranks, no collective",
+    return {"workload": "c4: 6M Gaussians, 500 bodies, 8 ring cameras 3840x2160; the cameras of each animation frame sharded over the ranks, no collective" + ("; tight tile lists" if tight_tiles else "; the reference's tile lists"),
             "n_gpus": world, "animation_frames": frames, "camera_frames": frames * C,
             "ms_per_animation_frame": round(ms / frames, 3), "camera_frames_per_s": round(frames * C / (ms * 1e-3), 2),
             "n_isects_sample_camera_mean": int(float(n_is[0]) / world), "workspace_ok": bool(ok),
@@ -797,8 +798,10 @@ def ours_arm(args):
     sc = {k: torch.from_numpy(v).to(dev) for k, v in sc_np.items()}
     q_np, t_np = domino_poses_np(N_BODIES, None, sc_np["body_centers"])
     q_all, t_all = torch.from_numpy(q_np).to(dev), torch.from_numpy(t_np).to(dev)  # [240,K,4], [240,K,3]
+    tight = not args.reference_tile_lists
     fr = rs.FrameRenderer(sc["means"], sc["quats"], sc["scales"], sc["opacities"], sc["colors"], WIDTH, HEIGHT,
-                          cluster_ids=sc["cluster_ids"], body_centers=sc["body_centers"], max_isects=args.max_isects)
+                          cluster_ids=sc["cluster_ids"], body_centers=sc["body_centers"], max_isects=args.max_isects,
+                          tight_tiles=tight)
     frames = bench_frames(rank, args.warmup + args.steps)
     warm_frames, timed_frames = frames[:args.warmup], frames[args.warmup:]
 
@@ -810,7 +813,7 @@ def ours_arm(args):
     # ---- device-resident throughput ------------------------------------------------------------------------------
     pipe = rs.FramePipeline(args.in_flight, sc["means"], sc["quats"], sc["scales"], sc["opacities"], sc["colors"], WIDTH,
                             HEIGHT, cluster_ids=sc["cluster_ids"], body_centers=sc["body_centers"],
-                            max_isects=args.max_isects, split=not args.no_split, rgb8=True)
+                            max_isects=args.max_isects, split=not args.no_split, rgb8=True, tight_tiles=tight)
     for f in warm_frames:
         fr.render(sc["viewmats"], sc["Ks"], q_all[f], t_all[f])
         pipe.submit(sc["viewmats"], sc["Ks"], q_all[f], t_all[f])
@@ -836,6 +839,42 @@ def ours_arm(args):
     launches = lib.rs_launch_count() - n0
     assert not pipe.overflowed()
     n_isects_last = pipe.renderers[(pipe.count - 1) % args.in_flight].n_isects()
+    # tight tile lists: the last timed frame once more from the reference's lists -- same pixels, bit for bit?
+    tile_lists = {"mode": "tight" if tight else "reference"}
+    if tight:
+        last = pipe.renderers[(pipe.count - 1) % args.in_flight]
+        plain = rs.FrameRenderer(sc["means"], sc["quats"], sc["scales"], sc["opacities"], sc["colors"], WIDTH, HEIGHT,
+                                 cluster_ids=sc["cluster_ids"], body_centers=sc["body_centers"], max_isects=args.max_isects,
+                                 rgb8=True)
+        f_last = timed_frames[-1]
+        img_p, alpha_p = plain.render(sc["viewmats"], sc["Ks"], q_all[f_last], t_all[f_last])
+        torch.cuda.synchronize()
+        tile_lists.update(
+            n_isects_tight=n_isects_last, n_isects_reference_lists=plain.n_isects(),
+            image_bit_identical_to_reference_lists=bool(torch.equal(img_p, last.render_colors) and
+                                                        torch.equal(alpha_p, last.render_alphas) and
+                                                        torch.equal(plain.render_rgb8, last.render_rgb8)),
+            what="a (tile, splat) pair is listed only where the splat can reach alpha >= 1/255 at a pixel centre of the tile; "
+                 "the pairs dropped are skipped at every pixel by RasterizeToPixels3DGSFwd.cu:148-149")
+        del plain
+        if not args.no_extras and world == 1:  # the same timed frames from the reference's lists, for comparison
+            pipe_ref = rs.FramePipeline(args.in_flight, sc["means"], sc["quats"], sc["scales"], sc["opacities"], sc["colors"],
+                                        WIDTH, HEIGHT, cluster_ids=sc["cluster_ids"], body_centers=sc["body_centers"],
+                                        max_isects=args.max_isects, split=not args.no_split, rgb8=True)
+            for f in warm_frames:
+                pipe_ref.submit(sc["viewmats"], sc["Ks"], q_all[f], t_all[f])
+            pipe_ref.join()
+            torch.cuda.synchronize()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            for f in timed_frames:
+                pipe_ref.submit(sc["viewmats"], sc["Ks"], q_all[f], t_all[f])
+            pipe_ref.join()
+            r1.record()
+            torch.cuda.synchronize()
+            tile_lists["value_with_reference_lists"] = round(args.steps / (r0.elapsed_time(r1) * 1e-3), 2)
+            del pipe_ref
+        torch.cuda.empty_cache()
 
     # ---- end to end: host inputs -> C ABI -> host results, `in_flight` frames pipelined ---------------------------------
     K = N_BODIES
@@ -909,7 +948,7 @@ def ours_arm(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_max / args.steps, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": base_config(),
-        "run": {"n_isects_last_frame": n_isects_last, "frames_in_flight_per_gpu": args.in_flight,
+        "run": {"n_isects_last_frame": n_isects_last, "tile_lists": tile_lists, "frames_in_flight_per_gpu": args.in_flight,
                 "sharding": f"{world} rank(s) x the same {args.steps} frames, no collective on the data path"},
         "e2e": {"value": round(e2e8_fps, 2), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h8,
                 "api": api, "result": "uint8 [H,W,3] frame, quantised as the reference's loop stores it (main.py:140-171 "
@@ -999,6 +1038,8 @@ def main():
                     help="one stream per in-flight frame instead of (high-priority binning stream, compositing stream)")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-extras", action="store_true", help="headline only: skip kernels / roofline / other_configs / cpu_baseline")
+    ap.add_argument("--reference-tile-lists", action="store_true",
+                    help="bin every tile of a splat's bounding rectangle (exactly the reference's lists) instead of the tight lists")
     ap.add_argument("--skip", default="", help="comma list of other_configs to skip: c4,c5")
     args = ap.parse_args()
     if args.impl == "reference":

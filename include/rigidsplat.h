@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RS_ABI_VERSION 16
+#define RS_ABI_VERSION 17
 
 /* gsplat/cuda/include/Common.h:46-51 (CameraModelType) */
 enum { RS_PINHOLE = 0, RS_ORTHO = 1, RS_FISHEYE = 2, RS_FTHETA = 3 };
@@ -113,6 +113,14 @@ typedef struct {
      * caller.  They are the first step of the depth ordering of rs_isect_sorted (depth_stats_ready), which rs_render_frame
      * fuses this way. */
     uint32_t *depth_stats;
+    /* optional (needs tiles_per_gauss and opacities): tight tile lists.  tile_footprints[row] = {mask lo, mask hi,
+     * x0 | y0 << 16, w | h << 16}: the bounding rectangle of tiles the reference lists (IntersectTile.cu:60-93) and, when it
+     * has at most 64 tiles, bit t of the 64-bit mask = "tile t of the rectangle (row-major) holds a pixel centre where the
+     * splat can reach alpha >= 1/255" -- every other (tile, splat) pair is skipped by every pixel of the tile in
+     * RasterizeToPixels3DGSFwd.cu:148-149, so dropping it changes no pixel.  tiles_per_gauss then counts the mask bits
+     * (rectangles of more than 64 tiles keep all their tiles).  Consumed by rs_isect_sorted_args.tile_footprints; the lists
+     * are a subset of the reference's, the images are bit-identical. */
+    uint32_t *tile_footprints;  /* [B*C*N,4] out, 16-byte aligned */
 } rs_project_fwd_args;
 int rs_project_fwd(const rs_project_fwd_args *a, rs_stream_t stream);
 
@@ -310,6 +318,9 @@ typedef struct {
      * by the producer of the rows (rs_project_fwd_args.depth_stats) after rs_isect_sorted_prepare(); 0: computed here */
     int32_t depth_stats_ready;
     int32_t _pad;
+    /* optional: emit only the tiles of rs_project_fwd_args.tile_footprints (isect.tiles_per_gauss must be the counts written
+     * with them); NULL: every tile of the bounding rectangle, exactly the reference's lists */
+    const uint32_t *tile_footprints;
 } rs_isect_sorted_args;
 /* for a caller that fuses the depth statistics into its projection: clear the ordering state of `workspace` (enqueued on
  * `stream`, BEFORE the kernel that accumulates the statistics) / where that kernel has to accumulate them */
@@ -501,7 +512,10 @@ typedef struct {
      * Lets a caller put the short latency-bound binning kernels of the next frame on a high-priority stream so that they
      * are dispatched underneath the compositing of the previous one (FramePipeline). */
     int32_t stages;
-    int32_t _pad;
+    /* != 0: tight tile lists (rs_project_fwd_args.tile_footprints): the same image bit for bit from fewer intersections;
+     * the exported lists (out_tile_offsets, rs_frame_workspace_ptr) are then a subset of the reference's.  0: the
+     * reference's lists exactly. */
+    int32_t tight_tiles;
     uint8_t *render_rgb8;        /* [C,H,W,3] out, optional: the frame as 8-bit RGB (see rs_raster_fwd_args.render_rgb8) */
 } rs_frame_args;
 #define RS_FRAME_BIN 1

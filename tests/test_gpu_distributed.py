@@ -130,12 +130,14 @@ def _peer_worker(rank, world, port, q):
                 assert torch.equal(alpha_p, alpha_n.detach()), (frame, variant)
         # (no per-rank content assertion here: a rank whose cameras look away from the scene legitimately receives no rows,
         # and a rank leaving early would strand the others inside a collective)
-        # nothing visible anywhere (every Gaussian behind every camera): zero rows sent and received on both routes
-        gone = t["means"][lo:hi] - torch.tensor([0.0, 0.0, 100.0], device=dev)
+        # nothing visible anywhere (a near plane beyond the whole scene culls every Gaussian for every camera of the ring,
+        # whatever the world size): zero rows sent and received on both routes
+        gone = t["means"][lo:hi]
         args = (t["quats"][lo:hi], t["scales"][lo:hi], t["opacities"][lo:hi], t["colors"][lo:hi], vm[mine], Ks[mine], W, H)
         with torch.no_grad():
-            img_p, alpha_p, meta_p = rs.rasterization(gone, *args, packed=True, distributed=True)
-        img_n, alpha_n, _ = rs.rasterization(gone.clone().requires_grad_(True), *args, packed=True, distributed=True)
+            img_p, alpha_p, meta_p = rs.rasterization(gone, *args, packed=True, distributed=True, near_plane=1e6, far_plane=1e7)
+        img_n, alpha_n, _ = rs.rasterization(gone.clone().requires_grad_(True), *args, packed=True, distributed=True,
+                                             near_plane=1e6, far_plane=1e7)
         assert meta_p["gaussian_ids"].numel() == 0 and float(alpha_p.abs().max()) == 0.0
         assert torch.equal(img_p, img_n.detach()) and torch.equal(alpha_p, alpha_n.detach())
         peer = next(iter(dmod.PeerSplatExchange._instances.values()))

@@ -450,6 +450,61 @@ def test_frame_renderer_matches_compat_path(rs, orc):
     assert torch.equal(img_3, img_f)
 
 
+@pytest.mark.parametrize("case", ["small_splats", "large_anisotropic", "low_opacity", "c2_full_size"])
+def test_tight_tile_lists_give_the_same_image(rs, case):
+    """FrameRenderer(tight_tiles=True) lists a (tile, splat) pair only where the splat can reach alpha >= 1/255 inside the
+    tile; every dropped pair is one the compositing of RasterizeToPixels3DGSFwd.cu:148-149 skips at every pixel, so the float
+    image, the alphas and the 8-bit frame must be BIT-identical to the frame rendered from the reference's lists, and the
+    tight lists must be an order-preserving subset of them."""
+    import bench
+
+    if case == "c2_full_size":
+        sc = bench.make_domino_scene(1_000_000, 20, device=DEV)
+        W, H, C = 1920, 1080, 1
+        vm, Ks = sc["viewmats"], sc["Ks"]
+        bq, bt = bench.domino_poses(20, frame=77, device=DEV, centers=sc["body_centers"])
+        scene = (sc["means"], sc["quats"], sc["scales"], sc["opacities"], sc["colors"])
+        ids, centers = sc["cluster_ids"], sc["body_centers"]
+    else:
+        W, H, C = 400, 300, 2
+        kw = dict(small_splats=dict(s_max=0.03), large_anisotropic=dict(s_max=0.5, spread=1.5),
+                  low_opacity=dict(s_max=0.15))[case]
+        s = synthetic_scene(21, 40_000, K=4, **kw)
+        if case == "large_anisotropic":  # needles: one long axis
+            s["scales"][:, 1:] *= 0.04
+        if case == "low_opacity":  # many splats near the 1/255 threshold
+            s["opacities"] = (s["opacities"] * 0.03).astype(np.float32)
+        vmn, Ksn = pinhole_cameras(C, W, H)
+        vm, Ks = T(vmn), T(Ksn)
+        scene = tuple(T(s[k]) for k in ("means", "quats", "scales", "opacities", "colors"))
+        ids, centers, bq, bt = T(s["cluster_ids"]), T(s["body_centers"]), T(s["body_quats"]), T(s["body_trans"])
+    out = {}
+    for tight in (False, True):
+        fr = rs.FrameRenderer(*scene, W, H, cluster_ids=ids, body_centers=centers, n_cameras=C, rgb8=True, tight_tiles=tight)
+        img, alpha = fr.render(vm, Ks, bq, bt)
+        torch.cuda.synchronize()
+        assert not fr.overflowed()
+        m = fr.meta()
+        out[tight] = (img.clone(), alpha.clone(), fr.render_rgb8.clone(), m["n_isects"], m["flatten_ids"].clone(),
+                      m["isect_offsets"].clone(), m["isect_ids"].clone())
+        del fr
+    ref_l, tight_l = out[False], out[True]
+    assert torch.equal(ref_l[0], tight_l[0]) and torch.equal(ref_l[1], tight_l[1]) and torch.equal(ref_l[2], tight_l[2])
+    assert float(ref_l[1].mean()) > 0.01
+    assert tight_l[3] <= ref_l[3]
+    if case != "low_opacity":
+        assert tight_l[3] < ref_l[3], "the test scene does not exercise the culling"
+    # subset in the same order: the tight list is the reference list with some entries removed
+    keys_ref = ref_l[6]
+    keys_tight = tight_l[6]
+    assert bool((keys_tight[1:] >= keys_tight[:-1]).all())
+    pair = lambda keys, ids: (keys >> 32) * (1 << 31) + ids.long()  # (image|tile, flatten id) identifies an entry
+    pr, pt = pair(keys_ref, ref_l[4]), pair(keys_tight, tight_l[4])
+    pos = torch.searchsorted(pr.sort().values, pt)
+    assert bool((pr.sort().values[pos.clamp(max=pr.numel() - 1)] == pt).all())
+    print(f"{case}: {ref_l[3]} -> {tight_l[3]} intersections ({tight_l[3] / max(ref_l[3], 1):.3f})")
+
+
 def test_full_size_properties_1m_1080p(rs):
     """BASELINE c2 size (1 M Gaussians, 20 bodies, 1080p): size-independent properties instead of a CPU comparison."""
     import bench

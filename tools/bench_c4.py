@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--frames", type=int, default=24, help="animation frames (each = 8 cameras)")
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--in-flight", type=int, default=3)
+    ap.add_argument("--reference-tile-lists", action="store_true")
     args = ap.parse_args()
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -32,7 +33,8 @@ def main():
 
         dist.init_process_group("nccl", device_id=dev)
     rs = importlib.import_module("3dgs_rigidbody_b200")
-    res = bench.bench_c4(rs, torch, dist, dev, rank, world, frames=args.frames, warmup=args.warmup, in_flight=args.in_flight)
+    res = bench.bench_c4(rs, torch, dist, dev, rank, world, frames=args.frames, warmup=args.warmup, in_flight=args.in_flight,
+                         tight_tiles=not args.reference_tile_lists)
     if rank == 0:
         print(json.dumps(res))
     if dist is not None:
