@@ -244,34 +244,43 @@ __device__ __forceinline__ int rs_tile_footprint_warp(bool valid, float mx, floa
             incl += v;
     }
     const int total = __shfl_sync(0xffffffffu, incl, 31);
-    fs.excl[lane] = incl - m;
-    fs.p0[lane] = make_float4(mx, my, qa, qb);
-    fs.p1[lane] = make_float4(qc, masked ? rs_cull_limit(qa, qb, qc, opac) : 0.f, __uint_as_float(x0 | (y0 << 16)),
-                              __uint_as_float(w));
-    fs.mask[lane][0] = 0u;
-    fs.mask[lane][1] = 0u;
+    // the lanes that own tiles, compacted: owner c = the c-th such lane
+    const unsigned has = __ballot_sync(0xffffffffu, m > 0);
+    const int ci = __popc(has & ((1u << lane) - 1u));
+    if (m > 0) {
+        fs.excl[ci] = incl - m;
+        fs.p0[ci] = make_float4(mx, my, qa, qb);
+        // (65536 / w + 1) * t >> 16 = t / w for t < 64, w <= 64
+        fs.p1[ci] = make_float4(qc, rs_cull_limit(qa, qb, qc, opac), __uint_as_float(x0 | (y0 << 16)),
+                                __uint_as_float((65536u / w + 1u) | (w << 20)));
+        fs.mask[ci][0] = 0u;
+        fs.mask[ci][1] = 0u;
+    }
     __syncwarp();
     const float ts = (float)tile_size;
-    for (int j = lane; j < total; j += 32) {
-        int l = 0; // owner of tile j: the last lane whose exclusive offset is <= j (it has tiles: see the scan)
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1)
-            if (fs.excl[l + s] <= j)
-                l += s;
-        const uint32_t t = (uint32_t)(j - fs.excl[l]);
-        const float4 g0 = fs.p0[l], g1 = fs.p1[l];
-        const uint32_t xy = __float_as_uint(g1.z), ww = __float_as_uint(g1.w);
-        const uint32_t row = (t * (65536u / ww + 1u)) >> 16; // t / ww for t < 64, ww <= 64
-        const uint32_t col = t - row * ww;
-        const float fx0 = (float)((xy & 0xffffu) + col) * ts + 0.5f, fy0 = (float)((xy >> 16) + row) * ts + 0.5f;
-        if (rs_splat_touches_rect(g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, fx0, fx0 + ts - 1.f, fy0, fy0 + ts - 1.f))
-            atomicOr(&fs.mask[l][t >> 5], 1u << (t & 31u));
+    int started = 0; // owners whose first tile lies before the current window of 32 tiles
+    for (int base = 0; base < total; base += 32) {
+        const int rel = incl - m - base;
+        const unsigned heads = __reduce_or_sync(0xffffffffu, (m > 0 && rel >= 0 && rel < 32) ? 1u << rel : 0u);
+        const int j = base + lane;
+        if (j < total) {
+            const int oc = started + __popc(heads & (0xffffffffu >> (31 - lane))) - 1; // owner of tile j
+            const uint32_t t = (uint32_t)(j - fs.excl[oc]);
+            const float4 g0 = fs.p0[oc], g1 = fs.p1[oc];
+            const uint32_t xy = __float_as_uint(g1.z), iw = __float_as_uint(g1.w);
+            const uint32_t row = (t * (iw & 0xfffffu)) >> 16;
+            const uint32_t col = t - row * (iw >> 20);
+            const float fx0 = (float)((xy & 0xffffu) + col) * ts + 0.5f, fy0 = (float)((xy >> 16) + row) * ts + 0.5f;
+            if (rs_splat_touches_rect(g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, fx0, fx0 + ts - 1.f, fy0, fy0 + ts - 1.f))
+                atomicOr(&fs.mask[oc][t >> 5], 1u << (t & 31u));
+        }
+        started += __popc(heads);
     }
     __syncwarp();
     unsigned long long mask = ~0ull;
     int cnt = (int)n;
     if (masked) {
-        mask = (unsigned long long)fs.mask[lane][0] | ((unsigned long long)fs.mask[lane][1] << 32);
+        mask = (unsigned long long)fs.mask[ci][0] | ((unsigned long long)fs.mask[ci][1] << 32);
         cnt = __popcll(mask);
     }
     __syncwarp(); // the scratch may be reused by the caller's next round

@@ -404,7 +404,7 @@ __device__ __forceinline__ void rs_bulk_g2s(void *smem_dst, const void *gmem_src
 }
 
 template <bool HAS_RIGID, bool PACKED>
-__global__ void __launch_bounds__(PROJ_CHUNK, PACKED ? 4 : 3) // packed: one more resident CTA hides the look-back wait
+__global__ void __launch_bounds__(PROJ_CHUNK, 4)
 rs_project_fwd_staged_kernel(const rs_project_fwd_args a, const PackOut po) {
     extern __shared__ __align__(16) float smem_dyn[]; // pose table (HAS_RIGID only)
     __shared__ __align__(16) ProjStage st;
