@@ -376,12 +376,20 @@ rs_project_bwd_kernel(const rs_project_bwd_args a) {
             }
         }
 
-        if (a.v_viewmats != nullptr) {
-            // reduce over the Gaussians of one camera: warp shuffle when the warp is on a single image
+        if (a.v_viewmats != nullptr) { // (uniform over the CTA: the barriers below are reached by every thread)
+            // Reduce over the Gaussians of one camera: warp shuffle when the warp is on a single image, then the eight warp
+            // sums of the CTA through shared memory, so that a camera receives one atomic per (CTA, component) instead of
+            // one per warp -- 8 x fewer float atomics in arbitrary order, i.e. a smaller rounding error of the 16 sums
+            // every row contributes to (the reference adds one atomic per warp, ProjectionEWA3DGSFused.cu:515-530).
+            __shared__ float vw_sum[RS_ISECT_THREADS / 32][12];
+            __shared__ int vw_img[RS_ISECT_THREADS / 32];
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
             const unsigned any_active = __ballot_sync(0xffffffffu, active);
+            bool uniform = false;
+            uint32_t img_lane0 = 0;
             if (any_active) {
-                const uint32_t img_lane0 = __shfl_sync(0xffffffffu, img, __ffs(any_active) - 1);
-                const bool uniform = __all_sync(0xffffffffu, !active || img == img_lane0);
+                img_lane0 = __shfl_sync(0xffffffffu, img, __ffs(any_active) - 1);
+                uniform = __all_sync(0xffffffffu, !active || img == img_lane0);
                 if (uniform) {
 #pragma unroll
                     for (int q = 0; q < 9; ++q)
@@ -393,8 +401,16 @@ rs_project_bwd_kernel(const rs_project_bwd_args a) {
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1)
                             v_t[q] += __shfl_xor_sync(0xffffffffu, v_t[q], o);
-                }
-                if (active && (!uniform || (threadIdx.x & 31) == (unsigned)(__ffs(any_active) - 1))) {
+                    if (lane == __ffs(any_active) - 1) {
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) {
+#pragma unroll
+                            for (int j = 0; j < 3; ++j)
+                                vw_sum[warp][i * 4 + j] = v_R[3 * i + j];
+                            vw_sum[warp][i * 4 + 3] = v_t[i];
+                        }
+                    }
+                } else if (active) { // a warp straddling two images: per-row atomics
                     float *o = a.v_viewmats + (size_t)img * 16;
 #pragma unroll
                     for (int i = 0; i < 3; ++i) {
@@ -405,6 +421,27 @@ rs_project_bwd_kernel(const rs_project_bwd_args a) {
                     }
                 }
             }
+            if (lane == 0)
+                vw_img[warp] = uniform ? (int)img_lane0 : -1;
+            __syncthreads();
+            if (threadIdx.x < 12) { // one thread per component: runs of warps on the same image share one atomic
+                float run = 0.f;
+                int run_img = -1;
+                for (int w = 0; w < RS_ISECT_THREADS / 32; ++w) {
+                    const int wi = vw_img[w];
+                    if (wi != run_img) {
+                        if (run_img >= 0)
+                            atomicAdd(a.v_viewmats + (size_t)run_img * 16 + threadIdx.x, run);
+                        run = 0.f;
+                        run_img = wi;
+                    }
+                    if (wi >= 0)
+                        run += vw_sum[w][threadIdx.x];
+                }
+                if (run_img >= 0)
+                    atomicAdd(a.v_viewmats + (size_t)run_img * 16 + threadIdx.x, run);
+            }
+            __syncthreads();
         }
     }
 }

@@ -651,6 +651,10 @@ def _c5_cameras(torch, dev, n_cams, W, H):
     return torch.from_numpy(vms).to(dev), torch.from_numpy(Ks).to(dev)
 
 
+class _Skip(Exception):
+    pass
+
+
 def bench_c5(rs, torch, dist, dev, rank, world, n_total=20_000_000, steps=5, warmup=2, n_cams=8):
     """c5 (BASELINE configs[4]): 20 M Gaussians sharded over the ranks (contiguous blocks), 8 ring cameras at 1080p owned
     8 / world per rank; every rank projects ITS Gaussians to ALL cameras and the projected splats travel to the rank owning the
@@ -730,7 +734,7 @@ def bench_c5(rs, torch, dist, dev, rank, world, n_total=20_000_000, steps=5, war
     # ---- the same frame without any host read on the way (distributed.ShardedFrameRenderer) ----------------------------
     try:
         if dist is None:
-            raise RuntimeError("needs a torch.distributed process group (run with --gpus N >= 2)")
+            raise _Skip("needs a torch.distributed process group (run with --gpus N >= 2)")
         fr = dmod.ShardedFrameRenderer(sc["means"], sc["quats"], sc["scales"], sc["opac"], sc["colors"], W, H, cl)
         for _ in range(warmup):
             img_f, alpha_f = fr.render(vm[mine], Ks[mine])
@@ -755,6 +759,8 @@ def bench_c5(rs, torch, dist, dev, rank, world, n_total=20_000_000, steps=5, war
                                           "n_isects_rank0": info["n_isects"], "regrow": info["regrow"],
                                           "image_equal_to_rasterization_route": same}
         del fr
+    except _Skip as e:
+        out["peer_exchange_sync_free"] = {"skipped": str(e)}
     except Exception as e:
         out["peer_exchange_sync_free"] = {"error": f"{type(e).__name__}: {e}"[:300]}
         if dist is not None:

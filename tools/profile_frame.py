@@ -1,10 +1,10 @@
 #!/usr/bin/env python
 """One c2 frame at a time through FrameRenderer on a single stream: the target of the `ncu --set full` captures.
 
-    ncu --set full --clock-control none --import-source on -s <13 * warm-up frames> -c 13 -o gpurun_out/prof \
+    ncu --set full --clock-control none --import-source on -s <12 * warm-up frames> -c 12 -o gpurun_out/prof \
         python tools/profile_frame.py --frames 4
-A frame is 13 kernel launches (projection; depth order: min/max, count, scan, scatter, sort; tile count, scan, emission; 2
-tile-key radix passes; offsets; compositing);
+A frame is 12 kernel launches (projection incl. the depth statistics; depth order: count, scan, scatter, sort; tile count,
+scan, emission; 2 tile-key radix passes; offsets; compositing), with the tight tile lists bench.py uses;
 `--packed` profiles the packed projection instead (1 launch per frame)."""
 import argparse
 import importlib
@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--frames", type=int, default=4)
     ap.add_argument("--packed", action="store_true")
     ap.add_argument("--channels", type=int, default=3)
+    ap.add_argument("--reference-tile-lists", action="store_true", help="the reference's tile lists instead of the tight ones")
     args = ap.parse_args()
     rs = importlib.import_module("3dgs_rigidbody_b200")
     dev = "cuda:0"
@@ -38,7 +39,8 @@ def main():
         print("nnz", out[1].numel())
         return
     fr = rs.FrameRenderer(sc["means"], sc["quats"], sc["scales"], sc["opacities"], colors, bench.WIDTH, bench.HEIGHT,
-                          cluster_ids=sc["cluster_ids"], body_centers=sc["body_centers"], max_isects=24_000_000)
+                          cluster_ids=sc["cluster_ids"], body_centers=sc["body_centers"], max_isects=24_000_000,
+                          tight_tiles=not args.reference_tile_lists)
     for f in range(args.frames):
         bq, bt = bench.domino_poses(bench.N_BODIES, frame=60 + f, device=dev, centers=sc["body_centers"])
         torch.cuda.synchronize()
