@@ -78,6 +78,9 @@ template <int NV> __device__ __forceinline__ int fold_owner(const int lane, int 
 
 // component layout of the reduced vector: [0,CDIM) v_colors, CDIM..+2 v_conics, +3..+4 v_means2d, +5 v_opacity,
 // +6..+7 v_means2d_abs (ABS only)
+#ifndef RS_BWD_PREFETCH
+#define RS_BWD_PREFETCH 1
+#endif
 template <int CDIM, bool ABS>
 __global__ void __launch_bounds__(RAST_THREADS, (CDIM <= 16) ? 3 : 2)
 rs_raster_bwd_kernel(const rs_raster_bwd_args b, const int ch_off, const int ch_cnt, const bool first_chunk) {
@@ -240,6 +243,24 @@ rs_raster_bwd_kernel(const rs_raster_bwd_args b, const int ch_off, const int ch_
 #endif
     };
 
+    // The id of this thread's splat in the NEXT batch is fetched one batch ahead and its rows are requested into L2, so a
+    // batch change costs one exposed L2 round trip instead of two dependent DRAM round trips (flatten id -> attributes).
+    auto fetch_id = [&](int bb) -> int32_t {
+        const int32_t idx = range_end - 1 - RAST_THREADS * bb - tr;
+        if (bb >= num_batches || idx < range_start)
+            return -1;
+        const int32_t g = a.flatten_ids[idx];
+#if RS_BWD_PREFETCH
+        const int32_t go = a.attr_mod_opacities > 0 ? g % a.attr_mod_opacities : g;
+        const int32_t gc = a.attr_mod_colors > 0 ? g % a.attr_mod_colors : g;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.means2d + (size_t)g * 2));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.conics + (size_t)g * 3));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.opacities + go));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(a.colors + (size_t)gc * a.channels + ch_off));
+#endif
+        return g;
+    };
+    int32_t g_next = fetch_id(first_batch);
     for (int bb = first_batch; bb < num_batches; ++bb) {
         __syncthreads();
         if (bb > first_batch)
@@ -248,8 +269,9 @@ rs_raster_bwd_kernel(const rs_raster_bwd_args b, const int ch_off, const int ch_
         const int32_t batch_end = range_end - 1 - RAST_THREADS * bb;
         const int32_t batch_size = min(RAST_THREADS, batch_end + 1 - range_start);
         const int32_t idx = batch_end - tr;
+        const int32_t g_cur = g_next;
         if (idx >= range_start) {
-            const int32_t g = a.flatten_ids[idx];
+            const int32_t g = g_cur;
             const int32_t go = a.attr_mod_opacities > 0 ? g % a.attr_mod_opacities : g;
             const int32_t gc = a.attr_mod_colors > 0 ? g % a.attr_mod_colors : g;
             const float2 xy = reinterpret_cast<const float2 *>(a.means2d)[g];
@@ -266,6 +288,7 @@ rs_raster_bwd_kernel(const rs_raster_bwd_args b, const int ch_off, const int ch_
                 if (k < ch_cnt)
                     sm.color[k][tr] = cp[k];
         }
+        g_next = fetch_id(bb + 1);
         __syncthreads();
 
         const int t_begin = max(0, batch_end - warp_bin_final);

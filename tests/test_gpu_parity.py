@@ -450,7 +450,7 @@ def test_frame_renderer_matches_compat_path(rs, orc):
     assert torch.equal(img_3, img_f)
 
 
-@pytest.mark.parametrize("case", ["small_splats", "large_anisotropic", "low_opacity", "c2_full_size"])
+@pytest.mark.parametrize("case", ["small_splats", "large_anisotropic", "low_opacity", "general_kernel", "c2_full_size"])
 def test_tight_tile_lists_give_the_same_image(rs, case):
     """FrameRenderer(tight_tiles=True) lists a (tile, splat) pair only where the splat can reach alpha >= 1/255 inside the
     tile; every dropped pair is one the compositing of RasterizeToPixels3DGSFwd.cu:148-149 skips at every pixel, so the float
@@ -468,7 +468,7 @@ def test_tight_tile_lists_give_the_same_image(rs, case):
     else:
         W, H, C = 400, 300, 2
         kw = dict(small_splats=dict(s_max=0.03), large_anisotropic=dict(s_max=0.5, spread=1.5),
-                  low_opacity=dict(s_max=0.15))[case]
+                  low_opacity=dict(s_max=0.15), general_kernel=dict(s_max=0.08))[case]
         s = synthetic_scene(21, 40_000, K=4, **kw)
         if case == "large_anisotropic":  # needles: one long axis
             s["scales"][:, 1:] *= 0.04
@@ -477,6 +477,11 @@ def test_tight_tile_lists_give_the_same_image(rs, case):
         vmn, Ksn = pinhole_cameras(C, W, H)
         vm, Ks = T(vmn), T(Ksn)
         scene = tuple(T(s[k]) for k in ("means", "quats", "scales", "opacities", "colors"))
+        if case == "general_kernel":  # means not 16-byte aligned: the projection kernel without TMA staging, which
+            # computes the footprints per lane instead of per warp
+            pad = torch.cat([torch.zeros(1, 3, device=DEV), scene[0]])
+            scene = (pad[1:],) + scene[1:]
+            assert scene[0].data_ptr() % 16 != 0 and scene[0].is_contiguous()
         ids, centers, bq, bt = T(s["cluster_ids"]), T(s["body_centers"]), T(s["body_quats"]), T(s["body_trans"])
     out = {}
     for tight in (False, True):
