@@ -605,6 +605,9 @@ def rasterize_to_pixels_3dgs_bwd(
         _fill_raster(a.f, means2d, conics, colors, opacities, backgrounds, masks, image_width, image_height,
                      tile_size, tile_offsets, flatten_ids, _attr_mod_colors, _attr_mod_opacities)
         a.f.render_alphas, a.f.last_ids = _ptr(render_alphas), _ptr(last_ids)
+        # staging records of the batch ring (32 B per projected splat), packed by rs_raster_bwd itself
+        records = torch.empty((max(a.f.n_rows, 1), 8), dtype=torch.float32, device=dev)
+        a.f.records, a.f.records_ready = records.data_ptr(), 0
         v_means2d = torch.zeros_like(means2d)
         v_conics = torch.zeros_like(conics)
         v_colors = torch.zeros_like(colors)

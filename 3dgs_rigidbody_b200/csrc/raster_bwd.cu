@@ -15,7 +15,7 @@
 //     memory is a compare-and-swap loop that spins when the eight warps of a tile hit the same words, while red.global is
 //     a fire-and-forget L2 operation.
 // Per-pixel math follows RasterizeToPixels3DGSBwd.cu:160-242.
-#include "common.cuh"
+#include "raster_common.cuh"
 
 #define RAST_THREADS 256
 #ifndef RS_BWD_SMEM_REDUCE
@@ -395,6 +395,329 @@ rs_raster_bwd_kernel(const rs_raster_bwd_args b, const int ch_off, const int ch_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Ring variant (RS_BWD_RING, default): the same per-pixel math and the same per-warp reduction, but the batches travel
+// through a 3-stage shared-memory ring filled by a producer warp (warp 8) with cp.async completing on mbarriers, as in
+// the forward kernel.  The eight compositing warps of a tile no longer meet at a __syncthreads per batch: ncu showed the
+// barrier as the top stall reason of the kernel above (3.6 warps per issue slot), because the warps of a tile hit very
+// different numbers of splats.  Batches of 128 splats, 32-byte records (packed by rs_raster_pack_records) + colour rows
+// + flatten ids per stage.
+// ---------------------------------------------------------------------------------------------------------------------
+#ifndef RS_BWD_RING
+#define RS_BWD_RING 1
+#endif
+#ifndef RS_BWD_RING_CTAS
+#define RS_BWD_RING_CTAS 3
+#endif
+#define BWD_BATCH 128
+#define BWD_STAGES 3
+#define BWD_CONSUMERS 8
+#define BWD_THREADS (32 * (BWD_CONSUMERS + 1))
+template <int CDIM> struct BwdRingCfg {
+    static constexpr int CP = (CDIM + 3) & ~3;
+    static constexpr int STAGE_FLOATS = BWD_BATCH * (8 + CP + 1); // records (2 x float4), colour row, flatten id
+    static constexpr size_t SMEM = (size_t)BWD_STAGES * STAGE_FLOATS * sizeof(float);
+};
+
+template <int CDIM, bool ABS>
+__global__ void __launch_bounds__(BWD_THREADS, (CDIM <= 16) ? RS_BWD_RING_CTAS : 2)
+rs_raster_bwd_ring_kernel(const rs_raster_bwd_args b, const int ch_off, const int ch_cnt, const bool first_chunk) {
+    using Cfg = BwdRingCfg<CDIM>;
+    constexpr int CP = Cfg::CP;
+    constexpr int NV = CDIM + 6 + (ABS ? 2 : 0);
+    extern __shared__ __align__(16) float ring[];
+    __shared__ uint64_t full_bar[BWD_STAGES], empty_bar[BWD_STAGES];
+    __shared__ int tile_bin_final;
+    const rs_raster_fwd_args &a = b.f;
+
+    const uint32_t tiles_per_image = (uint32_t)(a.tile_width * a.tile_height);
+    const uint32_t image_id = blockIdx.x / tiles_per_image;
+    const uint32_t tile_id = blockIdx.x - image_id * tiles_per_image;
+    const uint32_t tile_y = tile_id / (uint32_t)a.tile_width;
+    const uint32_t tile_x = tile_id - tile_y * (uint32_t)a.tile_width;
+    if (a.masks != nullptr && !a.masks[(size_t)image_id * tiles_per_image + tile_id])
+        return;
+
+    const int tr = threadIdx.x;
+    const int lane = tr & 31, warp = tr >> 5;
+    const bool producer = warp == BWD_CONSUMERS;
+    const int cw = producer ? 0 : warp;
+    const uint32_t sub_x = tile_x * RS_TILE + (cw & 1) * 8;
+    const uint32_t sub_y = tile_y * RS_TILE + (cw >> 1) * 4;
+    const uint32_t j = sub_x + (lane & 7);
+    const uint32_t i = sub_y + (lane >> 3);
+    const float px = (float)j + 0.5f;
+    const float py = (float)i + 0.5f;
+    const bool inside = !producer && (i < (uint32_t)a.image_height && j < (uint32_t)a.image_width);
+    const size_t img_pix = (size_t)image_id * a.image_height * a.image_width;
+    const size_t pix_id =
+        img_pix + min((size_t)i * a.image_width + j, (size_t)a.image_width * a.image_height - 1);
+
+    const int64_t n_isects = a.n_isects_dev != nullptr ? min((int64_t)*a.n_isects_dev, a.n_isects) : a.n_isects;
+    const int32_t *offs = a.tile_offsets + (size_t)image_id * tiles_per_image;
+    const int32_t range_start = offs[tile_id];
+    const int32_t range_end = (image_id == (uint32_t)a.I - 1 && tile_id == tiles_per_image - 1)
+                                  ? (int32_t)n_isects
+                                  : offs[tile_id + 1];
+    const int num_batches = (range_end - range_start + BWD_BATCH - 1) / BWD_BATCH;
+
+    const int32_t bin_final = inside ? a.last_ids[pix_id] : 0;
+    int32_t warp_bin_final = bin_final;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        warp_bin_final = max(warp_bin_final, __shfl_xor_sync(0xffffffffu, warp_bin_final, o));
+    const bool inside_any = __any_sync(0xffffffffu, inside);
+
+    if (tr == 0) {
+        for (int s = 0; s < BWD_STAGES; ++s) {
+            rs_mbar_init(&full_bar[s], 32);             // the 32 producer lanes
+            rs_mbar_init(&empty_bar[s], BWD_CONSUMERS); // one arrival per compositing warp
+        }
+        tile_bin_final = range_start - 1;
+    }
+    __syncthreads();
+    if (lane == 0 && inside_any)
+        atomicMax(&tile_bin_final, warp_bin_final);
+    __syncthreads(); // the last block-wide barrier of the kernel
+    // Splats behind the furthest-back contributor of the whole TILE were never blended by any of its pixels: their
+    // batches are not even loaded.
+    const int first_batch = max(0, (range_end - 1 - tile_bin_final) / BWD_BATCH);
+
+    if (producer) {
+        // slot t of batch bb holds list entry range_end - 1 - BWD_BATCH * bb - t (slot 0 = furthest back, Bwd.cu:132-150)
+        const float4 *records = reinterpret_cast<const float4 *>(a.records);
+        const bool vec = ch_cnt == CP && (a.channels & 3) == 0 && (ch_off & 3) == 0 &&
+                         (reinterpret_cast<uintptr_t>(a.colors) & 15) == 0;
+        constexpr int PER_LANE = BWD_BATCH / 32;
+        int32_t gid[PER_LANE], gnx[PER_LANE]; // flatten ids of batch bb and bb + 1 (fetched two batches ahead)
+#pragma unroll
+        for (int k = 0; k < PER_LANE; ++k) {
+            const int32_t idx = range_end - 1 - BWD_BATCH * first_batch - (k * 32 + lane);
+            gid[k] = (first_batch < num_batches && idx >= range_start) ? a.flatten_ids[idx] : -1;
+            gnx[k] = (first_batch + 1 < num_batches && idx - BWD_BATCH >= range_start) ? a.flatten_ids[idx - BWD_BATCH] : -1;
+        }
+        for (int bb = first_batch; bb < num_batches; ++bb) {
+            const int it = bb - first_batch;
+            const int st = it % BWD_STAGES;
+            const unsigned ph = (unsigned)(it / BWD_STAGES) & 1u;
+            while (!rs_mbar_try_wait(&empty_bar[st], ph ^ 1u)) { // released by all consumers (free at first use)
+            }
+            float *base = ring + (size_t)st * Cfg::STAGE_FLOATS;
+#pragma unroll
+            for (int k = 0; k < PER_LANE; ++k) {
+                const int32_t g = gid[k];
+                if (g >= 0) {
+                    const int t = k * 32 + lane;
+                    rs_cp_async16(reinterpret_cast<float4 *>(base) + t, records + (size_t)g * 2);
+                    rs_cp_async16(reinterpret_cast<float4 *>(base + BWD_BATCH * 4) + t, records + (size_t)g * 2 + 1);
+                    float *col = base + BWD_BATCH * 8 + t * CP;
+                    const int32_t gc = a.attr_mod_colors > 0 ? g % a.attr_mod_colors : g;
+                    const float *cp = a.colors + (size_t)gc * a.channels + ch_off;
+                    if (vec) {
+#pragma unroll
+                        for (int c = 0; c < CP; c += 4)
+                            rs_cp_async16(col + c, cp + c);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < CDIM; ++c)
+                            if (c < ch_cnt)
+                                rs_cp_async4(col + c, cp + c);
+                    }
+                    // the id travels the same way as the rows it names (no plain store to order against the barrier)
+                    rs_cp_async4(base + BWD_BATCH * (8 + CP) + t, a.flatten_ids + (range_end - 1 - BWD_BATCH * bb - t));
+                }
+            }
+            rs_cp_async_mbar_arrive(&full_bar[st]); // arrives once this lane's copies have landed
+#pragma unroll
+            for (int k = 0; k < PER_LANE; ++k) {
+                gid[k] = gnx[k];
+                const int32_t idx = range_end - 1 - BWD_BATCH * (bb + 2) - (k * 32 + lane);
+                gnx[k] = (bb + 2 < num_batches && idx >= range_start) ? a.flatten_ids[idx] : -1;
+            }
+        }
+        rs_cp_async_wait_all(); // nothing may still be landing in shared memory when the CTA retires
+        return;
+    }
+
+    // -------------------------------------------------------------------------------------------------------------------
+    // compositing warps
+    // -------------------------------------------------------------------------------------------------------------------
+    const float bx0 = (float)sub_x + 0.5f, bx1 = (float)sub_x + 7.5f;
+    const float by0 = (float)sub_y + 0.5f, by1 = (float)sub_y + 3.5f;
+
+    const float T_final = 1.0f - a.render_alphas[pix_id];
+    float T = T_final;
+    float buffer[CDIM];
+    float v_render_c[CDIM];
+#pragma unroll
+    for (int k = 0; k < CDIM; ++k) {
+        buffer[k] = 0.f;
+        v_render_c[k] = (k < ch_cnt) ? b.v_render_colors[pix_id * a.channels + ch_off + k] : 0.f;
+    }
+    const float v_render_a = first_chunk ? b.v_render_alphas[pix_id] : 0.f; // enters with the first channel chunk only
+
+    float bg_dot = 0.f; // sum_k bg_k * v_render_c_k  (Bwd.cu:210-217)
+    if (a.backgrounds != nullptr) {
+        const float *bg = a.backgrounds + (size_t)image_id * a.channels + ch_off;
+#pragma unroll
+        for (int k = 0; k < CDIM; ++k)
+            if (k < ch_cnt)
+                bg_dot += bg[k] * v_render_c[k];
+    }
+
+    // which reduced components this lane will own, and where they go
+    constexpr int OWN = fold_final_n(NV);
+    int own_real;
+    const int own0 = fold_owner<NV>(lane, own_real);
+    float *own_base[OWN];
+    int own_stride[OWN];
+    int own_kind[OWN]; // 0 = geometry (indexed by flatten id), 1 = colour row, 2 = opacity row
+#pragma unroll
+    for (int q = 0; q < OWN; ++q) {
+        const int own = own0 + q;
+        own_base[q] = nullptr;
+        own_stride[q] = 0;
+        own_kind[q] = 0;
+        if (q < own_real) {
+            if (own < CDIM) {
+                if (own < ch_cnt) {
+                    own_base[q] = b.v_colors + ch_off + own;
+                    own_stride[q] = a.channels;
+                    own_kind[q] = 1;
+                }
+            } else if (own < CDIM + 3) {
+                own_base[q] = b.v_conics + (own - CDIM);
+                own_stride[q] = 3;
+            } else if (own < CDIM + 5) {
+                own_base[q] = b.v_means2d + (own - CDIM - 3);
+                own_stride[q] = 2;
+            } else if (own < CDIM + 6) {
+                own_base[q] = b.v_opacities;
+                own_stride[q] = 1;
+                own_kind[q] = 2;
+            } else if (ABS) {
+                own_base[q] = b.v_means2d_abs + (own - CDIM - 6);
+                own_stride[q] = 2;
+            }
+        }
+    }
+
+    const unsigned smem_base = rs_smem_addr(ring);
+    for (int bb = first_batch; bb < num_batches; ++bb) {
+        const int it = bb - first_batch;
+        const int st = it % BWD_STAGES;
+        const unsigned ph = (unsigned)(it / BWD_STAGES) & 1u;
+        while (!rs_mbar_try_wait(&full_bar[st], ph)) {
+        }
+        const int32_t batch_end = range_end - 1 - BWD_BATCH * bb;
+        const int32_t batch_size = min(BWD_BATCH, batch_end + 1 - range_start);
+        unsigned a_r0 = smem_base + (unsigned)(st * Cfg::STAGE_FLOATS * 4);
+        asm volatile("mov.u32 %0, %0;\n" : "+r"(a_r0)); // opaque: keep it in a register
+        const unsigned a_r1 = a_r0 + BWD_BATCH * 16;
+        const unsigned a_col = a_r0 + BWD_BATCH * 32;
+        const unsigned a_id = a_col + BWD_BATCH * CP * 4;
+
+        const int t_begin = max(0, batch_end - warp_bin_final);
+        for (int chunk = (t_begin & ~31); chunk < batch_size; chunk += 32) {
+            const int t = chunk + lane;
+            bool hit = false;
+            if (t >= t_begin && t < batch_size) {
+                const float4 g0 = rs_lds128(a_r0 + t * 16);
+                const float4 g1 = rs_lds128(a_r1 + t * 16);
+                hit = rs_splat_touches_rect(g0.x, g0.y, g0.w, g1.x, g1.y, g1.z, bx0, bx1, by0, by1);
+            }
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            while (m) {
+                const int tt = chunk + __ffs(m) - 1;
+                m &= m - 1;
+                bool valid = inside && (batch_end - tt <= bin_final);
+                float alpha = 0.f, opac = 0.f, vis = 0.f, dx = 0.f, dy = 0.f;
+                float ca = 0.f, cb = 0.f, cc = 0.f;
+                if (valid) {
+                    const float4 g0 = rs_lds128(a_r0 + tt * 16);
+                    const float4 g1 = rs_lds128(a_r1 + tt * 16);
+                    opac = g0.z;
+                    ca = g0.w;
+                    cb = g1.x;
+                    cc = g1.y;
+                    dx = __fsub_rn(g0.x, px);
+                    dy = __fsub_rn(g0.y, py);
+                    const float tc = __fmul_rn(__fmul_rn(cc, dy), dy);
+                    const float s = __fmaf_rn(dx, __fmul_rn(ca, dx), tc);
+                    const float sigma = __fmaf_rn(dy, __fmul_rn(cb, dx), __fmul_rn(s, 0.5f));
+                    vis = __expf(-sigma);
+                    alpha = fminf(0.999f, __fmul_rn(opac, vis));
+                    if (sigma < 0.f || alpha < RS_ALPHA_THRESHOLD)
+                        valid = false;
+                }
+                if (!__any_sync(0xffffffffu, valid))
+                    continue;
+
+                float v[NV];
+#pragma unroll
+                for (int k = 0; k < NV; ++k)
+                    v[k] = 0.f;
+                if (valid) {
+                    const float ra = 1.0f / (1.0f - alpha);
+                    T *= ra;
+                    const float fac = alpha * T;
+                    float v_alpha = 0.f;
+                    const unsigned crow = a_col + tt * (CP * 4);
+#pragma unroll
+                    for (int k4 = 0; k4 < CP; k4 += 4) {
+                        const float4 c4 = rs_lds128(crow + k4 * 4);
+                        const float cs[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int k = k4 + q;
+                            if (k < CDIM && k < ch_cnt) {
+                                const float c = cs[q];
+                                v[k] = fac * v_render_c[k];
+                                v_alpha += (c * T - buffer[k] * ra) * v_render_c[k];
+                                buffer[k] += c * fac;
+                            }
+                        }
+                    }
+                    v_alpha += T_final * ra * v_render_a;
+                    if (a.backgrounds != nullptr)
+                        v_alpha += -T_final * ra * bg_dot;
+                    if (opac * vis <= 0.999f) {
+                        const float v_sigma = -opac * vis * v_alpha;
+                        v[CDIM + 0] = 0.5f * v_sigma * dx * dx;
+                        v[CDIM + 1] = v_sigma * dx * dy;
+                        v[CDIM + 2] = 0.5f * v_sigma * dy * dy;
+                        const float vx = v_sigma * (ca * dx + cb * dy);
+                        const float vy = v_sigma * (cb * dx + cc * dy);
+                        v[CDIM + 3] = vx;
+                        v[CDIM + 4] = vy;
+                        v[CDIM + 5] = vis * v_alpha;
+                        if (ABS) {
+                            v[CDIM + 6] = fabsf(vx);
+                            v[CDIM + 7] = fabsf(vy);
+                        }
+                    }
+                }
+                warp_fold_reduce<NV>(v, lane);
+                const int32_t g = rs_lds32i(a_id + tt * 4);
+#pragma unroll
+                for (int q = 0; q < OWN; ++q) {
+                    if (own_base[q] != nullptr) {
+                        int32_t row = g;
+                        if (own_kind[q] == 1 && a.attr_mod_colors > 0)
+                            row = g % a.attr_mod_colors;
+                        else if (own_kind[q] == 2 && a.attr_mod_opacities > 0)
+                            row = g % a.attr_mod_opacities;
+                        atomicAdd(own_base[q] + (size_t)row * own_stride[q], v[q]);
+                    }
+                }
+            }
+        }
+        __syncwarp(); // every lane is finished with this stage
+        if (lane == 0)
+            rs_mbar_arrive(&empty_bar[st]);
+    }
+}
+
 template <int CDIM>
 static int launch_raster_bwd(const rs_raster_bwd_args &b, int ch_off, int ch_cnt, bool first, cudaStream_t s) {
     const int64_t grid = (int64_t)b.f.I * b.f.tile_width * b.f.tile_height;
@@ -409,6 +732,27 @@ static int launch_raster_bwd(const rs_raster_bwd_args &b, int ch_off, int ch_cnt
             RS_CUDA(cudaFuncSetAttribute(rs_raster_bwd_kernel<CDIM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_bytes));
         rs_dev_mark(attr[abs_grad]);
     }
+#if RS_BWD_RING
+    if (b.f.records != nullptr) { // staged through the ring (records packed by rs_raster_bwd)
+        static RsPerDevice ring_attr[2];
+        const size_t ring_bytes = BwdRingCfg<CDIM>::SMEM;
+        if (ring_bytes > 47 * 1024 && !rs_dev_done(ring_attr[abs_grad])) {
+            if (abs_grad)
+                RS_CUDA(cudaFuncSetAttribute(rs_raster_bwd_ring_kernel<CDIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)ring_bytes));
+            else
+                RS_CUDA(cudaFuncSetAttribute(rs_raster_bwd_ring_kernel<CDIM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)ring_bytes));
+            rs_dev_mark(ring_attr[abs_grad]);
+        }
+        if (abs_grad)
+            rs_raster_bwd_ring_kernel<CDIM, true><<<(unsigned)grid, BWD_THREADS, ring_bytes, s>>>(b, ch_off, ch_cnt, first);
+        else
+            rs_raster_bwd_ring_kernel<CDIM, false><<<(unsigned)grid, BWD_THREADS, ring_bytes, s>>>(b, ch_off, ch_cnt, first);
+        RS_LAUNCH_CHECK("rs_raster_bwd_ring_kernel");
+        return 0;
+    }
+#endif
     if (abs_grad)
         rs_raster_bwd_kernel<CDIM, true><<<(unsigned)grid, RAST_THREADS, acc_bytes, s>>>(b, ch_off, ch_cnt, first);
     else
@@ -431,6 +775,12 @@ extern "C" int rs_raster_bwd(const rs_raster_bwd_args *b, rs_stream_t stream) {
                  b->v_colors && b->v_opacities,
              "rs_raster_bwd: null pointer");
     cudaStream_t s = (cudaStream_t)stream;
+    if (RS_BWD_RING && a.records != nullptr) {
+        RS_CHECK((reinterpret_cast<uintptr_t>(a.records) & 15) == 0, "rs_raster_bwd: records must be 16-byte aligned");
+        if (!a.records_ready)
+            if (int e = rs_raster_pack_records(a, s))
+                return e;
+    }
     for (int off = 0; off < a.channels; off += 32) {
         const int cnt = a.channels - off < 32 ? a.channels - off : 32;
         int e;

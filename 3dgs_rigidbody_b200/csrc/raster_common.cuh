@@ -39,6 +39,18 @@ __device__ __forceinline__ void rs_cp_async_mbar_arrive(uint64_t *bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared.b64 [%0];\n" ::"r"(rs_smem_addr(bar)) : "memory");
 }
 
+// explicit shared-space loads from 32-bit shared addresses (keeps the generic->shared conversion out of the inner loop)
+__device__ __forceinline__ float4 rs_lds128(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int rs_lds32i(unsigned addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(v) : "r"(addr));
+    return v;
+}
+
 #ifdef RS_RASTER_STATS
 __device__ unsigned long long rs_stats[8];
 extern "C" void rs_raster_stats(unsigned long long *out) { // {iterations, with >= 1 passing lane, passing, active, chunks}

@@ -40,12 +40,6 @@ __global__ void __launch_bounds__(256) rs_raster_pack_kernel(const rs_raster_fwd
     rec[1] = make_float4(cb, cc, rs_cull_limit(ca, cb, cc, op), 0.f);
 }
 
-// explicit shared-space loads from 32-bit shared addresses (keeps the generic->shared conversion out of the inner loop)
-__device__ __forceinline__ float4 rs_lds128(unsigned addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
 
 // CP = colour row pitch in shared memory (floats): CDIM rounded up to a multiple of 4 so rows can be read as float4
 #define RAST_BATCH 256                   // splats per ring stage

@@ -397,7 +397,10 @@ typedef struct {
 int rs_raster_fwd(const rs_raster_fwd_args *a, rs_stream_t stream);
 
 typedef struct {
-    rs_raster_fwd_args f;        /* forward inputs (render_colors unused; render_alphas/last_ids are inputs here) */
+    rs_raster_fwd_args f;        /* forward inputs (render_colors unused; render_alphas/last_ids are inputs here).
+                                  * f.records (+ f.n_rows, f.records_ready) as in rs_raster_fwd: with the scratch the splat
+                                  * batches are staged through a shared-memory ring by a producer warp (the default
+                                  * kernel); with f.records == NULL the barrier-per-batch kernel runs.  Same results. */
     const float *v_render_colors;/* [I,H,W,channels] */
     const float *v_render_alphas;/* [I,H,W,1] */
     float *v_means2d_abs;        /* [I*N,2] optional (absgrad); zero-initialised by the caller */
