@@ -593,6 +593,7 @@ def rasterize_to_pixels_3dgs_bwd(
     absgrad: bool,
     _attr_mod_colors: int = 0,
     _attr_mod_opacities: int = 0,
+    _ring: bool = True,  # False: no record scratch -> the barrier-per-batch kernel (kept for C callers without scratch)
 ) -> Tuple[Optional[Tensor], Tensor, Tensor, Tensor, Tensor]:
     lib = _lib.load()
     dev = means2d.device
@@ -606,8 +607,9 @@ def rasterize_to_pixels_3dgs_bwd(
                      tile_size, tile_offsets, flatten_ids, _attr_mod_colors, _attr_mod_opacities)
         a.f.render_alphas, a.f.last_ids = _ptr(render_alphas), _ptr(last_ids)
         # staging records of the batch ring (32 B per projected splat), packed by rs_raster_bwd itself
-        records = torch.empty((max(a.f.n_rows, 1), 8), dtype=torch.float32, device=dev)
-        a.f.records, a.f.records_ready = records.data_ptr(), 0
+        if _ring:
+            records = torch.empty((max(a.f.n_rows, 1), 8), dtype=torch.float32, device=dev)
+            a.f.records, a.f.records_ready = records.data_ptr(), 0
         v_means2d = torch.zeros_like(means2d)
         v_conics = torch.zeros_like(conics)
         v_colors = torch.zeros_like(colors)

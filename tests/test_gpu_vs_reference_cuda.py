@@ -214,6 +214,28 @@ def _worse_than_reference(ours, theirs, exact, slack=2.0):
                                    ref_l2=float(e_t.norm()), scale=float(exact.abs().max()))
 
 
+@pytest.mark.parametrize("D,absgrad", [(3, True), (16, False), (20, False)])
+def test_raster_bwd_ring_kernel_equals_barrier_kernel(rs, ref, D, absgrad):
+    """The two compositing-backward kernels of the library (batch ring with a producer warp; one barrier per batch for
+    callers without record scratch) compute the same per-warp sums; only the order of the float atomics between warps
+    differs."""
+    W, H, C = 200, 160, 2
+    means2d, conics, colors, opac, off, flat = _raster_inputs(rs, ref, 8, 20_000, W, H, C, D)
+    a = (means2d, conics, colors, opac, None, None, W, H, 16, off, flat)
+    rc, ra, li = rs._C.rasterize_to_pixels_3dgs_fwd(*a)
+    g = torch.Generator(device=DEV).manual_seed(4)
+    v_rc = torch.randn(rc.shape, device=DEV, generator=g)
+    v_ra = torch.randn(ra.shape, device=DEV, generator=g)
+    ring = rs._C.rasterize_to_pixels_3dgs_bwd(*a, ra, li, v_rc, v_ra, absgrad)
+    plain = rs._C.rasterize_to_pixels_3dgs_bwd(*a, ra, li, v_rc, v_ra, absgrad, _ring=False)
+    for x, y in zip(ring, plain):
+        if x is None:
+            assert y is None
+            continue
+        scale = float(y.abs().max())
+        assert scale > 0 and float((x - y).abs().max()) <= 2e-5 * scale
+
+
 @pytest.mark.parametrize("D,absgrad", [(3, True), (16, False)])
 def test_raster_bwd_matches_reference_cuda(rs, ref, orc, D, absgrad):
     W, H, C = 200, 160, 2
