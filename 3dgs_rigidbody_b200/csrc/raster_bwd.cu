@@ -416,7 +416,13 @@ rs_raster_bwd_kernel(const rs_raster_bwd_args b, const int ch_off, const int ch_
 template <int CDIM> struct BwdRingCfg {
     static constexpr int CP = (CDIM + 3) & ~3;
     static constexpr int STAGE_FLOATS = BWD_BATCH * (8 + CP + 1); // records (2 x float4), colour row, flatten id
-    static constexpr size_t SMEM = (size_t)BWD_STAGES * STAGE_FLOATS * sizeof(float);
+    // Wide colour rows: the per-pixel cotangent v_render_colors[CDIM] lives in shared memory ([CP/4][256 pixels] float4,
+    // conflict-free LDS.128, each lane reads only what it wrote) instead of CDIM registers -- with it, buffer[CDIM] and
+    // the NV-wide reduction vector the 16-channel kernel spilled 124 bytes per thread at 72 registers, and ncu showed the
+    // spill reloads as the top stall (long scoreboard 2.6 warps per issue slot).
+    static constexpr bool VRC_SMEM = CDIM > 8;
+    static constexpr int VRC_FLOATS = VRC_SMEM ? CP * 32 * BWD_CONSUMERS : 0;
+    static constexpr size_t SMEM = ((size_t)BWD_STAGES * STAGE_FLOATS + VRC_FLOATS) * sizeof(float);
 };
 
 template <int CDIM, bool ABS>
@@ -548,22 +554,37 @@ rs_raster_bwd_ring_kernel(const rs_raster_bwd_args b, const int ch_off, const in
     const float T_final = 1.0f - a.render_alphas[pix_id];
     float T = T_final;
     float buffer[CDIM];
-    float v_render_c[CDIM];
+    constexpr bool VRC_SMEM = Cfg::VRC_SMEM;
+    float v_render_c[VRC_SMEM ? 1 : CDIM];
+    const unsigned smem_base = rs_smem_addr(ring);
+    // (VRC_SMEM) this pixel's cotangent: float4 number k4 at [k4][tr]; written and read by this lane only
+    const unsigned a_vrc = smem_base + (unsigned)(BWD_STAGES * Cfg::STAGE_FLOATS * 4) + (unsigned)tr * 16u;
+    float bg_dot = 0.f; // sum_k bg_k * v_render_c_k  (Bwd.cu:210-217)
+    {
+        const float *bg = a.backgrounds != nullptr ? a.backgrounds + (size_t)image_id * a.channels + ch_off : nullptr;
+        const float *vr = b.v_render_colors + pix_id * a.channels + ch_off;
 #pragma unroll
-    for (int k = 0; k < CDIM; ++k) {
-        buffer[k] = 0.f;
-        v_render_c[k] = (k < ch_cnt) ? b.v_render_colors[pix_id * a.channels + ch_off + k] : 0.f;
+        for (int k4 = 0; k4 < CP; k4 += 4) {
+            float vv[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int k = k4 + q;
+                vv[q] = (k < CDIM && k < ch_cnt) ? vr[k] : 0.f;
+                if (k < CDIM) {
+                    buffer[k] = 0.f;
+                    if (!VRC_SMEM)
+                        v_render_c[VRC_SMEM ? 0 : k] = vv[q];
+                    if (bg != nullptr && k < ch_cnt)
+                        bg_dot += bg[k] * vv[q];
+                }
+            }
+            if (VRC_SMEM)
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(a_vrc + (unsigned)(k4 / 4) * (BWD_CONSUMERS * 32 * 16)),
+                             "f"(vv[0]), "f"(vv[1]), "f"(vv[2]), "f"(vv[3])
+                             : "memory");
+        }
     }
     const float v_render_a = first_chunk ? b.v_render_alphas[pix_id] : 0.f; // enters with the first channel chunk only
-
-    float bg_dot = 0.f; // sum_k bg_k * v_render_c_k  (Bwd.cu:210-217)
-    if (a.backgrounds != nullptr) {
-        const float *bg = a.backgrounds + (size_t)image_id * a.channels + ch_off;
-#pragma unroll
-        for (int k = 0; k < CDIM; ++k)
-            if (k < ch_cnt)
-                bg_dot += bg[k] * v_render_c[k];
-    }
 
     // which reduced components this lane will own, and where they go
     constexpr int OWN = fold_final_n(NV);
@@ -602,7 +623,6 @@ rs_raster_bwd_ring_kernel(const rs_raster_bwd_args b, const int ch_off, const in
         }
     }
 
-    const unsigned smem_base = rs_smem_addr(ring);
     for (int bb = first_batch; bb < num_batches; ++bb) {
         const int it = bb - first_batch;
         const int st = it % BWD_STAGES;
@@ -667,13 +687,19 @@ rs_raster_bwd_ring_kernel(const rs_raster_bwd_args b, const int ch_off, const in
                     for (int k4 = 0; k4 < CP; k4 += 4) {
                         const float4 c4 = rs_lds128(crow + k4 * 4);
                         const float cs[4] = {c4.x, c4.y, c4.z, c4.w};
+                        float vs[4] = {0.f, 0.f, 0.f, 0.f};
+                        if (VRC_SMEM) {
+                            const float4 v4 = rs_lds128(a_vrc + (unsigned)(k4 / 4) * (BWD_CONSUMERS * 32 * 16));
+                            vs[0] = v4.x, vs[1] = v4.y, vs[2] = v4.z, vs[3] = v4.w;
+                        }
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             const int k = k4 + q;
                             if (k < CDIM && k < ch_cnt) {
                                 const float c = cs[q];
-                                v[k] = fac * v_render_c[k];
-                                v_alpha += (c * T - buffer[k] * ra) * v_render_c[k];
+                                const float vr = VRC_SMEM ? vs[q] : v_render_c[VRC_SMEM ? 0 : k];
+                                v[k] = fac * vr;
+                                v_alpha += (c * T - buffer[k] * ra) * vr;
                                 buffer[k] += c * fac;
                             }
                         }

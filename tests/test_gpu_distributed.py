@@ -271,6 +271,15 @@ def _syncfree_worker(rank, world, port, q):
                                                       body_centers=t["body_centers"])
             assert info["rows"] == meta["gaussian_ids"].numel() and info["n_isects"] == meta["flatten_ids"].numel(), (frame, info)
             assert torch.equal(got_img, want) and torch.equal(got_alpha, want_a), frame
+        # an intersection workspace that is too small is reported by check() -- on every rank -- and re-sized; the frame
+        # rendered again is the right one
+        fr._alloc_render(fr._alloc_rows, 1024)
+        fr.render(vm[mine], Ks[mine], t["body_quats"], bt)
+        info = fr.check()
+        assert info["regrow"] and fr.max_isects >= info["n_isects"] > 1024, info
+        img2, alpha2 = fr.render(vm[mine], Ks[mine], t["body_quats"], bt)
+        assert not fr.check()["regrow"]
+        assert torch.equal(img2, want) and torch.equal(alpha2, want_a)
         q.put((rank, "ok"))
     except Exception:  # pragma: no cover
         import traceback
