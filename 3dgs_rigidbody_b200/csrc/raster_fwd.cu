@@ -45,9 +45,12 @@ __global__ void __launch_bounds__(256) rs_raster_pack_kernel(const rs_raster_fwd
 #define RAST_BATCH 256                   // splats per ring stage
 #define RAST_CONSUMERS 8                 // compositing warps (one 8x4 pixel sub-block each)
 #define RAST_THREADS (32 * (RAST_CONSUMERS + 1)) // + one producer warp
+#ifndef RS_RASTER_3STAGE_MAX_CDIM
+#define RS_RASTER_3STAGE_MAX_CDIM 8 // widest colour row that still gets a 3-stage ring (shared memory per CTA)
+#endif
 template <int CDIM> struct RastCfg {
     static constexpr int CP = (CDIM + 3) & ~3;
-    static constexpr int STAGES = (CDIM <= 8) ? 3 : 2;
+    static constexpr int STAGES = (CDIM <= RS_RASTER_3STAGE_MAX_CDIM) ? 3 : 2;
     static constexpr int STAGE_FLOATS = RAST_BATCH * (8 + CP);
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_FLOATS * sizeof(float);
 };

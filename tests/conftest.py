@@ -64,6 +64,9 @@ def refpy(rs):
             mod.install()
         except FileNotFoundError:
             pytest.skip("baseline/_ref not installed (needs /root/reference at build time)")
+    # make `gsplat` importable right away (our operator module stands in for its extension; tests that want the
+    # reference's own kernels call set_backend(ref)): reference_functions() needs gsplat.utils whatever test runs first
+    mod.load_reference(rs._C)
     return mod
 
 
