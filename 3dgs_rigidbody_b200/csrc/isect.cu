@@ -5,9 +5,13 @@
 // write all tiles of a Gaussian (serial double loop, IntersectTile.cu:102-113).  Here:
 //   count  : 1 thread / element, writes tiles_per_gauss and one partial sum per 1024-element block
 //   scan   : one CTA turns the block sums into exclusive offsets and the device-side total (no host sync needed)
-//   emit   : a CTA re-scans its 1024 counts in shared memory and its 256 threads write the block's intersections
-//            cooperatively: output slot j finds its owner by binary search, so stores are fully coalesced and a
-//            Gaussian that covers thousands of tiles is spread over the whole CTA.
+//   emit   : (operator path, unsorted 64-bit keys) a CTA re-scans its 1024 counts in shared memory and its 256 threads
+//            write the block's intersections cooperatively: output slot j finds its owner by binary search, so stores
+//            are fully coalesced and a Gaussian that covers thousands of tiles is spread over the whole CTA.
+//   sorted : (frame path and intersect_tile(sort=True)) rs_isect_sorted further down -- depth order of the elements
+//            (depth_order.cu), emission of 32-bit (image | tile) keys in that order through a shared-memory window
+//            (rs_bin_emit_kernel; optionally only the tiles of the projection's tile footprints), two stable radix
+//            passes on the tile bits (sort.cu), offsets.
 // All of it is HBM-bound integer work: 20 B read per element + 12 B written per intersection.
 #include "common.cuh"
 #include "sort_ws.cuh"

@@ -5,7 +5,7 @@ Compiles the reference's own CUDA extension *from the sources where they lie* un
 with the flags the reference's loader uses (gsplat/cuda/_backend.py:176-185: ``-O3 -use_fast_math``,
 arch autodetected -> sm_100 on a B200).  The resulting pybind module exposes the reference `_C` ops
 (gsplat/cuda/ext.cpp:6-104); `tests/` load it on the GPU box to compare our kernels against the
-reference's kernels on identical inputs, and `bench.py --ref-cuda` times it as "the kernel to beat".
+reference's kernels on identical inputs, and `bench.py` times it in its `ref_cuda` leg as "the kernel to beat".
 
 oracle/_ref/ is git-ignored but travels to the GPU box with the gpurun snapshot.
 Only runs where /root/reference exists (the build container); on the GPU box the prebuilt .so is used.
