@@ -450,7 +450,8 @@ def test_frame_renderer_matches_compat_path(rs, orc):
     assert torch.equal(img_3, img_f)
 
 
-@pytest.mark.parametrize("case", ["small_splats", "large_anisotropic", "low_opacity", "general_kernel", "c2_full_size"])
+@pytest.mark.parametrize("case", ["small_splats", "large_anisotropic", "low_opacity", "general_kernel", "huge_splats",
+                                  "c2_full_size"])
 def test_tight_tile_lists_give_the_same_image(rs, case):
     """FrameRenderer(tight_tiles=True) lists a (tile, splat) pair only where the splat can reach alpha >= 1/255 inside the
     tile; every dropped pair is one the compositing of RasterizeToPixels3DGSFwd.cu:148-149 skips at every pixel, so the float
@@ -468,8 +469,10 @@ def test_tight_tile_lists_give_the_same_image(rs, case):
     else:
         W, H, C = 400, 300, 2
         kw = dict(small_splats=dict(s_max=0.03), large_anisotropic=dict(s_max=0.5, spread=1.5),
-                  low_opacity=dict(s_max=0.15), general_kernel=dict(s_max=0.08))[case]
-        s = synthetic_scene(21, 40_000, K=4, **kw)
+                  low_opacity=dict(s_max=0.15), general_kernel=dict(s_max=0.08), huge_splats=dict(s_max=3.0))[case]
+        # huge_splats: every rectangle has far more than 64 tiles (kept whole) and a CTA of the emission meets more such
+        # elements than its whole-CTA list holds (256), so the per-thread rectangle walk of the masked kernel runs too
+        s = synthetic_scene(21, 6_000 if case == "huge_splats" else 40_000, K=4, **kw)
         if case == "large_anisotropic":  # needles: one long axis
             s["scales"][:, 1:] *= 0.04
         if case == "low_opacity":  # many splats near the 1/255 threshold
@@ -485,7 +488,8 @@ def test_tight_tile_lists_give_the_same_image(rs, case):
         ids, centers, bq, bt = T(s["cluster_ids"]), T(s["body_centers"]), T(s["body_quats"]), T(s["body_trans"])
     out = {}
     for tight in (False, True):
-        fr = rs.FrameRenderer(*scene, W, H, cluster_ids=ids, body_centers=centers, n_cameras=C, rgb8=True, tight_tiles=tight)
+        fr = rs.FrameRenderer(*scene, W, H, cluster_ids=ids, body_centers=centers, n_cameras=C, rgb8=True, tight_tiles=tight,
+                              max_isects=(8 << 20) if case == "huge_splats" else None)
         img, alpha = fr.render(vm, Ks, bq, bt)
         torch.cuda.synchronize()
         assert not fr.overflowed()
@@ -497,7 +501,7 @@ def test_tight_tile_lists_give_the_same_image(rs, case):
     assert torch.equal(ref_l[0], tight_l[0]) and torch.equal(ref_l[1], tight_l[1]) and torch.equal(ref_l[2], tight_l[2])
     assert float(ref_l[1].mean()) > 0.01
     assert tight_l[3] <= ref_l[3]
-    if case != "low_opacity":
+    if case not in ("low_opacity", "huge_splats"):
         assert tight_l[3] < ref_l[3], "the test scene does not exercise the culling"
     # subset in the same order: the tight list is the reference list with some entries removed
     keys_ref = ref_l[6]
