@@ -9,18 +9,14 @@
 //     the 5 steps a lane keeps one half of its values and trades the other half, so the whole vector costs ~NV shuffles
 //     instead of 5*NV, and the totals end up spread over NV lanes which then issue ONE predicated red.global each.
 //   * per-lane destination pointers (which output array / component a lane ends up owning) are computed once per thread.
-//   * (experiment, off by default: -DRS_BWD_SMEM_REDUCE=1) CTA-level reduction: the owning lanes add into a shared-memory
-//     accumulator [256 splats][NV] and the CTA flushes ONE red.global per (tile, splat, component) per batch.  Measured
-//     SLOWER -- 1.63 ms vs 1.03 ms at c3 (profiles/r02_raster_bwd_smem_reduce_experiment.txt): float atomicAdd on shared
-//     memory is a compare-and-swap loop that spins when the eight warps of a tile hit the same words, while red.global is
-//     a fire-and-forget L2 operation.
+//   * a CTA-level reduction through a shared-memory accumulator (one red.global per (tile, splat, component)) was built
+//     and measured SLOWER -- 1.63 ms vs 1.03 ms at c3 (profiles/r02_raster_bwd_smem_reduce_experiment.txt): float atomicAdd
+//     on shared memory is a compare-and-swap loop that spins when the eight warps of a tile hit the same words, while
+//     red.global is a fire-and-forget L2 operation.  The variant was removed again.
 // Per-pixel math follows RasterizeToPixels3DGSBwd.cu:160-242.
 #include "raster_common.cuh"
 
 #define RAST_THREADS 256
-#ifndef RS_BWD_SMEM_REDUCE
-#define RS_BWD_SMEM_REDUCE 0
-#endif
 
 int rs_check_raster_args(const rs_raster_fwd_args *a, const char *who);
 
@@ -85,10 +81,7 @@ template <int CDIM, bool ABS>
 __global__ void __launch_bounds__(RAST_THREADS, (CDIM <= 16) ? 3 : 2)
 rs_raster_bwd_kernel(const rs_raster_bwd_args b, const int ch_off, const int ch_cnt, const bool first_chunk) {
     constexpr int NV = CDIM + 6 + (ABS ? 2 : 0);
-    constexpr int NVP = NV | 1; // odd pitch of the per-splat accumulator rows
     __shared__ RastBwdSmem<CDIM> sm;
-    extern __shared__ __align__(16) float bwd_acc[]; // [RAST_THREADS][NVP] (RS_BWD_SMEM_REDUCE)
-    __shared__ unsigned int touched[RAST_THREADS / 32];
     const rs_raster_fwd_args &a = b.f;
 
     const uint32_t tiles_per_image = (uint32_t)(a.tile_width * a.tile_height);
@@ -193,55 +186,12 @@ rs_raster_bwd_kernel(const rs_raster_bwd_args b, const int ch_off, const int ch_
     __shared__ int tile_bin_final;
     if (tr == 0)
         tile_bin_final = range_start - 1;
-#if RS_BWD_SMEM_REDUCE
-#pragma unroll
-    for (int k = 0; k < NVP; ++k)
-        bwd_acc[tr * NVP + k] = 0.f;
-    if (tr < RAST_THREADS / 32)
-        touched[tr] = 0u;
-#endif
     __syncthreads();
     if (lane == 0 && inside_any)
         atomicMax(&tile_bin_final, warp_bin_final);
     __syncthreads();
     const int first_batch = max(0, (range_end - 1 - tile_bin_final) / RAST_THREADS);
 
-    // flush of the CTA-level accumulator: thread t owns splat slot t of the batch that was just processed
-    auto flush = [&]() {
-#if RS_BWD_SMEM_REDUCE
-        if ((touched[tr >> 5] >> (tr & 31)) & 1u) {
-            const int32_t g = sm.id[tr];
-            const int32_t gc = a.attr_mod_colors > 0 ? g % a.attr_mod_colors : g;
-            const int32_t go = a.attr_mod_opacities > 0 ? g % a.attr_mod_opacities : g;
-            float *acc = bwd_acc + tr * NVP;
-#pragma unroll
-            for (int k = 0; k < CDIM; ++k)
-                if (k < ch_cnt) {
-                    atomicAdd(b.v_colors + (size_t)gc * a.channels + ch_off + k, acc[k]);
-                    acc[k] = 0.f;
-                }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                atomicAdd(b.v_conics + (size_t)g * 3 + k, acc[CDIM + k]);
-                acc[CDIM + k] = 0.f;
-            }
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                atomicAdd(b.v_means2d + (size_t)g * 2 + k, acc[CDIM + 3 + k]);
-                acc[CDIM + 3 + k] = 0.f;
-                if (ABS) {
-                    atomicAdd(b.v_means2d_abs + (size_t)g * 2 + k, acc[CDIM + 6 + k]);
-                    acc[CDIM + 6 + k] = 0.f;
-                }
-            }
-            atomicAdd(b.v_opacities + go, acc[CDIM + 5]);
-            acc[CDIM + 5] = 0.f;
-        }
-        __syncwarp();
-        if ((tr & 31) == 0)
-            touched[tr >> 5] = 0u;
-#endif
-    };
 
     // The id of this thread's splat in the NEXT batch is fetched one batch ahead and its rows are requested into L2, so a
     // batch change costs one exposed L2 round trip instead of two dependent DRAM round trips (flatten id -> attributes).
@@ -262,9 +212,7 @@ rs_raster_bwd_kernel(const rs_raster_bwd_args b, const int ch_off, const int ch_
     };
     int32_t g_next = fetch_id(first_batch);
     for (int bb = first_batch; bb < num_batches; ++bb) {
-        __syncthreads();
-        if (bb > first_batch)
-            flush(); // the previous batch (reads its sm.id[tr] before the load below replaces it)
+        __syncthreads(); // every warp is finished with the previous batch
         // slot 0 of a batch is its furthest-back splat (Bwd.cu:132-150)
         const int32_t batch_end = range_end - 1 - RAST_THREADS * bb;
         const int32_t batch_size = min(RAST_THREADS, batch_end + 1 - range_start);
@@ -365,14 +313,6 @@ rs_raster_bwd_kernel(const rs_raster_bwd_args b, const int ch_off, const int ch_
                     }
                 }
                 warp_fold_reduce<NV>(v, lane);
-#if RS_BWD_SMEM_REDUCE
-#pragma unroll
-                for (int q = 0; q < OWN; ++q)
-                    if (q < own_real)
-                        atomicAdd(bwd_acc + tt * NVP + own0 + q, v[q]);
-                if (lane == 0)
-                    atomicOr(&touched[tt >> 5], 1u << (tt & 31));
-#else
                 const int32_t g = sm.id[tt];
 #pragma unroll
                 for (int q = 0; q < OWN; ++q) {
@@ -385,13 +325,8 @@ rs_raster_bwd_kernel(const rs_raster_bwd_args b, const int ch_off, const int ch_
                         atomicAdd(own_base[q] + (size_t)row * own_stride[q], v[q]);
                     }
                 }
-#endif
             }
         }
-    }
-    if (num_batches > first_batch) {
-        __syncthreads();
-        flush();
     }
 }
 
@@ -748,16 +683,6 @@ template <int CDIM>
 static int launch_raster_bwd(const rs_raster_bwd_args &b, int ch_off, int ch_cnt, bool first, cudaStream_t s) {
     const int64_t grid = (int64_t)b.f.I * b.f.tile_width * b.f.tile_height;
     const bool abs_grad = b.v_means2d_abs != nullptr;
-    const int nv = CDIM + 6 + (abs_grad ? 2 : 0);
-    const size_t acc_bytes = RS_BWD_SMEM_REDUCE ? (size_t)RAST_THREADS * (nv | 1) * sizeof(float) : 0;
-    static RsPerDevice attr[2];
-    if (acc_bytes + sizeof(RastBwdSmem<CDIM>) > 47 * 1024 && !rs_dev_done(attr[abs_grad])) {
-        if (abs_grad)
-            RS_CUDA(cudaFuncSetAttribute(rs_raster_bwd_kernel<CDIM, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_bytes));
-        else
-            RS_CUDA(cudaFuncSetAttribute(rs_raster_bwd_kernel<CDIM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)acc_bytes));
-        rs_dev_mark(attr[abs_grad]);
-    }
 #if RS_BWD_RING
     if (b.f.records != nullptr) { // staged through the ring (records packed by rs_raster_bwd)
         static RsPerDevice ring_attr[2];
@@ -780,9 +705,9 @@ static int launch_raster_bwd(const rs_raster_bwd_args &b, int ch_off, int ch_cnt
     }
 #endif
     if (abs_grad)
-        rs_raster_bwd_kernel<CDIM, true><<<(unsigned)grid, RAST_THREADS, acc_bytes, s>>>(b, ch_off, ch_cnt, first);
+        rs_raster_bwd_kernel<CDIM, true><<<(unsigned)grid, RAST_THREADS, 0, s>>>(b, ch_off, ch_cnt, first);
     else
-        rs_raster_bwd_kernel<CDIM, false><<<(unsigned)grid, RAST_THREADS, acc_bytes, s>>>(b, ch_off, ch_cnt, first);
+        rs_raster_bwd_kernel<CDIM, false><<<(unsigned)grid, RAST_THREADS, 0, s>>>(b, ch_off, ch_cnt, first);
     RS_LAUNCH_CHECK("rs_raster_bwd_kernel");
     return 0;
 }
