@@ -42,6 +42,56 @@ __global__ void __launch_bounds__(RS_ISECT_THREADS) rs_isect_count_kernel(const 
         a.block_sums[blockIdx.x] = s;
 }
 
+// Tile counts + tile footprints of operator-level rows in one pass (rs_isect_footprints): what the projection kernel
+// writes for the frame path (rs_project_fwd_args.tile_footprints), for rows that come from somewhere else -- the receive
+// arrays of the splat exchange.  With conics + opacities the masks are tight (only tiles where the splat can reach
+// alpha >= 1/255), without them every tile of the bounding rectangle is listed (exactly the reference's lists).
+__global__ void __launch_bounds__(RS_ISECT_THREADS)
+rs_isect_footprints_kernel(const rs_isect_args a, const float *__restrict__ conics, const float *__restrict__ opacities,
+                           uint4 *__restrict__ footprints) {
+    __shared__ RsFootWarp foot[RS_ISECT_THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * RS_ISECT_BLOCK;
+#pragma unroll 1
+    for (int it = 0; it < RS_ISECT_BLOCK / RS_ISECT_THREADS; ++it) { // (uniform trip count: the warp version syncs)
+        const int64_t idx = base + it * RS_ISECT_THREADS + threadIdx.x;
+        const bool in = idx < a.n_elems;
+        int2 r = make_int2(0, 0);
+        float2 m = make_float2(0.f, 0.f);
+        if (in) {
+            r = reinterpret_cast<const int2 *>(a.radii)[idx];
+            if (r.x > 0 && r.y > 0)
+                m = reinterpret_cast<const float2 *>(a.means2d)[idx];
+        }
+        const bool vis = in && r.x > 0 && r.y > 0;
+        uint4 fp = make_uint4(0u, 0u, 0u, 0u);
+        int cnt = 0;
+        if (conics != nullptr) {
+            float ca = 0.f, cb = 0.f, cc = 0.f, op = 0.f;
+            if (vis) {
+                ca = conics[idx * 3 + 0];
+                cb = conics[idx * 3 + 1];
+                cc = conics[idx * 3 + 2];
+                op = opacities[idx];
+            }
+            cnt = rs_tile_footprint_warp(vis, m.x, m.y, r.x, r.y, ca, cb, cc, op, (uint32_t)a.tile_size,
+                                         (uint32_t)a.tile_width, (uint32_t)a.tile_height, fp, foot[threadIdx.x >> 5]);
+        } else if (vis) {
+            const RsTileRect tr = rs_tile_rect(m.x, m.y, (float)r.x, (float)r.y, (uint32_t)a.tile_size,
+                                               (uint32_t)a.tile_width, (uint32_t)a.tile_height);
+            const uint32_t w = tr.x1 - tr.x0, h = tr.y1 - tr.y0, n = w * h;
+            cnt = (int)n;
+            if (n > 0u) {
+                const unsigned long long mask = n >= 64u ? ~0ull : ((1ull << n) - 1ull);
+                fp = make_uint4((uint32_t)mask, (uint32_t)(mask >> 32), tr.x0 | (tr.y0 << 16), w | (h << 16));
+            }
+        }
+        if (in) {
+            a.tiles_per_gauss[idx] = cnt;
+            footprints[idx] = fp;
+        }
+    }
+}
+
 // Exclusive scan of `nb` block sums (in place) by a single CTA; block_sums[nb] and *n_isects receive the total.
 // nb is small (1M elements -> 977 blocks), so a serial-over-chunks CTA scan is launch-latency bound.
 #define RS_SCAN_THREADS 1024
@@ -324,6 +374,21 @@ extern "C" int rs_isect_count(const rs_isect_args *a, rs_stream_t stream) {
     RS_CHECK(a->means2d && a->radii && a->tiles_per_gauss && a->block_sums, "rs_isect_count: null pointer");
     rs_isect_count_kernel<<<rs_isect_num_blocks(a->n_elems), RS_ISECT_THREADS, 0, (cudaStream_t)stream>>>(*a);
     RS_LAUNCH_CHECK("rs_isect_count_kernel");
+    return 0;
+}
+
+extern "C" int rs_isect_footprints(const rs_isect_args *a, const float *conics, const float *opacities,
+                                   uint32_t *tile_footprints, rs_stream_t stream) {
+    if (int e = check_isect_args(a, "rs_isect_footprints"))
+        return e;
+    if (a->n_elems == 0)
+        return 0;
+    RS_CHECK(a->means2d && a->radii && a->tiles_per_gauss && tile_footprints, "rs_isect_footprints: null pointer");
+    RS_CHECK((conics == nullptr) == (opacities == nullptr), "rs_isect_footprints: conics and opacities go together");
+    RS_CHECK((reinterpret_cast<uintptr_t>(tile_footprints) & 15) == 0, "rs_isect_footprints: tile_footprints must be 16-byte aligned");
+    rs_isect_footprints_kernel<<<rs_isect_num_blocks(a->n_elems), RS_ISECT_THREADS, 0, (cudaStream_t)stream>>>(
+        *a, conics, opacities, reinterpret_cast<uint4 *>(tile_footprints));
+    RS_LAUNCH_CHECK("rs_isect_footprints_kernel");
     return 0;
 }
 

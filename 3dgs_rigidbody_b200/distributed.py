@@ -409,9 +409,12 @@ class ShardedFrameRenderer:
                  height: int, cameras_per_rank: int, group=None, max_isects: Optional[int] = None,
                  row_capacity: Optional[int] = None, cluster_ids: Optional[Tensor] = None,
                  body_centers: Optional[Tensor] = None, near_plane: float = 0.01, far_plane: float = 1e10,
-                 radius_clip: float = 0.0, eps2d: float = 0.3):
+                 radius_clip: float = 0.0, eps2d: float = 0.3, tight_tiles: bool = False):
         self.lib = _lib.load()
         self.group = group
+        # True: a received splat is binned only into the tiles where it can reach alpha >= 1/255 (rs_isect_footprints with
+        # conics + opacities): the same pixels bit for bit from ~20 % fewer intersections.  False: the reference's lists.
+        self.tight_tiles = bool(tight_tiles)
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         dev = means.device
         self.device = dev
@@ -457,6 +460,7 @@ class ShardedFrameRenderer:
         self._alloc_rows, self.max_isects = rows, max_isects
         with torch.cuda.device(dev):
             self.tiles_per_gauss = torch.empty(rows, dtype=torch.int32, device=dev)
+            self.footprints = torch.empty((rows, 4), dtype=torch.int32, device=dev)  # 16 B per row, see rs_isect_footprints
             self.block_sums = torch.empty(self.lib.rs_isect_num_blocks(rows) + 2, dtype=torch.int32, device=dev)
             self.records = torch.empty((rows, 8), dtype=torch.float32, device=dev)
             self.flatten_ids = torch.empty(max_isects, dtype=torch.int32, device=dev)
@@ -554,9 +558,12 @@ class ShardedFrameRenderer:
             ia.tiles_per_gauss, ia.block_sums = self.tiles_per_gauss.data_ptr(), self.block_sums.data_ptr()
             ia.n_isects, ia.overflow = self.status.data_ptr(), self.status.data_ptr() + 4
             ia.isect_ids, ia.flatten_ids, ia.capacity = None, self.flatten_ids.data_ptr(), self.max_isects
-            _lib.check(lib.rs_isect_count(ctypes.byref(ia), stream))
+            # counts + one 16-byte footprint per row: the emission then gathers one record per row instead of three
+            _lib.check(lib.rs_isect_footprints(ctypes.byref(ia), col(2) if self.tight_tiles else None,
+                                               col(3) if self.tight_tiles else None, self.footprints.data_ptr(), stream))
             sa = _lib.rs_isect_sorted_args()
             ctypes.memmove(ctypes.byref(sa.isect), ctypes.byref(ia), ctypes.sizeof(ia))
+            sa.tile_footprints = self.footprints.data_ptr()
             sa.tile_offsets = self.offsets.data_ptr()
             sa.workspace, sa.workspace_bytes = self.bin_ws.data_ptr(), self.bin_ws.numel()
             _lib.check(lib.rs_isect_sorted(ctypes.byref(sa), stream))

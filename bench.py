@@ -739,7 +739,8 @@ def bench_c5(rs, torch, dist, dev, rank, world, n_total=20_000_000, steps=5, war
     try:
         if dist is None:
             raise _Skip("needs a torch.distributed process group (run with --gpus N >= 2)")
-        fr = dmod.ShardedFrameRenderer(sc["means"], sc["quats"], sc["scales"], sc["opac"], sc["colors"], W, H, cl)
+        fr = dmod.ShardedFrameRenderer(sc["means"], sc["quats"], sc["scales"], sc["opac"], sc["colors"], W, H, cl,
+                                       tight_tiles=True)
         for _ in range(warmup):
             img_f, alpha_f = fr.render(vm[mine], Ks[mine])
         info = fr.check()
@@ -759,7 +760,7 @@ def bench_c5(rs, torch, dist, dev, rank, world, n_total=20_000_000, steps=5, war
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t[0]) / steps
         out["peer_exchange_sync_free"] = {"ms_per_step": round(ms, 3), "camera_frames_per_s": round(n_cams / (ms * 1e-3), 2),
-                                          "host_reads_per_frame": 0, "rows_received_rank0": info["rows"],
+                                          "host_reads_per_frame": 0, "tile_lists": "tight", "rows_received_rank0": info["rows"],
                                           "n_isects_rank0": info["n_isects"], "regrow": info["regrow"],
                                           "image_equal_to_rasterization_route": same}
         del fr

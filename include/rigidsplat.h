@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define RS_ABI_VERSION 17
+#define RS_ABI_VERSION 18
 
 /* gsplat/cuda/include/Common.h:46-51 (CameraModelType) */
 enum { RS_PINHOLE = 0, RS_ORTHO = 1, RS_FISHEYE = 2, RS_FTHETA = 3 };
@@ -324,6 +324,13 @@ typedef struct {
 } rs_isect_sorted_args;
 /* for a caller that fuses the depth statistics into its projection: clear the ordering state of `workspace` (enqueued on
  * `stream`, BEFORE the kernel that accumulates the statistics) / where that kernel has to accumulate them */
+/* Tile counts (isect.tiles_per_gauss) + tile footprints (format of rs_project_fwd_args.tile_footprints) of projected rows
+ * that did not come out of rs_project_fwd -- e.g. the receive arrays of the splat exchange -- in one pass, for
+ * rs_isect_sorted_args.tile_footprints.  conics / opacities ([n_elems,3] / [n_elems], per row) both given: tight lists;
+ * both NULL: every tile of the bounding rectangle, exactly the reference's lists (the emission then needs one 16-byte
+ * record per row instead of radii + means2d + count).  isect.block_sums is not used. */
+int rs_isect_footprints(const rs_isect_args *a, const float *conics, const float *opacities, uint32_t *tile_footprints,
+                        rs_stream_t stream);
 int rs_isect_sorted_prepare(void *workspace, int64_t n_elems, int64_t capacity, rs_stream_t stream);
 uint32_t *rs_isect_sorted_depth_stats(void *workspace, int64_t n_elems, int64_t capacity);
 uint64_t rs_isect_sorted_workspace_bytes(int64_t n_elems, int64_t capacity);

@@ -28,7 +28,7 @@ def test_struct_layouts_match(rs):
         assert lib.rs_sizeof_args(which) == ctypes.sizeof(st), st.__name__
     assert lib.rs_sizeof_args(99) == 0
     header_version = int(re.search(r"#define\s+RS_ABI_VERSION\s+(\d+)", open(_lib.HEADER).read()).group(1))
-    assert lib.rs_abi_version() == header_version >= 17
+    assert lib.rs_abi_version() == header_version >= 18
 
 
 def test_host_only_entry_points(rs):

@@ -259,6 +259,7 @@ def _syncfree_worker(rank, world, port, q):
         shard = [t[k][lo:hi].contiguous() for k in ("means", "quats", "scales", "opacities", "colors")]
         ids = t["cluster_ids"][lo:hi].contiguous()
         fr = rs.ShardedFrameRenderer(*shard, W, H, Cl, cluster_ids=ids, body_centers=t["body_centers"])
+        fr_tight = rs.ShardedFrameRenderer(*shard, W, H, Cl, cluster_ids=ids, body_centers=t["body_centers"], tight_tiles=True)
         for frame in range(4):
             bt = t["body_trans"] + 0.07 * frame
             img, alpha = fr.render(vm[mine], Ks[mine], t["body_quats"], bt)
@@ -271,6 +272,11 @@ def _syncfree_worker(rank, world, port, q):
                                                       body_centers=t["body_centers"])
             assert info["rows"] == meta["gaussian_ids"].numel() and info["n_isects"] == meta["flatten_ids"].numel(), (frame, info)
             assert torch.equal(got_img, want) and torch.equal(got_alpha, want_a), frame
+            # tight tile lists (rs_isect_footprints with conics + opacities): fewer intersections, the same pixels
+            img_t, alpha_t = fr_tight.render(vm[mine], Ks[mine], t["body_quats"], bt)
+            info_t = fr_tight.check()
+            assert not info_t["regrow"] and info_t["rows"] == info["rows"] and info_t["n_isects"] <= info["n_isects"], info_t
+            assert torch.equal(img_t, want) and torch.equal(alpha_t, want_a), frame
         # an intersection workspace that is too small is reported by check() -- on every rank -- and re-sized; the frame
         # rendered again is the right one
         fr._alloc_render(fr._alloc_rows, 1024)
