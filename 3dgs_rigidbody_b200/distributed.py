@@ -398,8 +398,9 @@ class ShardedFrameRenderer:
     all-gathered, every rank projects ITS Gaussians to ALL cameras, the projected splats travel to the rank owning the camera,
     binning and compositing are local -- but every size stays on the device: the packed projection writes into capacity-sized
     row buffers (device-side nnz / indptr), the peer-memory exchange places rows from the device-side count matrix,
-    rs_exchange_seal blanks the unused tail of the receive arrays, and tile binning / compositing run over the whole row
-    capacity with the device-side intersection count (as rs_render_frame does on one GPU).  The reference reads back sizes
+    rs_exchange_seal blanks the unused tail of the receive arrays, and tile binning (rs_isect_footprints: counts + one
+    16-byte tile footprint per received row, so the depth-ordered emission gathers one record per row) / compositing run
+    over the whole row capacity with the device-side intersection count (as rs_render_frame does on one GPU).  The reference reads back sizes
     three times per frame (projection nnz, all-to-all counts, intersection count); here the host reads NOTHING unless
     `check()` is called (one read of six integers: rows received, capacity needed, exchange error, intersections, overflow),
     so the ranks do not drift apart between frames.  Per-Gaussian colours [N, D] (sh_degree=None), no gradients.
