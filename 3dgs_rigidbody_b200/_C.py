@@ -458,8 +458,13 @@ def intersect_tile(
         a.capacity = 0
         n_isects = 0
         s = _stream()
+        footprints = None
         if n_elems > 0:
-            _lib.check(lib.rs_isect_count(ctypes.byref(a), s))
+            if sort:  # counts + one 16-byte tile footprint per row: the depth-ordered emission gathers one record per row
+                footprints = torch.empty((n_elems, 4), dtype=torch.int32, device=dev)
+                _lib.check(lib.rs_isect_footprints(ctypes.byref(a), None, None, footprints.data_ptr(), s))
+            else:
+                _lib.check(lib.rs_isect_count(ctypes.byref(a), s))
             _lib.check(lib.rs_isect_scan(ctypes.byref(a), s))
             out = ctypes.c_int64(0)
             # the one host sync of the compat path (csrc/Intersect.cpp:79-80)
@@ -481,6 +486,7 @@ def intersect_tile(
                 offsets = torch.empty((int(I), int(tile_height), int(tile_width)), dtype=torch.int32, device=dev)
                 sa.tile_offsets = offsets.data_ptr()
                 sa.workspace, sa.workspace_bytes = ws.data_ptr(), ws_bytes
+                sa.tile_footprints = footprints.data_ptr()
                 _lib.check(lib.rs_isect_sorted(ctypes.byref(sa), s))
                 _remember_offsets(isect_ids, offsets, I, tile_width, tile_height)
     return tiles_per_gauss, isect_ids, flatten_ids

@@ -50,7 +50,9 @@ __global__ void __launch_bounds__(RS_ISECT_THREADS)
 rs_isect_footprints_kernel(const rs_isect_args a, const float *__restrict__ conics, const float *__restrict__ opacities,
                            uint4 *__restrict__ footprints) {
     __shared__ RsFootWarp foot[RS_ISECT_THREADS / 32];
+    __shared__ int sums[8];
     const int64_t base = (int64_t)blockIdx.x * RS_ISECT_BLOCK;
+    int mine = 0;
 #pragma unroll 1
     for (int it = 0; it < RS_ISECT_BLOCK / RS_ISECT_THREADS; ++it) { // (uniform trip count: the warp version syncs)
         const int64_t idx = base + it * RS_ISECT_THREADS + threadIdx.x;
@@ -88,7 +90,13 @@ rs_isect_footprints_kernel(const rs_isect_args a, const float *__restrict__ coni
         if (in) {
             a.tiles_per_gauss[idx] = cnt;
             footprints[idx] = fp;
+            mine += cnt;
         }
+    }
+    if (a.block_sums != nullptr) { // optional: the per-block sums rs_isect_scan turns into offsets and the total
+        const int s = rs_block_sum_256(mine, sums);
+        if (threadIdx.x == 0)
+            a.block_sums[blockIdx.x] = s;
     }
 }
 
@@ -385,6 +393,7 @@ extern "C" int rs_isect_footprints(const rs_isect_args *a, const float *conics, 
         return 0;
     RS_CHECK(a->means2d && a->radii && a->tiles_per_gauss && tile_footprints, "rs_isect_footprints: null pointer");
     RS_CHECK((conics == nullptr) == (opacities == nullptr), "rs_isect_footprints: conics and opacities go together");
+    RS_CHECK(a->tile_width < 65536 && a->tile_height < 65536, "rs_isect_footprints: more than 65535 tiles per axis");
     RS_CHECK((reinterpret_cast<uintptr_t>(tile_footprints) & 15) == 0, "rs_isect_footprints: tile_footprints must be 16-byte aligned");
     rs_isect_footprints_kernel<<<rs_isect_num_blocks(a->n_elems), RS_ISECT_THREADS, 0, (cudaStream_t)stream>>>(
         *a, conics, opacities, reinterpret_cast<uint4 *>(tile_footprints));

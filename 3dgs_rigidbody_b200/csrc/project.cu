@@ -590,6 +590,8 @@ static int rs_project_launch(const rs_project_fwd_args *a, PackOut *po, cudaStre
     RS_CHECK(a->tile_footprints == nullptr || (a->tiles_per_gauss != nullptr && a->opacities != nullptr &&
                                                aligned16(a->tile_footprints)),
              "%s: tile_footprints needs tiles_per_gauss, opacities and a 16-byte aligned array", who);
+    RS_CHECK(a->tile_footprints == nullptr || (a->tile_width < 65536 && a->tile_height < 65536),
+             "%s: tile_footprints: more than 65535 tiles per axis", who);
     RS_CHECK(a->depth_stats == nullptr || (a->tiles_per_gauss != nullptr && po == nullptr),
              "%s: depth_stats needs tiles_per_gauss and dense (not packed) rows", who);
     if (a->sh_coeffs != nullptr)

@@ -328,7 +328,8 @@ typedef struct {
  * that did not come out of rs_project_fwd -- e.g. the receive arrays of the splat exchange -- in one pass, for
  * rs_isect_sorted_args.tile_footprints.  conics / opacities ([n_elems,3] / [n_elems], per row) both given: tight lists;
  * both NULL: every tile of the bounding rectangle, exactly the reference's lists (the emission then needs one 16-byte
- * record per row instead of radii + means2d + count).  isect.block_sums is not used. */
+ * record per row instead of radii + means2d + count).  isect.block_sums, when given, receives the per-block sums as from
+ * rs_isect_count (for rs_isect_scan / rs_isect_count_total). */
 int rs_isect_footprints(const rs_isect_args *a, const float *conics, const float *opacities, uint32_t *tile_footprints,
                         rs_stream_t stream);
 int rs_isect_sorted_prepare(void *workspace, int64_t n_elems, int64_t capacity, rs_stream_t stream);
