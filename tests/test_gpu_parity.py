@@ -514,6 +514,48 @@ def test_tight_tile_lists_give_the_same_image(rs, case):
     print(f"{case}: {ref_l[3]} -> {tight_l[3]} intersections ({tight_l[3] / max(ref_l[3], 1):.3f})")
 
 
+def test_tight_tile_lists_drop_only_pairs_no_pixel_can_use(rs):
+    """The direct statement of the culling rule, independent of occlusion: every (tile, splat) pair of the reference's list
+    that the tight list leaves out has alpha < 1/255 at ALL 256 pixel centres of the tile (evaluated here in float64), i.e.
+    RasterizeToPixels3DGSFwd.cu:148-149 would skip it at every pixel."""
+    W, H, C, N = 400, 300, 2, 40_000
+    s = synthetic_scene(33, N, K=4, s_max=0.25, spread=1.3)
+    s["scales"][::2, 1:] *= 0.1  # half of the splats needle-shaped
+    vmn, Ksn = pinhole_cameras(C, W, H)
+    scene = tuple(T(s[k]) for k in ("means", "quats", "scales", "opacities", "colors"))
+    kw = dict(cluster_ids=T(s["cluster_ids"]), body_centers=T(s["body_centers"]), n_cameras=C)
+    lists = {}
+    for tight in (False, True):
+        fr = rs.FrameRenderer(*scene, W, H, tight_tiles=tight, **kw)
+        fr.render(T(vmn), T(Ksn), T(s["body_quats"]), T(s["body_trans"]))
+        torch.cuda.synchronize()
+        m = fr.meta()
+        lists[tight] = ((m["isect_ids"] >> 32).clone(), m["flatten_ids"].long().clone())
+        if not tight:
+            means2d, conics = m["means2d"].reshape(-1, 2).double().clone(), m["conics"].reshape(-1, 3).double().clone()
+            tw, th = m["tile_width"], m["tile_height"]
+        del fr
+    pair = lambda kt: kt[0] * (1 << 31) + kt[1]
+    pr, pt = pair(lists[False]), pair(lists[True])
+    dropped = ~torch.isin(pr, pt)
+    assert int(dropped.sum()) > 1000 and bool(torch.isin(pt, pr).all())
+    tile_bits = int(tw * th).bit_length()  # IntersectTile.cu: floor(log2(n_tiles)) + 1
+    key, row = lists[False][0][dropped], lists[False][1][dropped]
+    tile = key & ((1 << tile_bits) - 1)
+    tx, ty = (tile % tw).double(), torch.div(tile, tw, rounding_mode="floor").double()
+    off = torch.arange(16, device=DEV, dtype=torch.float64) + 0.5
+    px = (tx * 16)[:, None, None] + off[None, None, :]  # [P,1,16]
+    py = (ty * 16)[:, None, None] + off[None, :, None]  # [P,16,1]
+    mu, cn = means2d[row], conics[row]
+    op = scene[3].double()[row % N]
+    dx, dy = mu[:, 0, None, None] - px, mu[:, 1, None, None] - py
+    sigma = 0.5 * (cn[:, 0, None, None] * dx * dx + cn[:, 2, None, None] * dy * dy) + cn[:, 1, None, None] * dx * dy
+    alpha = torch.minimum(torch.full_like(sigma, 0.999), op[:, None, None] * torch.exp(-sigma))
+    alpha = torch.where(sigma < 0, torch.zeros_like(alpha), alpha)
+    worst = float(alpha.reshape(alpha.shape[0], -1).max(dim=1).values.max())
+    assert worst < (1.0 / 255.0) * (1.0 - 5e-4), worst
+
+
 def test_full_size_properties_1m_1080p(rs):
     """BASELINE c2 size (1 M Gaussians, 20 bodies, 1080p): size-independent properties instead of a CPU comparison."""
     import bench
