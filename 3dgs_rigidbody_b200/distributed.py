@@ -390,6 +390,10 @@ class _PeerExchangeFn(torch.autograd.Function):
         return (None,) * 7 + (g_m2, g_d, g_con, g_op, g_col)
 
 
+class PeerRouteUnavailable(RuntimeError):
+    """Raised on EVERY rank alike (the probe is collective) when the ranks cannot map each other's memory."""
+
+
 class ShardedFrameRenderer:
     """One Gaussian-sharded frame (BASELINE config c5) with NO host synchronisation on the way: the distributed counterpart
     of animation.FrameRenderer.
@@ -430,6 +434,10 @@ class ShardedFrameRenderer:
         sizes = torch.empty(self.world, dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(sizes, torch.tensor([self.N], dtype=torch.int64, device=dev), group=group)
         self.gaussian_base = int(sizes[: self.rank].sum().item())
+        if not PeerSplatExchange.usable(group, dev):
+            raise PeerRouteUnavailable("ShardedFrameRenderer needs the peer-memory exchange (all ranks on one host, peer access "
+                                       "between every pair of devices, at most 16 ranks); use rasterization(distributed=True), "
+                                       "which falls back to NCCL")
         self.peer = PeerSplatExchange.get(group, dev, self.D)
         # packed projection: every (camera, Gaussian) pair fits, so the projection can never overflow
         cap_p = max(self.N * self.Ct, 1)

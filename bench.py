@@ -764,7 +764,7 @@ def bench_c5(rs, torch, dist, dev, rank, world, n_total=20_000_000, steps=5, war
                                           "n_isects_rank0": info["n_isects"], "regrow": info["regrow"],
                                           "image_equal_to_rasterization_route": same}
         del fr
-    except _Skip as e:
+    except (_Skip, dmod.PeerRouteUnavailable) as e:  # (the second is raised on every rank alike: nobody is stranded)
         out["peer_exchange_sync_free"] = {"skipped": str(e)}
     except Exception as e:
         out["peer_exchange_sync_free"] = {"error": f"{type(e).__name__}: {e}"[:300]}
